@@ -1,0 +1,172 @@
+/*
+ * simetuc_b200 - C ABI of the B200-native microscopic rate-equation path.
+ *
+ * This is the drop-in boundary: plain C, caller-owned pointers and sizes, no
+ * torch / numpy types.  Every entry point names the reference interface it replaces
+ * (paths relative to /root/reference/simetuc).  The Python host side
+ * (`simetuc_b200/_lib.py`) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - ion types: 0 = sensitizer (S), 1 = activator (A)          (util.py:82-87)
+ *   - state vectors at this boundary use the REFERENCE layout: ion-major, ions in lattice
+ *     order, ion q at y[gs_q .. gs_q + states(type_q))           (lattice.py:259-298)
+ *   - all floating point is IEEE float64; indices as documented per call
+ *   - every function returns 0 on success, a negative STB_E* code on failure; the message is
+ *     available from stb_last_error() (thread-local).  Solver non-convergence is NOT an error
+ *     (odesolver.py:129-134): stb_integrate returns 0 and reports it in stb_stats.status.
+ *   - pointers are HOST pointers unless the parameter is documented "device" and the call has
+ *     the _dev suffix.
+ */
+#ifndef SIMETUC_B200_H
+#define SIMETUC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_OK 0
+#define STB_EINVAL (-1)   /* bad argument (maps to ValueError / lattice.LatticeError) */
+#define STB_ECUDA (-2)    /* CUDA runtime failure */
+#define STB_ENOMEM (-3)
+#define STB_ESTATE (-4)   /* call made in the wrong order (e.g. batch not set) */
+
+#define STB_MAX_STATES 16 /* states per ion type */
+#define STB_MAX_PROC 32   /* pair ET processes */
+
+/* One pair energy-transfer process: util.py:235-292 (EneryTransferProcess).
+ * (ii, fi, if, ff) = process.indices: initial state of donor / partner, final state of
+ * donor / partner.  Rate of one interaction = strength * d^(-mult) * y[donor ii] * y[partner fi]
+ * (precalculate.py:277-294). */
+typedef struct stb_process {
+    int32_t donor_type;
+    int32_t partner_type;
+    int32_t ii, fi, if_, ff;
+    int32_t mult;
+    int32_t reserved;
+    double strength;
+} stb_process;
+
+/* Per-system integration report (replaces the log messages of odesolver.py:129-134). */
+typedef struct stb_stats {
+    int64_t n_steps;        /* accepted BDF steps */
+    int64_t n_rejected;     /* steps rejected by the error test */
+    int64_t n_newton_fail;  /* Newton / Krylov convergence failures (step halved) */
+    int64_t n_rhs;          /* RHS evaluations (pair-stream passes with y) */
+    int64_t n_jv;           /* Jacobian-vector products (pair-stream passes with v) */
+    int64_t n_lin;          /* linear solves */
+    int64_t n_out;          /* output rows written (== n_t on success) */
+    int32_t status;         /* 0 ok, 1 = too many steps (nsteps), 2 = step size underflow,
+                               3 = non-finite values */
+    int32_t last_order;
+    double t_reached;
+    double last_h;
+} stb_stats;
+
+typedef struct stb_system stb_system; /* opaque: one doped lattice resident on one GPU */
+
+const char* stb_last_error(void);
+int stb_device_count(void);
+/* Library / kernel configuration summary (arch, launch shapes) written into buf. */
+int stb_describe(char* buf, int64_t buf_len);
+
+/* ---- ET coupling build -------------------------------------------------------------------
+ * Replaces lattice.create_ground_states (lattice.py:259-298), create_interaction_matrices
+ * (lattice.py:301-374) and the pair part of precalculate._create_ET_matrices
+ * (precalculate.py:235-415): from the ion table and geometry it builds, on the device, the
+ * ion-owned pair lists (partner index + d^-mult, sliced-ELL) that RHS / Jv / integrator stream.
+ *
+ * Geometry: pass EITHER dist_array (n_ions x n_ions, row-major, 0 on the diagonal; the
+ * reference's shared lattice input) OR positions (n_ions x 3, Angstrom) with cell (3x3 row
+ * vectors of the periodic supercell, NULL = open boundaries).  d_max <= 0 pairs every ion with
+ * every other ion of non-zero distance (the reference's behaviour: lattice.py:335); d_max > 0
+ * applies the cutoff the reference parses but never uses (settings.py:35).
+ * Processes with strength 0 may be listed (they are skipped exactly like
+ * precalculate.py:353-354 until stb_set_strengths makes them non-zero). */
+stb_system* stb_system_create(int32_t device, int64_t n_ions, const uint8_t* ion_type,
+                              int32_t n_S_states, int32_t n_A_states,
+                              const double* dist_array, const double* positions,
+                              const double* cell, double d_max,
+                              int32_t n_proc, const stb_process* procs);
+void stb_system_destroy(stb_system* sys);
+
+/* Sizes: out[0]=n_ions, [1]=n_S, [2]=n_A, [3]=N (states), [4]=P (stored ordered pairs),
+ * [5]=bytes of pair data streamed per RHS pass, [6]=padded pair slots. */
+int stb_system_info(const stb_system* sys, int64_t out[8]);
+
+/* index_S_i / index_A_j (int64[n_ions], -1 = other type) and initial_population
+ * (uint64[N]) exactly as lattice.create_ground_states returns them. */
+int stb_ground_states(const stb_system* sys, int64_t* index_S_i, int64_t* index_A_j,
+                      uint64_t* initial_population);
+
+/* ---- parameter batch ----------------------------------------------------------------------
+ * n_sys ODE systems share the lattice; they differ in their per-type linear blocks
+ * (absorption scales with power: precalculate.py:99-120) and ET strengths (optimiser
+ * candidates: optimize.py:84-85).  New systems start with zero blocks and the strengths given
+ * at creation. */
+int stb_set_batch(stb_system* sys, int32_t n_sys);
+/* which: 0 = decay block (precalculate.py:184-213), 1 = absorption block
+ * (precalculate.py:96-120, already multiplied by power_dens).  blk_S is sS x sS row-major,
+ * blk_A is sA x sA (either may be NULL when that type has no states).  system = -1: all. */
+int stb_set_blocks(stb_system* sys, int32_t system, int32_t which, const double* blk_S,
+                   const double* blk_A);
+int stb_set_strengths(stb_system* sys, int32_t system, const double* strengths /*[n_proc]*/);
+
+/* ---- reference-layout view of the pair ET operator ------------------------------------------
+ * Number M of interactions of `system` in the reference's sense (precalculate.py:296,858). */
+int64_t stb_num_interactions(const stb_system* sys, int32_t system);
+/* The interaction list in the reference's exact order (precalculate.py:349-392):
+ *   N_indices   uint32[M,2]  (precalculate.py:293-294,413)
+ *   et_rows     int32[M,4]   rows of the 4 entries of ET column r: donor ii, donor if,
+ *                            partner fi, partner ff (precalculate.py:277-283)
+ *   et_w        double[M]    w_r = strength * d^-mult; column r holds (-w,+w,-w,+w) (:289-291)
+ *   jac_indices uint32[2M,3] (precalculate.py:603-623)
+ * Any output pointer may be NULL. */
+int stb_export_interactions(const stb_system* sys, int32_t system, uint32_t* N_indices,
+                            int32_t* et_rows, double* et_w, uint32_t* jac_indices);
+
+/* ---- RHS and Jacobian-vector product ----------------------------------------------------------
+ * stb_rhs: odesolver._rate_eq (pulse=0, odesolver.py:33-43) / _rate_eq_pulse (pulse=1, :65-71)
+ * for systems [first, first+n): y, dy are [n, N] in reference layout.
+ * stb_jv:  (_jac_rate_eq[_pulse](y) @ v) without forming the dense Jacobian
+ * (odesolver.py:46-62, 74-80). */
+int stb_rhs(stb_system* sys, int32_t first, int32_t n, int32_t pulse, const double* y,
+            double* dy);
+int stb_jv(stb_system* sys, int32_t first, int32_t n, int32_t pulse, const double* y,
+           const double* v, double* jv);
+/* Same with DEVICE pointers in the library's internal plane layout (see stb_to_planes):
+ * used by bench.py to time the kernels with operands resident in HBM.  Runs `repeat` launches
+ * back to back on the library stream and returns the mean kernel time in ms (CUDA events). */
+int stb_rhs_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, const double* y_planes,
+                double* dy_planes, int32_t repeat, float* ms_per_launch);
+int stb_jv_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, const double* y_planes,
+               const double* v_planes, double* jv_planes, int32_t repeat, float* ms_per_launch);
+/* Reference layout (host) -> internal plane layout (device buffer owned by the caller,
+ * n*N doubles) and back. */
+int stb_to_planes(const stb_system* sys, int32_t n, const double* y_host, double* y_planes_dev);
+int stb_from_planes(const stb_system* sys, int32_t n, const double* y_planes_dev, double* y_host);
+
+/* ---- stiff integrator ------------------------------------------------------------------------
+ * Replaces odesolver._solve_ode / solve_pulse / solve_relax (odesolver.py:85-209) and scipy's
+ * VODE/LSODA: variable-order (1-5) BDF, Jacobian-free Newton-Krylov (GMRES) with a per-ion
+ * block-Jacobi preconditioner, entirely on the device.
+ *   t        double[n_t]           output times, t[0] = start (shared by the batch)
+ *   y0       double[n, N]          initial populations (reference layout)
+ *   y_out    double[n, n_t, N]     row 0 = y0 verbatim (odesolver.py:107); may be NULL
+ *   avg_out  double[n, n_t, sS+sA] per-state ion averages clipped at 0
+ *                                  (simulations.py:100-128); may be NULL
+ *   nsteps   max internal steps between two output times (odesolver.py:89,101)
+ * Rows not reached stay zero, as in the reference (odesolver.py:97). */
+int stb_integrate(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                  const double* t, const double* y0, double rtol, double atol, int64_t nsteps,
+                  double* y_out, double* avg_out, stb_stats* stats /*[n]*/);
+/* Device time (ms, CUDA events) of the last stb_integrate call's kernels, and the number of
+ * kernel launches it made. */
+int stb_last_timing(const stb_system* sys, float* ms, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIMETUC_B200_H */

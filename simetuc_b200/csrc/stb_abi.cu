@@ -1,0 +1,840 @@
+// simetuc_b200 - C ABI implementation (host side) for include/simetuc_b200.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "stb_build.cuh"
+#include "stb_integrate.cuh"
+#include "stb_kernels.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return STB_ECUDA;                                                         \
+        }                                                                             \
+    } while (0)
+
+#define CKP(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return nullptr;                                                           \
+        }                                                                             \
+    } while (0)
+
+struct stb_system {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n_ions = 0;
+    int n[2] = {0, 0}, s[2] = {0, 0}, N = 0;
+    int n_proc = 0;
+    std::vector<stb_process> procs;
+    std::vector<uint8_t> type;
+    std::vector<int> local_idx, gs_ref, plane_of_ref, ref_of_plane;
+    std::vector<int> gs_of_local[2];
+    std::vector<int> len;  // [2][n]
+    DevLattice hL;         // host copy (device pointers inside)
+    DevLattice* dL = nullptr;
+    // device buffers
+    uint8_t* d_type = nullptr;
+    int *d_local_idx = nullptr, *d_gs_ref = nullptr, *d_plane_of_ref = nullptr,
+        *d_ref_of_plane = nullptr, *d_len = nullptr;
+    int* d_gs_of_local[2] = {nullptr, nullptr};
+    uint32_t* d_col[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    double* d_g[2][2][STB_MAXM] = {};
+    int64_t* d_line_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int64_t pairs = 0, slots = 0, stream_bytes = 0;
+    // batch
+    int n_sys = 0;
+    std::vector<double> h_blocks, h_strengths;
+    double *d_blocks = nullptr, *d_strengths = nullptr;
+    bool params_dirty = true;
+    // scratch for rhs/jv
+    double *d_y = nullptr, *d_v = nullptr, *d_out = nullptr, *d_F = nullptr, *d_tmp = nullptr;
+    int64_t scratch_n = 0;
+    float last_ms = 0.f;
+    int64_t last_launches = 0;
+    int sm_count = 148;
+};
+
+extern "C" const char* stb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int stb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int stb_describe(char* buf, int64_t buf_len) {
+    snprintf(buf, (size_t)buf_len,
+             "simetuc_b200 sm_100a; integrator: persistent cooperative kernel, %d threads/CTA, "
+             "GMRES(%d), BDF order<=%d; pair stream: sliced-ELL u32+f64",
+             STB_NT, STB_KRYLOV, STB_MAXORD);
+    return STB_OK;
+}
+
+template <class T>
+static cudaError_t upload(T** dst, const std::vector<T>& v) {
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc((void**)dst, bytes);
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return e;
+}
+
+static bool invert3(const double* m, double* inv) {
+    double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                 m[2] * (m[3] * m[7] - m[4] * m[6]);
+    if (det == 0.0) return false;
+    double id = 1.0 / det;
+    inv[0] = (m[4] * m[8] - m[5] * m[7]) * id;
+    inv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+    inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    inv[3] = (m[5] * m[6] - m[3] * m[8]) * id;
+    inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+    inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    inv[6] = (m[3] * m[7] - m[4] * m[6]) * id;
+    inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+    inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return true;
+}
+
+extern "C" void stb_system_destroy(stb_system* S) {
+    if (!S) return;
+    cudaSetDevice(S->device);
+    cudaFree(S->dL);
+    cudaFree(S->d_type);
+    cudaFree(S->d_local_idx);
+    cudaFree(S->d_gs_ref);
+    cudaFree(S->d_plane_of_ref);
+    cudaFree(S->d_ref_of_plane);
+    cudaFree(S->d_len);
+    for (int T = 0; T < 2; ++T) {
+        cudaFree(S->d_gs_of_local[T]);
+        for (int U = 0; U < 2; ++U) {
+            cudaFree(S->d_col[T][U]);
+            cudaFree(S->d_line_ptr[T][U]);
+            for (int m = 0; m < STB_MAXM; ++m) cudaFree(S->d_g[T][U][m]);
+        }
+    }
+    cudaFree(S->d_blocks);
+    cudaFree(S->d_strengths);
+    cudaFree(S->d_y);
+    cudaFree(S->d_v);
+    cudaFree(S->d_out);
+    cudaFree(S->d_F);
+    cudaFree(S->d_tmp);
+    if (S->stream) cudaStreamDestroy(S->stream);
+    delete S;
+}
+
+// Field slots and rate terms of the process table (see stb_fields.cuh).
+static int build_tables(stb_system* S, DevLattice& L) {
+    // distinct multipolarities
+    L.n_mult = 0;
+    for (auto& p : S->procs) {
+        bool seen = false;
+        for (int m = 0; m < L.n_mult; ++m) seen |= L.mults[m] == p.mult;
+        if (!seen) {
+            if (L.n_mult == STB_MAXM) return fail(STB_EINVAL, "more than 3 distinct multipolarities");
+            L.mults[L.n_mult++] = p.mult;
+        }
+    }
+    if (L.n_mult == 0) { L.n_mult = 1; L.mults[0] = 6; }
+    auto mult_index = [&](int mult) {
+        for (int m = 0; m < L.n_mult; ++m) if (L.mults[m] == mult) return m;
+        return 0;
+    };
+    for (int T = 0; T < 2; ++T) {
+        for (int U = 0; U < 2; ++U) L.blk[T][U].n_slots = 0;
+        L.terms[T].n_terms = 0;
+    }
+    auto slot_of = [&](int T, int U, int col, int mi) -> int {
+        PairBlock& B = L.blk[T][U];
+        for (int k = 0; k < B.n_slots; ++k)
+            if (B.slot_col[k] == col && B.slot_mult[k] == mi) return k;
+        if (B.n_slots == STB_MAXC) return -1;
+        B.slot_col[B.n_slots] = col;
+        B.slot_mult[B.n_slots] = mi;
+        return B.n_slots++;
+    };
+    struct Raw { int T, U, slot, a, b, proc; };
+    std::vector<Raw> raw;
+    for (int p = 0; p < S->n_proc; ++p) {
+        const stb_process& pr = S->procs[p];
+        int dt = pr.donor_type, pt = pr.partner_type, mi = mult_index(pr.mult);
+        if (S->s[dt] == 0 || S->s[pt] == 0) continue;
+        // donor term on rows of type dt: field over partners pt, column fi
+        int k1 = slot_of(dt, pt, pr.fi, mi);
+        // acceptor term on rows of type pt: field over donors dt, column ii
+        int k2 = slot_of(pt, dt, pr.ii, mi);
+        if (k1 < 0 || k2 < 0) return fail(STB_EINVAL, "too many distinct field slots");
+        raw.push_back({dt, pt, k1, pr.ii, pr.if_, p});
+        raw.push_back({pt, dt, k2, pr.fi, pr.ff, p});
+    }
+    for (int T = 0; T < 2; ++T) {
+        L.nf[T] = L.blk[T][0].n_slots + L.blk[T][1].n_slots;
+    }
+    for (auto& r : raw) {
+        TermTable& tt = L.terms[r.T];
+        if (tt.n_terms == STB_MAXT) return fail(STB_EINVAL, "too many ET terms");
+        int k = tt.n_terms++;
+        tt.fslot[k] = (short)(r.U == 0 ? r.slot : L.blk[r.T][0].n_slots + r.slot);
+        tt.a[k] = (short)r.a;
+        tt.b[k] = (short)r.b;
+        tt.proc[k] = (short)r.proc;
+    }
+    L.foff[0] = 0;
+    L.foff[1] = L.nf[0] * L.n[0];
+    L.NF = L.nf[0] * L.n[0] + L.nf[1] * L.n[1];
+    return STB_OK;
+}
+
+extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const uint8_t* ion_type,
+                                         int32_t n_S_states, int32_t n_A_states,
+                                         const double* dist_array, const double* positions,
+                                         const double* cell, double d_max, int32_t n_proc,
+                                         const stb_process* procs) {
+    if (n_ions <= 0 || !ion_type) { fail(STB_EINVAL, "empty ion table"); return nullptr; }
+    if ((dist_array == nullptr) == (positions == nullptr)) {
+        fail(STB_EINVAL, "pass exactly one of dist_array / positions");
+        return nullptr;
+    }
+    if (n_S_states < 0 || n_A_states < 0 || n_S_states > STB_MAX_STATES ||
+        n_A_states > STB_MAX_STATES) {
+        fail(STB_EINVAL, "states per ion must be in [0, 16]");
+        return nullptr;
+    }
+    if (n_proc < 0 || n_proc > STB_MAX_PROC) { fail(STB_EINVAL, "too many processes"); return nullptr; }
+    if (n_ions > 2000000) { fail(STB_EINVAL, "too many ions"); return nullptr; }
+    CKP(cudaSetDevice(device));
+    stb_system* S = new stb_system();
+    S->device = device;
+    S->n_ions = n_ions;
+    S->s[0] = n_S_states;
+    S->s[1] = n_A_states;
+    S->n_proc = n_proc;
+    S->procs.assign(procs, procs + n_proc);
+    for (auto& p : S->procs) {
+        int sd = S->s[p.donor_type & 1], sp = S->s[p.partner_type & 1];
+        bool bad = p.donor_type < 0 || p.donor_type > 1 || p.partner_type < 0 || p.partner_type > 1 ||
+                   p.ii < 0 || p.if_ < 0 || p.fi < 0 || p.ff < 0 || p.mult <= 0;
+        // a process naming a state that does not exist is an error when it is active
+        // (precalculate.py:325-345 raises LatticeError)
+        if (!bad && stb_active_strength(p.strength) && sd > 0 && sp > 0)
+            bad = p.ii >= sd || p.if_ >= sd || p.fi >= sp || p.ff >= sp;
+        if (bad) {
+            fail(STB_EINVAL, "The number of A or S states is lower than required by a process.");
+            delete S;
+            return nullptr;
+        }
+    }
+    cudaDeviceProp prop;
+    CKP(cudaGetDeviceProperties(&prop, device));
+    S->sm_count = prop.multiProcessorCount;
+    CKP(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+
+    // ---- ion table: type-local indices, ground states, layout maps (lattice.py:259-298) -------
+    const int n = (int)n_ions;
+    S->type.assign(ion_type, ion_type + n);
+    S->local_idx.resize(n);
+    S->gs_ref.resize(n);
+    int cnt[2] = {0, 0}, gs = 0;
+    for (int q = 0; q < n; ++q) {
+        int T = S->type[q] != 0;
+        S->type[q] = (uint8_t)T;
+        S->local_idx[q] = cnt[T]++;
+        S->gs_ref[q] = gs;
+        S->gs_of_local[T].push_back(gs);
+        gs += S->s[T];
+    }
+    S->n[0] = cnt[0];
+    S->n[1] = cnt[1];
+    S->N = gs;
+    if (S->N == 0) { fail(STB_EINVAL, "No states: the number of energy states is zero."); delete S; return nullptr; }
+    DevLattice& L = S->hL;
+    memset(&L, 0, sizeof(L));
+    L.n_ions = n;
+    L.N = S->N;
+    for (int T = 0; T < 2; ++T) { L.n[T] = S->n[T]; L.s[T] = S->s[T]; }
+    L.off[0] = 0;
+    L.off[1] = S->s[0] * S->n[0];
+    L.n_proc = n_proc;
+    S->plane_of_ref.resize(S->N);
+    S->ref_of_plane.resize(S->N);
+    for (int q = 0; q < n; ++q) {
+        int T = S->type[q];
+        for (int a = 0; a < S->s[T]; ++a) {
+            int pl = L.off[T] + a * S->n[T] + S->local_idx[q];
+            S->plane_of_ref[S->gs_ref[q] + a] = pl;
+            S->ref_of_plane[pl] = S->gs_ref[q] + a;
+        }
+    }
+    if (build_tables(S, L) != STB_OK) { delete S; return nullptr; }
+
+    CKP(upload(&S->d_type, S->type));
+    CKP(upload(&S->d_local_idx, S->local_idx));
+    CKP(upload(&S->d_gs_ref, S->gs_ref));
+    CKP(upload(&S->d_plane_of_ref, S->plane_of_ref));
+    CKP(upload(&S->d_ref_of_plane, S->ref_of_plane));
+    for (int T = 0; T < 2; ++T) CKP(upload(&S->d_gs_of_local[T], S->gs_of_local[T]));
+    L.plane_of_ref = S->d_plane_of_ref;
+    L.ref_of_plane = S->d_ref_of_plane;
+
+    // ---- geometry ------------------------------------------------------------------------------
+    Geo G;
+    memset(&G, 0, sizeof(G));
+    G.n = n;
+    G.d_max = d_max;
+    double* d_geo = nullptr;
+    if (dist_array) {
+        CKP(cudaMalloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
+        CKP(cudaMemcpy(d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+        G.dist = d_geo;
+    } else {
+        CKP(cudaMalloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
+        CKP(cudaMemcpy(d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
+        G.pos = d_geo;
+        if (cell) {
+            G.periodic = 1;
+            memcpy(G.cell, cell, sizeof(double) * 9);
+            if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); cudaFree(d_geo); delete S; return nullptr; }
+        }
+    }
+    // ---- pass 1: row lengths ---------------------------------------------------------------------
+    CKP(cudaMalloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
+    int blocks = std::min((n + 7) / 8, S->sm_count * 8);
+    k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
+    CKP(cudaGetLastError());
+    S->len.resize(2 * (size_t)n);
+    CKP(cudaMemcpyAsync(S->len.data(), S->d_len, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, S->stream));
+    CKP(cudaStreamSynchronize(S->stream));
+    // lanes per row from the mean row length (about 16 entries per lane)
+    double mean_len = 0;
+    for (int q = 0; q < n; ++q) mean_len += S->len[q] + S->len[n + q];
+    mean_len /= n;
+    int lpr = 1;
+    while (lpr < 32 && lpr * 16 < mean_len) lpr *= 2;
+    L.lpr = lpr;
+    L.R = 32 / lpr;
+    for (int T = 0; T < 2; ++T) L.n_slices[T] = (S->n[T] + L.R - 1) / L.R;
+    // ---- slice line pointers ---------------------------------------------------------------------
+    std::vector<int> ion_of_local[2];
+    for (int T = 0; T < 2; ++T) ion_of_local[T].resize(S->n[T]);
+    for (int q = 0; q < n; ++q) ion_of_local[S->type[q]][S->local_idx[q]] = q;
+    S->pairs = 0;
+    S->slots = 0;
+    for (int T = 0; T < 2; ++T)
+        for (int U = 0; U < 2; ++U) {
+            std::vector<int64_t> lp(L.n_slices[T] + 1, 0);
+            bool used = L.blk[T][U].n_slots > 0;
+            for (int sl = 0; sl < L.n_slices[T]; ++sl) {
+                int w = 0;
+                for (int r = 0; r < L.R; ++r) {
+                    int ql = sl * L.R + r;
+                    if (ql >= S->n[T]) break;
+                    int ln = S->len[(size_t)U * n + ion_of_local[T][ql]];
+                    w = std::max(w, (ln + lpr - 1) / lpr);
+                    if (used) S->pairs += ln;
+                }
+                lp[sl + 1] = lp[sl] + (used ? w : 0);
+            }
+            int64_t lines = lp.back();
+            CKP(upload(&S->d_line_ptr[T][U], lp));
+            size_t slots = std::max<int64_t>(lines * 32, 1);
+            CKP(cudaMalloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
+            CKP(cudaMemsetAsync(S->d_col[T][U], 0, slots * sizeof(uint32_t), S->stream));
+            for (int m = 0; m < L.n_mult; ++m) {
+                CKP(cudaMalloc((void**)&S->d_g[T][U][m], slots * sizeof(double)));
+                CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, slots * sizeof(double), S->stream));
+            }
+            S->slots += lines * 32;
+            L.blk[T][U].col = S->d_col[T][U];
+            for (int m = 0; m < L.n_mult; ++m) L.blk[T][U].g[m] = S->d_g[T][U][m];
+            L.blk[T][U].line_ptr = S->d_line_ptr[T][U];
+        }
+    S->stream_bytes = S->slots * (4 + 8 * (int64_t)L.n_mult);
+    // ---- pass 2: fill ----------------------------------------------------------------------------
+    FillArgs FA;
+    memset(&FA, 0, sizeof(FA));
+    FA.G = G;
+    FA.type = S->d_type;
+    FA.local_idx = S->d_local_idx;
+    FA.lpr = L.lpr;
+    FA.R = L.R;
+    FA.n_mult = L.n_mult;
+    for (int m = 0; m < L.n_mult; ++m) FA.mults[m] = L.mults[m];
+    for (int T = 0; T < 2; ++T)
+        for (int U = 0; U < 2; ++U) {
+            FA.col[T][U] = S->d_col[T][U];
+            FA.line_ptr[T][U] = S->d_line_ptr[T][U];
+            for (int m = 0; m < L.n_mult; ++m) FA.g[T][U][m] = S->d_g[T][U][m];
+        }
+    // blocks whose fields are never used hold no lines: skip them in the fill through a
+    // zero-width slice (pos / lpr stays inside the slice only when lines exist), so make the
+    // kernel ignore them explicitly
+    for (int T = 0; T < 2; ++T)
+        for (int U = 0; U < 2; ++U)
+            if (L.blk[T][U].n_slots == 0) FA.col[T][U] = nullptr;
+    k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
+    CKP(cudaGetLastError());
+    CKP(cudaStreamSynchronize(S->stream));
+    cudaFree(d_geo);
+    L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
+    CKP(cudaMalloc((void**)&S->dL, sizeof(DevLattice)));
+    CKP(cudaMemcpy(S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
+    if (stb_set_batch(S, 1) != STB_OK) { stb_system_destroy(S); return nullptr; }
+    return S;
+}
+
+extern "C" int stb_system_info(const stb_system* S, int64_t out[8]) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    out[0] = S->n_ions;
+    out[1] = S->n[0];
+    out[2] = S->n[1];
+    out[3] = S->N;
+    out[4] = S->pairs;
+    out[5] = S->stream_bytes;
+    out[6] = S->slots;
+    out[7] = S->hL.lpr;
+    return STB_OK;
+}
+
+extern "C" int stb_ground_states(const stb_system* S, int64_t* index_S_i, int64_t* index_A_j,
+                                 uint64_t* initial_population) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    if (initial_population) memset(initial_population, 0, sizeof(uint64_t) * S->N);
+    for (int q = 0; q < S->n_ions; ++q) {
+        int T = S->type[q];
+        bool has = S->s[T] != 0;
+        if (index_S_i) index_S_i[q] = (T == 0 && has) ? S->gs_ref[q] : -1;
+        if (index_A_j) index_A_j[q] = (T == 1 && has) ? S->gs_ref[q] : -1;
+        if (initial_population && has) initial_population[S->gs_ref[q]] = 1;
+    }
+    return STB_OK;
+}
+
+extern "C" int stb_set_batch(stb_system* S, int32_t n_sys) {
+    if (!S || n_sys <= 0) return fail(STB_EINVAL, "n_sys must be positive");
+    CK(cudaSetDevice(S->device));
+    int per = S->hL.blk_stride;
+    S->n_sys = n_sys;
+    S->h_blocks.assign((size_t)n_sys * std::max(per, 1), 0.0);
+    S->h_strengths.resize((size_t)n_sys * std::max(S->n_proc, 1));
+    for (int b = 0; b < n_sys; ++b)
+        for (int p = 0; p < S->n_proc; ++p) S->h_strengths[(size_t)b * S->n_proc + p] = S->procs[p].strength;
+    cudaFree(S->d_blocks);
+    cudaFree(S->d_strengths);
+    S->d_blocks = S->d_strengths = nullptr;
+    CK(cudaMalloc((void**)&S->d_blocks, sizeof(double) * S->h_blocks.size()));
+    CK(cudaMalloc((void**)&S->d_strengths, sizeof(double) * S->h_strengths.size()));
+    S->params_dirty = true;
+    return STB_OK;
+}
+
+extern "C" int stb_set_blocks(stb_system* S, int32_t system, int32_t which, const double* blk_S,
+                              const double* blk_A) {
+    if (!S || which < 0 || which > 1 || system >= S->n_sys) return fail(STB_EINVAL, "bad arguments");
+    int sS2 = S->s[0] * S->s[0], sA2 = S->s[1] * S->s[1], per = sS2 + sA2;
+    for (int b = (system < 0 ? 0 : system); b < (system < 0 ? S->n_sys : system + 1); ++b) {
+        double* dst = S->h_blocks.data() + (size_t)b * 2 * per + (size_t)which * per;
+        if (blk_S && sS2) memcpy(dst, blk_S, sizeof(double) * sS2);
+        if (blk_A && sA2) memcpy(dst + sS2, blk_A, sizeof(double) * sA2);
+    }
+    S->params_dirty = true;
+    return STB_OK;
+}
+
+extern "C" int stb_set_strengths(stb_system* S, int32_t system, const double* strengths) {
+    if (!S || !strengths || system >= S->n_sys) return fail(STB_EINVAL, "bad arguments");
+    for (int p = 0; p < S->n_proc; ++p) {
+        const stb_process& pr = S->procs[p];
+        if (stb_active_strength(strengths[p]) && S->s[pr.donor_type] > 0 && S->s[pr.partner_type] > 0 &&
+            (pr.ii >= S->s[pr.donor_type] || pr.if_ >= S->s[pr.donor_type] ||
+             pr.fi >= S->s[pr.partner_type] || pr.ff >= S->s[pr.partner_type]))
+            return fail(STB_EINVAL, "The number of A or S states is lower than required by a process.");
+    }
+    for (int b = (system < 0 ? 0 : system); b < (system < 0 ? S->n_sys : system + 1); ++b)
+        memcpy(S->h_strengths.data() + (size_t)b * S->n_proc, strengths, sizeof(double) * S->n_proc);
+    S->params_dirty = true;
+    return STB_OK;
+}
+
+static int sync_params(stb_system* S) {
+    if (!S->params_dirty) return STB_OK;
+    CK(cudaMemcpyAsync(S->d_blocks, S->h_blocks.data(), sizeof(double) * S->h_blocks.size(),
+                       cudaMemcpyHostToDevice, S->stream));
+    CK(cudaMemcpyAsync(S->d_strengths, S->h_strengths.data(), sizeof(double) * S->h_strengths.size(),
+                       cudaMemcpyHostToDevice, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    S->params_dirty = false;
+    return STB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t stb_num_interactions(const stb_system* S, int32_t system) {
+    if (!S || system < 0 || system >= S->n_sys) { fail(STB_EINVAL, "bad system"); return -1; }
+    const int n = (int)S->n_ions;
+    if (S->N <= 2) return 0;  // precalculate.py:304
+    int np[2][2] = {{0, 0}, {0, 0}};
+    for (int p = 0; p < S->n_proc; ++p)
+        if (stb_active_strength(S->h_strengths[(size_t)system * S->n_proc + p]))
+            np[S->procs[p].donor_type][S->procs[p].partner_type]++;
+    int64_t M = 0;
+    for (int q = 0; q < n; ++q) {
+        int T = S->type[q];
+        if (S->s[T] == 0) continue;
+        for (int U = 0; U < 2; ++U)
+            if (S->s[U]) M += (int64_t)np[T][U] * S->len[(size_t)U * n + q];
+    }
+    return M;
+}
+
+extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint32_t* N_indices,
+                                       int32_t* et_rows, double* et_w, uint32_t* jac_indices) {
+    int64_t M = stb_num_interactions(S, system);
+    if (M < 0) return STB_EINVAL;
+    if (M == 0) return STB_OK;
+    CK(cudaSetDevice(S->device));
+    const int n = (int)S->n_ions;
+    std::vector<stb_process> pr = S->procs;
+    int np[2][2] = {{0, 0}, {0, 0}};
+    for (int p = 0; p < S->n_proc; ++p) {
+        pr[p].strength = S->h_strengths[(size_t)system * S->n_proc + p];
+        if (stb_active_strength(pr[p].strength)) np[pr[p].donor_type][pr[p].partner_type]++;
+    }
+    std::vector<int64_t> off(n);
+    int64_t run = 0;
+    for (int q = 0; q < n; ++q) {
+        off[q] = run;
+        int T = S->type[q];
+        if (S->s[T] == 0) continue;
+        for (int U = 0; U < 2; ++U)
+            if (S->s[U]) run += (int64_t)np[T][U] * S->len[(size_t)U * n + q];
+    }
+    ExportArgs EA;
+    memset(&EA, 0, sizeof(EA));
+    int64_t* d_off = nullptr;
+    stb_process* d_pr = nullptr;
+    CK(upload(&d_off, off));
+    CK(upload(&d_pr, pr));
+    EA.L = S->dL;
+    EA.type = S->d_type;
+    EA.local_idx = S->d_local_idx;
+    EA.gs_ref = S->d_gs_ref;
+    EA.gs_of_local[0] = S->d_gs_of_local[0];
+    EA.gs_of_local[1] = S->d_gs_of_local[1];
+    EA.len = S->d_len;
+    EA.offset = d_off;
+    EA.procs = d_pr;
+    EA.n_proc = S->n_proc;
+    EA.n = n;
+    if (N_indices) CK(cudaMalloc((void**)&EA.N_indices, sizeof(uint32_t) * 2 * M));
+    if (et_rows) CK(cudaMalloc((void**)&EA.et_rows, sizeof(int32_t) * 4 * M));
+    if (et_w) CK(cudaMalloc((void**)&EA.et_w, sizeof(double) * M));
+    if (jac_indices) CK(cudaMalloc((void**)&EA.jac, sizeof(uint32_t) * 6 * M));
+    int blocks = std::min((n + 7) / 8, S->sm_count * 8);
+    k_export<<<blocks, 256, 0, S->stream>>>(EA);
+    CK(cudaGetLastError());
+    if (N_indices) CK(cudaMemcpyAsync(N_indices, EA.N_indices, sizeof(uint32_t) * 2 * M, cudaMemcpyDeviceToHost, S->stream));
+    if (et_rows) CK(cudaMemcpyAsync(et_rows, EA.et_rows, sizeof(int32_t) * 4 * M, cudaMemcpyDeviceToHost, S->stream));
+    if (et_w) CK(cudaMemcpyAsync(et_w, EA.et_w, sizeof(double) * M, cudaMemcpyDeviceToHost, S->stream));
+    if (jac_indices) CK(cudaMemcpyAsync(jac_indices, EA.jac, sizeof(uint32_t) * 6 * M, cudaMemcpyDeviceToHost, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    cudaFree(EA.N_indices);
+    cudaFree(EA.et_rows);
+    cudaFree(EA.et_w);
+    cudaFree(EA.jac);
+    cudaFree(d_off);
+    cudaFree(d_pr);
+    return STB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int ensure_scratch(stb_system* S, int n) {
+    if (S->scratch_n >= n) return STB_OK;
+    cudaFree(S->d_y); cudaFree(S->d_v); cudaFree(S->d_out); cudaFree(S->d_F); cudaFree(S->d_tmp);
+    S->d_y = S->d_v = S->d_out = S->d_F = S->d_tmp = nullptr;
+    size_t bytes = sizeof(double) * (size_t)n * S->N;
+    CK(cudaMalloc((void**)&S->d_y, bytes));
+    CK(cudaMalloc((void**)&S->d_v, bytes));
+    CK(cudaMalloc((void**)&S->d_out, bytes));
+    CK(cudaMalloc((void**)&S->d_tmp, bytes));
+    CK(cudaMalloc((void**)&S->d_F, sizeof(double) * (size_t)n * std::max(S->hL.NF, 1)));
+    S->scratch_n = n;
+    return STB_OK;
+}
+
+static dim3 op_grid(const stb_system* S, int n) {
+    int total = S->hL.n_slices[0] + S->hL.n_slices[1];
+    int bx = std::max(1, std::min((total + STB_NW - 1) / STB_NW, S->sm_count * 4));
+    return dim3(bx, n, 1);
+}
+
+static int check_range(const stb_system* S, int first, int n) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    if (first < 0 || n <= 0 || first + n > S->n_sys) return fail(STB_EINVAL, "system range outside the batch");
+    return STB_OK;
+}
+
+extern "C" int stb_to_planes(const stb_system* S, int32_t n, const double* y_host, double* y_planes_dev) {
+    if (!S || n <= 0) return fail(STB_EINVAL, "bad arguments");
+    CK(cudaSetDevice(S->device));
+    double* tmp = nullptr;
+    size_t bytes = sizeof(double) * (size_t)n * S->N;
+    CK(cudaMalloc((void**)&tmp, bytes));
+    CK(cudaMemcpyAsync(tmp, y_host, bytes, cudaMemcpyHostToDevice, S->stream));
+    int64_t tot = (int64_t)n * S->N;
+    k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, tmp, y_planes_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(S->stream));
+    cudaFree(tmp);
+    return STB_OK;
+}
+
+extern "C" int stb_from_planes(const stb_system* S, int32_t n, const double* y_planes_dev, double* y_host) {
+    if (!S || n <= 0) return fail(STB_EINVAL, "bad arguments");
+    CK(cudaSetDevice(S->device));
+    double* tmp = nullptr;
+    size_t bytes = sizeof(double) * (size_t)n * S->N;
+    CK(cudaMalloc((void**)&tmp, bytes));
+    int64_t tot = (int64_t)n * S->N;
+    k_planes_to_ref<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, y_planes_dev, tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(y_host, tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    cudaFree(tmp);
+    return STB_OK;
+}
+
+static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* y, double* out, double* F) {
+    OpArgs A;
+    A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
+    A.first = first; A.pulse = pulse; A.y = y; A.v = nullptr; A.Fy = nullptr; A.out = out; A.F = F;
+    k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    CK(cudaGetLastError());
+    return STB_OK;
+}
+
+static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y, const double* v,
+                     const double* Fy, double* out) {
+    OpArgs A;
+    A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
+    A.first = first; A.pulse = pulse; A.y = y; A.v = v; A.Fy = Fy; A.out = out; A.F = nullptr;
+    k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    CK(cudaGetLastError());
+    return STB_OK;
+}
+
+extern "C" int stb_rhs(stb_system* S, int32_t first, int32_t n, int32_t pulse, const double* y, double* dy) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(S->device));
+    if ((rc = sync_params(S))) return rc;
+    if ((rc = ensure_scratch(S, n))) return rc;
+    size_t bytes = sizeof(double) * (size_t)n * S->N;
+    int64_t tot = (int64_t)n * S->N;
+    unsigned gb = (unsigned)((tot + 255) / 256);
+    CK(cudaMemcpyAsync(S->d_tmp, y, bytes, cudaMemcpyHostToDevice, S->stream));
+    k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_y);
+    if ((rc = launch_rhs(S, first, n, pulse, S->d_y, S->d_out, S->d_F))) return rc;
+    k_planes_to_ref<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_out, S->d_tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dy, S->d_tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    return STB_OK;
+}
+
+extern "C" int stb_jv(stb_system* S, int32_t first, int32_t n, int32_t pulse, const double* y,
+                      const double* v, double* jv) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(S->device));
+    if ((rc = sync_params(S))) return rc;
+    if ((rc = ensure_scratch(S, n))) return rc;
+    size_t bytes = sizeof(double) * (size_t)n * S->N;
+    int64_t tot = (int64_t)n * S->N;
+    unsigned gb = (unsigned)((tot + 255) / 256);
+    CK(cudaMemcpyAsync(S->d_tmp, y, bytes, cudaMemcpyHostToDevice, S->stream));
+    k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_y);
+    CK(cudaMemcpyAsync(S->d_tmp, v, bytes, cudaMemcpyHostToDevice, S->stream));
+    k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_v);
+    if ((rc = launch_rhs(S, first, n, pulse, S->d_y, S->d_out, S->d_F))) return rc;   // fields at y
+    if ((rc = launch_jv(S, first, n, pulse, S->d_y, S->d_v, S->d_F, S->d_out))) return rc;
+    k_planes_to_ref<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_out, S->d_tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(jv, S->d_tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    return STB_OK;
+}
+
+extern "C" int stb_rhs_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse,
+                           const double* y_planes, double* dy_planes, int32_t repeat, float* ms) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(S->device));
+    if ((rc = sync_params(S))) return rc;
+    if ((rc = ensure_scratch(S, n))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    repeat = std::max(repeat, 1);
+    CK(cudaEventRecord(e0, S->stream));
+    for (int r = 0; r < repeat; ++r)
+        if ((rc = launch_rhs(S, first, n, pulse, y_planes, dy_planes, S->d_F))) return rc;
+    CK(cudaEventRecord(e1, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = t / repeat;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return STB_OK;
+}
+
+extern "C" int stb_jv_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse,
+                          const double* y_planes, const double* v_planes, double* jv_planes,
+                          int32_t repeat, float* ms) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(S->device));
+    if ((rc = sync_params(S))) return rc;
+    if ((rc = ensure_scratch(S, n))) return rc;
+    // fields at y once (what the integrator caches from its RHS pass)
+    if ((rc = launch_rhs(S, first, n, pulse, y_planes, S->d_out, S->d_F))) return rc;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    repeat = std::max(repeat, 1);
+    CK(cudaEventRecord(e0, S->stream));
+    for (int r = 0; r < repeat; ++r)
+        if ((rc = launch_jv(S, first, n, pulse, y_planes, v_planes, S->d_F, jv_planes))) return rc;
+    CK(cudaEventRecord(e1, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, e0, e1));
+    if (ms) *ms = t / repeat;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return STB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                             const double* t, const double* y0, double rtol, double atol,
+                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    if (n_t < 1 || !t || !y0) return fail(STB_EINVAL, "bad time grid / initial state");
+    if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(STB_EINVAL, "rtol must be > 0 and atol >= 0");
+    for (int64_t k = 1; k < n_t; ++k)
+        if (!(t[k] > t[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    CK(cudaSetDevice(S->device));
+    if ((rc = sync_params(S))) return rc;
+    const int N = S->N;
+    const DevLattice& L = S->hL;
+    const int NMinv = L.s[0] * L.s[0] * L.n[0] + L.s[1] * L.s[1] * L.n[1];
+
+    // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate, STB_NT, 0));
+    if (occ < 1) return fail(STB_ECUDA, "integrator kernel does not fit on an SM");
+    const int max_ctas = S->sm_count;   // one CTA per SM
+    const int total_slices = L.n_slices[0] + L.n_slices[1];
+    // a CTA wants at least ~2 slices per warp; never more CTAs per group than that allows
+    int G_work = std::max(1, total_slices / (2 * STB_NW));
+    int G = std::max(1, std::min(max_ctas / std::min(n, max_ctas), G_work));
+    if (const char* env = getenv("STB_GROUP_CTAS")) G = std::max(1, std::min(atoi(env), max_ctas));
+    int n_groups = std::max(1, std::min(max_ctas / G, n));
+    const int grid = n_groups * G;
+
+    const int64_t work_stride = stb_work_doubles(N, L.NF, NMinv);
+    double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_part = nullptr,
+           *d_tmp = nullptr, *d_avg = nullptr;
+    unsigned long long* d_bar = nullptr;
+    stb_stats* d_stats = nullptr;
+    size_t out_bytes = sizeof(double) * (size_t)n * n_t * N;
+    auto cleanup = [&]() {
+        cudaFree(d_work); cudaFree(d_y0); cudaFree(d_yout); cudaFree(d_t); cudaFree(d_part);
+        cudaFree(d_tmp); cudaFree(d_avg); cudaFree(d_bar); cudaFree(d_stats);
+    };
+#define CKI(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            cleanup();                                                                \
+            return e_ == cudaErrorMemoryAllocation ? STB_ENOMEM : STB_ECUDA;          \
+        }                                                                             \
+    } while (0)
+    CKI(cudaMalloc((void**)&d_work, sizeof(double) * (size_t)n_groups * work_stride));
+    CKI(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
+    CKI(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
+    CKI(cudaMalloc((void**)&d_yout, out_bytes));
+    CKI(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+    CKI(cudaMalloc((void**)&d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED));
+    CKI(cudaMalloc((void**)&d_bar, sizeof(unsigned long long) * n_groups));
+    CKI(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
+    CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * n_groups, S->stream));
+    CKI(cudaMemsetAsync(d_yout, 0, out_bytes, S->stream));
+    CKI(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
+    CKI(cudaMemsetAsync(d_work, 0, sizeof(double) * (size_t)n_groups * work_stride, S->stream));
+    CKI(cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
+    CKI(cudaMemcpyAsync(d_tmp, y0, sizeof(double) * (size_t)n * N, cudaMemcpyHostToDevice, S->stream));
+    int64_t tot = (int64_t)n * N;
+    k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
+    CKI(cudaGetLastError());
+
+    IntArgs A;
+    A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
+    A.first = first; A.n_sys = n; A.pulse = pulse; A.G = G; A.n_groups = n_groups;
+    A.n_t = n_t; A.t = d_t; A.y0 = d_y0; A.rtol = rtol; A.atol = atol;
+    A.nsteps = nsteps > 0 ? nsteps : 1000;
+    A.y_out = d_yout; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
+    A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv;
+    cudaEvent_t e0, e1;
+    CKI(cudaEventCreate(&e0));
+    CKI(cudaEventCreate(&e1));
+    CKI(cudaEventRecord(e0, S->stream));
+    void* kargs[] = {&A};
+    CKI(cudaLaunchCooperativeKernel((void*)k_integrate, dim3(grid), dim3(STB_NT), kargs, 0, S->stream));
+    CKI(cudaEventRecord(e1, S->stream));
+    S->last_launches = 1;
+    if (avg_out) {
+        CKI(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
+        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, d_yout, n_t, d_avg);
+        CKI(cudaGetLastError());
+        S->last_launches += 1;
+        CKI(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
+                            cudaMemcpyDeviceToHost, S->stream));
+    }
+    if (y_out) CKI(cudaMemcpyAsync(y_out, d_yout, out_bytes, cudaMemcpyDeviceToHost, S->stream));
+    if (stats) CKI(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
+    CKI(cudaStreamSynchronize(S->stream));
+    CKI(cudaEventElapsedTime(&S->last_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cleanup();
+    return STB_OK;
+}
+
+extern "C" int stb_last_timing(const stb_system* S, float* ms, int64_t* launches) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    if (ms) *ms = S->last_ms;
+    if (launches) *launches = S->last_launches;
+    return STB_OK;
+}

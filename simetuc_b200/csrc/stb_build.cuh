@@ -1,0 +1,185 @@
+// ET coupling build on the device: distances -> ion-owned sliced-ELL pair lists, and the
+// reference-ordered interaction view (N_indices, ET columns, jac_indices).
+//
+// Replaces lattice.create_interaction_matrices (lattice.py:301-374: for every ion the ascending
+// list of all other ions of each type with non-zero distance) and the pair part of
+// precalculate._create_ET_matrices (precalculate.py:235-415: w = strength * d^-mult).
+#pragma once
+#include "stb_common.cuh"
+
+struct Geo {
+    const double* dist;   // [n*n] or null
+    const double* pos;    // [n*3] or null
+    double cell[9], inv[9];
+    int periodic;
+    int n;
+    double d_max;         // <= 0: no cutoff
+};
+
+// minimum-image distance, same arithmetic as simetuc_b200/lattice.py:mic_distances
+__device__ __forceinline__ double geo_dist(const Geo& G, int a, int b) {
+    if (G.dist) return G.dist[(int64_t)a * G.n + b];
+    double d0 = G.pos[3 * b] - G.pos[3 * a];
+    double d1 = G.pos[3 * b + 1] - G.pos[3 * a + 1];
+    double d2 = G.pos[3 * b + 2] - G.pos[3 * a + 2];
+    if (!G.periodic) return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    double f0 = d0 * G.inv[0] + d1 * G.inv[3] + d2 * G.inv[6];
+    double f1 = d0 * G.inv[1] + d1 * G.inv[4] + d2 * G.inv[7];
+    double f2 = d0 * G.inv[2] + d1 * G.inv[5] + d2 * G.inv[8];
+    f0 -= rint(f0); f1 -= rint(f1); f2 -= rint(f2);
+    d0 = f0 * G.cell[0] + f1 * G.cell[3] + f2 * G.cell[6];
+    d1 = f0 * G.cell[1] + f1 * G.cell[4] + f2 * G.cell[7];
+    d2 = f0 * G.cell[2] + f1 * G.cell[5] + f2 * G.cell[8];
+    double best = 1e300;
+    for (int i = -1; i <= 1; ++i)
+        for (int j = -1; j <= 1; ++j)
+            for (int k = -1; k <= 1; ++k) {
+                double e0 = d0 + i * G.cell[0] + j * G.cell[3] + k * G.cell[6];
+                double e1 = d1 + i * G.cell[1] + j * G.cell[4] + k * G.cell[7];
+                double e2 = d2 + i * G.cell[2] + j * G.cell[5] + k * G.cell[8];
+                double r2 = e0 * e0 + e1 * e1 + e2 * e2;
+                best = r2 < best ? r2 : best;
+            }
+    return sqrt(best);
+}
+
+__device__ __forceinline__ bool geo_pair(const Geo& G, double d) {
+    return d != 0.0 && (G.d_max <= 0.0 || d <= G.d_max);
+}
+
+// row lengths: len[U][ion] = number of partners of type U of ion `ion` (global ion index)
+__global__ void k_count_pairs(Geo G, const uint8_t* type, int* len /*[2][n]*/) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = warp; q < G.n; q += nwarps) {
+        int c0 = 0, c1 = 0;
+        for (int k0 = 0; k0 < G.n; k0 += 32) {
+            int k = k0 + lane;
+            bool ok = false;
+            int U = 0;
+            if (k < G.n) {
+                ok = geo_pair(G, geo_dist(G, q, k));
+                U = type[k] != 0;
+            }
+            c0 += __popc(__ballot_sync(0xffffffffu, ok && U == 0));
+            c1 += __popc(__ballot_sync(0xffffffffu, ok && U == 1));
+        }
+        if (lane == 0) { len[q] = c0; len[G.n + q] = c1; }
+    }
+}
+
+struct FillArgs {
+    Geo G;
+    const uint8_t* type;
+    const int* local_idx;       // [n] type-local index of each ion
+    int lpr, R, n_mult;
+    int mults[STB_MAXM];
+    uint32_t* col[2][2];        // [T][U]
+    double* g[2][2][STB_MAXM];
+    const int64_t* line_ptr[2][2];
+};
+
+// one warp per ion row; partners in ascending lattice order (lattice.py:335-371)
+__global__ void k_fill_pairs(FillArgs A) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const Geo& G = A.G;
+    for (int q = warp; q < G.n; q += nwarps) {
+        int T = A.type[q] != 0;
+        int ql = A.local_idx[q];
+        int slice = ql / A.R, rl = ql % A.R;
+        int e[2] = {0, 0};
+        for (int k0 = 0; k0 < G.n; k0 += 32) {
+            int k = k0 + lane;
+            bool ok = false;
+            int U = 0;
+            double d = 0.0;
+            if (k < G.n) {
+                d = geo_dist(G, q, k);
+                ok = geo_pair(G, d);
+                U = A.type[k] != 0;
+            }
+#pragma unroll
+            for (int UU = 0; UU < 2; ++UU) {
+                unsigned m = __ballot_sync(0xffffffffu, ok && U == UU);
+                if (ok && U == UU && A.col[T][UU] != nullptr) {
+                    int pos = e[UU] + __popc(m & ((1u << lane) - 1u));
+                    int64_t line = A.line_ptr[T][UU][slice] + pos / A.lpr;
+                    int64_t idx = line * 32 + rl * A.lpr + pos % A.lpr;
+                    A.col[T][UU][idx] = (uint32_t)A.local_idx[k];
+                    for (int mm = 0; mm < A.n_mult; ++mm)
+                        A.g[T][UU][mm][idx] = pow(d, -(double)A.mults[mm]);
+                }
+                e[UU] += __popc(m);
+            }
+        }
+    }
+}
+
+struct ExportArgs {
+    const DevLattice* L;
+    const uint8_t* type;
+    const int* local_idx;
+    const int* gs_ref;          // [n] ground-state index of each ion, reference layout
+    const int* gs_of_local[2];  // [n_T] the same, by type-local index
+    const int* len;             // [2][n]
+    const int64_t* offset;      // [n] first interaction of each ion
+    const stb_process* procs;   // device copy, strengths already replaced by the system's
+    int n_proc, n;
+    uint32_t* N_indices;        // [M,2]
+    int32_t* et_rows;           // [M,4]
+    double* et_w;               // [M]
+    uint32_t* jac;              // [2M,3]
+};
+
+// The reference's interaction order (precalculate.py:349-392): ions in lattice order; for an
+// ion of type T first the (T,T) processes in dict order, each over all same-type partners,
+// then the (T, other) processes over all other-type partners.
+__global__ void k_export(ExportArgs A) {
+    const DevLattice& L = *A.L;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = warp; q < A.n; q += nwarps) {
+        int T = A.type[q] != 0;
+        int ql = A.local_idx[q];
+        int slice = ql / L.R, rl = ql % L.R;
+        int64_t r = A.offset[q];
+        int gs = A.gs_ref[q];
+        for (int ord = 0; ord < 2; ++ord) {
+            int U = ord == 0 ? T : 1 - T;
+            int cnt = A.len[U * A.n + q];
+            const PairBlock& B = L.blk[T][U];
+            for (int p = 0; p < A.n_proc; ++p) {
+                const stb_process pr = A.procs[p];
+                if (pr.donor_type != T || pr.partner_type != U || !stb_active_strength(pr.strength))
+                    continue;
+                int mi = 0;
+                for (int m = 0; m < L.n_mult; ++m) if (L.mults[m] == pr.mult) mi = m;
+                for (int e = lane; e < cnt; e += 32) {
+                    int64_t line = B.line_ptr[slice] + e / L.lpr;
+                    int64_t idx = line * 32 + rl * L.lpr + e % L.lpr;
+                    int gk = A.gs_of_local[U][B.col[idx]];
+                    double w = B.g[mi][idx] * pr.strength;   // dist**(-mult)*strength (:289)
+                    int64_t o = r + e;
+                    if (A.N_indices) {
+                        A.N_indices[2 * o] = gs + pr.ii;
+                        A.N_indices[2 * o + 1] = gk + pr.fi;
+                    }
+                    if (A.et_rows) {
+                        A.et_rows[4 * o] = gs + pr.ii;
+                        A.et_rows[4 * o + 1] = gs + pr.if_;
+                        A.et_rows[4 * o + 2] = gk + pr.fi;
+                        A.et_rows[4 * o + 3] = gk + pr.ff;
+                    }
+                    if (A.et_w) A.et_w[o] = w;
+                    if (A.jac) {
+                        uint32_t* j = A.jac + 6 * o;
+                        j[0] = (uint32_t)o; j[1] = gs + pr.ii; j[2] = gk + pr.fi;
+                        j[3] = (uint32_t)o; j[4] = gk + pr.fi; j[5] = gs + pr.ii;
+                    }
+                }
+                r += cnt;
+            }
+        }
+    }
+}

@@ -1,0 +1,68 @@
+// simetuc_b200 - shared device/host structures of the rate-equation path (sm_100a).
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   * state vectors are kept in PLANE layout inside the library: for ion type T (0 = S, 1 = A)
+//     and state s, the populations of all ions of that type are contiguous:
+//         z[off[T] + s * n[T] + i],  i = type-local ion index (lattice order within the type)
+//     so that per-ion work (lane = ion) and partner gathers (lane = partner) are coalesced.
+//     The reference layout (ion-major, lattice.py:279-292) only exists at the C ABI.
+//   * pair lists are ion-owned ("pull"): every ion row holds all its partners of type U as
+//     (partner index u32, d^-mult f64) in a sliced-ELL block: a slice is R = 32/lpr consecutive
+//     rows of one type handled by one warp, `lpr` lanes cooperate on a row, and the slice is
+//     stored as lines of 32 entries so that lane L reads entry [line*32 + L]: fully coalesced.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/simetuc_b200.h"
+
+#define STB_MAXC 6    // field slots (partner state, multipolarity) per (row type, partner type)
+#define STB_MAXM 3    // distinct multipolarities
+#define STB_MAXT 64   // rate terms per row type (a process contributes a donor and an acceptor term)
+#define STB_MAXS STB_MAX_STATES
+#define STB_KRYLOV 30 // GMRES basis size
+#define STB_MAXORD 5
+#define STB_NT 512    // threads per CTA of the integrator / rhs kernels
+#define STB_NW (STB_NT / 32)
+
+struct PairBlock {
+    const uint32_t* col;         // [lines*32] partner index, type-local
+    const double* g[STB_MAXM];   // [lines*32] d^-mult
+    const int64_t* line_ptr;     // [n_slices(T)+1]
+    int n_slots;
+    int slot_col[STB_MAXC];      // partner state whose population is accumulated
+    int slot_mult[STB_MAXC];     // which g[]
+};
+
+// rate = C[proc] * y_q[a] * F[slot];  dy_q[a] -= rate;  dy_q[b] += rate
+struct TermTable {
+    int n_terms;
+    short fslot[STB_MAXT];       // index into the row's field array (U-major)
+    short a[STB_MAXT], b[STB_MAXT], proc[STB_MAXT];
+};
+
+struct DevLattice {
+    int n_ions, N, NF;
+    int n[2], s[2], off[2];      // ions / states / plane offset per type
+    int lpr, R;                  // lanes per row, rows per slice (R*lpr == 32)
+    int n_slices[2];
+    int n_mult, mults[STB_MAXM];
+    int n_proc;
+    int nf[2], foff[2];          // field slots per row type, offset of the type's field planes
+    PairBlock blk[2][2];         // [row type][partner type]
+    TermTable terms[2];
+    const int* plane_of_ref;     // [N]
+    const int* ref_of_plane;     // [N]
+    int blk_stride;              // doubles per system in the `blocks` array
+};
+
+// per-system parameters as the kernels see them
+struct SysParams {
+    double lin[2][STB_MAXS * STB_MAXS];  // decay (+ absorption when pulse), row-major
+    double C[STB_MAX_PROC];              // effective strengths (0 when |strength| <= 1e-8)
+};
+
+__host__ __device__ inline bool stb_active_strength(double s) {
+    // the reference skips a process when np.isclose(strength, 0.0) (precalculate.py:354)
+    return (s > 1e-8) || (s < -1e-8);
+}

@@ -1,0 +1,751 @@
+// Persistent device-resident stiff integrator: variable-order (1-5) BDF in the
+// quasi-constant-step NDF form, Jacobian-free Newton-Krylov (left-preconditioned, scaled
+// GMRES(30)) with a per-ion block-Jacobi preconditioner.  Replaces odesolver._solve_ode
+// (odesolver.py:85-137) and the scipy VODE/LSODA call behind it, with no host round trip per
+// step: the grid is split into groups of G CTAs, each group integrates whole ODE systems of the
+// batch one after the other; CTAs of a group own fixed sets of ion rows, exchange only the
+// gathered state vector, and synchronise through a monotonic counter in global memory
+// (co-residency is guaranteed by the cooperative launch).  Every CTA runs the (tiny) scalar
+// step/order/Newton/Givens logic redundantly from identical reduced values, so control flow is
+// uniform across the group by construction.
+#pragma once
+#include "stb_fields.cuh"
+
+#define STB_KRED (STB_KRYLOV + 4)
+#define STB_NEWTON_MAXIT 4
+#define STB_MIN_FACTOR 0.2
+#define STB_MAX_FACTOR 10.0
+#define STB_EPS_LIN 0.05
+
+struct IntArgs {
+    const DevLattice* L;
+    const double* blocks;
+    const double* strengths;
+    int first, n_sys, pulse;
+    int G, n_groups;
+    int64_t n_t;
+    const double* t;          // [n_t]
+    const double* y0;         // [n_sys][N] planes
+    double rtol, atol;
+    int64_t nsteps;
+    double* y_out;            // [n_sys][n_t][N] reference layout
+    stb_stats* stats;         // [n_sys]
+    double* work;             // [n_groups][work_stride]
+    int64_t work_stride;
+    unsigned long long* bar;  // [n_groups]
+    double* partials;         // [n_groups][2][G][STB_KRED]
+    int NMinv;                // doubles of block-Jacobi inverses per system
+};
+
+__host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
+    // D[8] yk d psi scale f wv gv wbuf  V[KRYLOV+1]  F  Minv
+    return (int64_t)N * (8 + 8 + STB_KRYLOV + 1) + NF + NMinv;
+}
+
+struct Ctl {
+    double t, h, t_end, c, newton_tol, tol_lin;
+    double beta, inrm, dy_norm, dy_norm_old, err_norm, safety;
+    double RU[(STB_MAXORD + 1) * (STB_MAXORD + 1)];
+    double p[STB_MAXORD + 1];
+    int order, n_equal, status, kk, flag, newton_it, n_iter;
+    int64_t k_out, steps_since_out;
+    stb_stats st;
+};
+
+struct GroupCtx {
+    unsigned long long* counter;
+    unsigned long long epoch;
+    double* partials;   // [2][G][STB_KRED]
+    int G, cta, buf;
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void group_sync(GroupCtx& g) {
+    __syncthreads();
+    if (g.G > 1) {
+        if (threadIdx.x == 0) {
+            g.epoch += 1;
+            __threadfence();
+            atomicAdd(g.counter, 1ull);
+            unsigned long long target = g.epoch * (unsigned long long)g.G;
+            while (ld_acquire_u64(g.counter) < target) { }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+}
+
+// vals[0..K) hold this CTA's partial sums (smem); on return they hold the group totals,
+// summed in CTA order (deterministic, identical in every CTA).
+__device__ __forceinline__ void group_reduce(GroupCtx& g, double* vals, int K) {
+    if (g.G == 1) { __syncthreads(); return; }
+    double* mine = g.partials + ((int64_t)g.buf * g.G + g.cta) * STB_KRED;
+    if ((int)threadIdx.x < K) __stcg(mine + threadIdx.x, vals[threadIdx.x]);
+    group_sync(g);
+    if ((int)threadIdx.x < K) {
+        const double* base = g.partials + (int64_t)g.buf * g.G * STB_KRED + threadIdx.x;
+        double acc = 0.0;
+        for (int c = 0; c < g.G; ++c) acc += __ldcg(base + (int64_t)c * STB_KRED);
+        vals[threadIdx.x] = acc;
+    }
+    g.buf ^= 1;
+    __syncthreads();
+}
+
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], double* red /*[NW*K]*/, double* outs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) red[warp * K + k] = v[k];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        double acc = 0.0;
+        for (int w = 0; w < STB_NW; ++w) acc += red[w * K + threadIdx.x];
+        outs[threadIdx.x] = acc;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void compute_R(int order, double factor, double* R /*6x6*/) {
+    const int n = order + 1;
+    for (int j = 0; j < n; ++j) R[j] = 1.0;
+    for (int i = 1; i < n; ++i) {
+        R[i * 6] = 0.0;
+        for (int j = 1; j < n; ++j)
+            R[i * 6 + j] = R[(i - 1) * 6 + j] * ((i - 1 - factor * j) / i);
+    }
+}
+
+// RU = R(order, factor) . R(order, 1)   (thread 0)
+__device__ __forceinline__ void compute_RU(int order, double factor, double* RU) {
+    double R[36], U[36];
+    compute_R(order, factor, R);
+    compute_R(order, 1.0, U);
+    const int n = order + 1;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc += R[i * 6 + k] * U[k * 6 + j];
+            RU[i * 6 + j] = acc;
+        }
+}
+
+#define OWN_LOOP(e)                                                          \
+    for (int T_ = 0; T_ < 2; ++T_) {                                         \
+        const int cnt_ = r_hi[T_] - r_lo[T_];                                \
+        const int tot_ = cnt_ * L.s[T_];                                     \
+        for (int k_ = threadIdx.x; k_ < tot_; k_ += STB_NT) {                \
+            const int e = L.off[T_] + (k_ / cnt_) * L.n[T_] + r_lo[T_] + (k_ % cnt_);
+#define OWN_END }}
+
+__global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
+    __shared__ DevLattice L;
+    __shared__ SysParams P;
+    __shared__ Ctl C;
+    __shared__ double H[(STB_KRYLOV + 1) * STB_KRYLOV];
+    __shared__ double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
+    __shared__ double red[STB_NW * 4];
+    __shared__ double rv[STB_KRED];
+
+    const int gid = blockIdx.x / A.G;
+    if (gid >= A.n_groups) return;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
+        ((int*)&L)[i] = ((const int*)A.L)[i];
+    __syncthreads();
+
+    GroupCtx g;
+    g.G = A.G;
+    g.cta = blockIdx.x % A.G;
+    g.counter = A.bar + gid;
+    g.epoch = 0;
+    g.buf = 0;
+    g.partials = A.partials + (int64_t)gid * 2 * A.G * STB_KRED;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = L.N;
+    int sl_lo[2], sl_hi[2], r_lo[2], r_hi[2];
+    for (int T = 0; T < 2; ++T) {
+        sl_lo[T] = (int)(((int64_t)L.n_slices[T] * g.cta) / g.G);
+        sl_hi[T] = (int)(((int64_t)L.n_slices[T] * (g.cta + 1)) / g.G);
+        r_lo[T] = min(sl_lo[T] * L.R, L.n[T]);
+        r_hi[T] = min(sl_hi[T] * L.R, L.n[T]);
+    }
+    const int n_own_slices = (sl_hi[0] - sl_lo[0]) + (sl_hi[1] - sl_lo[1]);
+
+    double* W = A.work + (int64_t)gid * A.work_stride;
+    double* D = W;                       // [8][N]
+    double* yk = D + 8 * (int64_t)N;
+    double* dd = yk + N;
+    double* psi = dd + N;
+    double* scale = psi + N;
+    double* f = scale + N;
+    double* wv = f + N;
+    double* gv = wv + N;
+    double* wbuf = gv + N;
+    double* V = wbuf + N;                // [KRYLOV+1][N]
+    double* F = V + (int64_t)(STB_KRYLOV + 1) * N;
+    double* Minv = F + L.NF;
+
+    const double KAPPA[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+    double GAMMA[6], ALPHA[6], ERRC[6];
+    GAMMA[0] = 0.0;
+    for (int k = 1; k <= 5; ++k) GAMMA[k] = GAMMA[k - 1] + 1.0 / k;
+    for (int k = 0; k <= 5; ++k) {
+        ALPHA[k] = (1.0 - KAPPA[k]) * GAMMA[k];
+        ERRC[k] = KAPPA[k] * GAMMA[k] + 1.0 / (k + 1);
+    }
+    const double sqrtN = sqrt((double)N);
+
+    // ---- RHS phase: f = rhs(z) for own rows, fields F; optional block-Jacobi setup and
+    //      preconditioned scaled residual (Newton) -------------------------------------------
+    // mode 0: plain RHS (f only).  mode 1: Newton: also Minv(c), wv = Minv(c f - psi - d)/scale,
+    //         gv = wv*scale; returns partial ||wv||^2 and a non-finite flag in part[].
+    auto rhs_phase = [&](const double* z, double* fout, int mode, double c, double (&part)[2]) {
+        part[0] = 0.0;
+        part[1] = 0.0;
+        for (int task = warp; task < n_own_slices; task += STB_NW) {
+            int T = task >= (sl_hi[0] - sl_lo[0]);
+            int slice = T ? sl_lo[1] + task - (sl_hi[0] - sl_lo[0]) : sl_lo[0] + task;
+            double Fq[2 * STB_MAXC];
+            slice_fields(L, T, slice, z, lane, 1.0, Fq);
+            int q = slice * L.R + lane / L.lpr;
+            if ((lane % L.lpr) == 0 && q < L.n[T]) {
+                double zq[STB_MAXS], oq[STB_MAXS];
+                load_row(L, T, q, z, zq);
+                row_rhs(L, P, T, zq, Fq, oq);
+                store_row(L, T, q, fout, oq);
+                const int nT = L.n[T], s = L.s[T];
+                double* Fp = F + L.foff[T] + q;
+                for (int k = 0; k < L.nf[T]; ++k) Fp[(int64_t)k * nT] = Fq[k];
+                if (mode == 1) {
+                    double Am[STB_MAXS * STB_MAXS], Ai[STB_MAXS * STB_MAXS];
+                    row_block_inverse(L, P, T, Fq, c, Am, Ai);
+                    double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
+                    for (int k = 0; k < s * s; ++k) Mp[(int64_t)k * nT] = Ai[k];
+                    const int base = L.off[T] + q;
+                    double r[STB_MAXS];
+                    for (int a = 0; a < s; ++a) {
+                        int e = base + a * nT;
+                        r[a] = c * oq[a] - psi[e] - dd[e];
+                        if (!isfinite(oq[a])) part[1] = 1.0;
+                    }
+                    for (int a = 0; a < s; ++a) {
+                        double acc = 0.0;
+                        for (int b = 0; b < s; ++b) acc = fma(Ai[a * s + b], r[b], acc);
+                        int e = base + a * nT;
+                        double x = acc / scale[e];
+                        wv[e] = x;
+                        gv[e] = acc;
+                        part[0] = fma(x, x, part[0]);
+                    }
+                }
+            }
+        }
+    };
+
+    // ---- Arnoldi phase: wbuf = Minv (v - c J v) / scale with v = inrm * gv ------------------
+    auto arnoldi_phase = [&](double inrm, double c) {
+        for (int task = warp; task < n_own_slices; task += STB_NW) {
+            int T = task >= (sl_hi[0] - sl_lo[0]);
+            int slice = T ? sl_lo[1] + task - (sl_hi[0] - sl_lo[0]) : sl_lo[0] + task;
+            double Fv[2 * STB_MAXC];
+            slice_fields(L, T, slice, gv, lane, inrm, Fv);
+            int q = slice * L.R + lane / L.lpr;
+            if ((lane % L.lpr) == 0 && q < L.n[T]) {
+                const int nT = L.n[T], s = L.s[T];
+                double Fq[2 * STB_MAXC], yq[STB_MAXS], vq[STB_MAXS], jq[STB_MAXS];
+                const double* Fp = F + L.foff[T] + q;
+                for (int k = 0; k < L.nf[T]; ++k) Fq[k] = Fp[(int64_t)k * nT];
+                load_row(L, T, q, yk, yq);
+                load_row(L, T, q, gv, vq);
+                for (int a = 0; a < s; ++a) vq[a] *= inrm;
+                row_jv(L, P, T, yq, vq, Fq, Fv, jq);
+                for (int a = 0; a < s; ++a) jq[a] = vq[a] - c * jq[a];
+                const double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
+                const int base = L.off[T] + q;
+                for (int a = 0; a < s; ++a) {
+                    double acc = 0.0;
+                    for (int b = 0; b < s; ++b) acc = fma(Mp[(int64_t)(a * s + b) * nT], jq[b], acc);
+                    int e = base + a * nT;
+                    wbuf[e] = acc / scale[e];
+                }
+            }
+        }
+    };
+
+    // dots of `vec` (own elements) against V[0..nv) and itself: rv[i] (i<nv), rv[nv] = <vec,vec>
+    auto own_dots = [&](const double* vec, int nv) {
+        __syncthreads();
+        for (int i = warp; i <= nv; i += STB_NW) {
+            const double* Vi = i < nv ? V + (int64_t)i * N : vec;
+            double acc = 0.0;
+            for (int T = 0; T < 2; ++T) {
+                const int cnt = r_hi[T] - r_lo[T];
+                const int tot = cnt * L.s[T];
+                for (int k = lane; k < tot; k += 32) {
+                    int e = L.off[T] + (k / cnt) * L.n[T] + r_lo[T] + (k % cnt);
+                    acc = fma(vec[e], Vi[e], acc);
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) rv[i] = acc;
+        }
+        __syncthreads();
+    };
+
+    // D[0..order] <- RU^T D[0..order] for own elements (C.RU set by thread 0)
+    auto apply_change_D = [&](int order) {
+        OWN_LOOP(e)
+            double dv[6], nd[6];
+            for (int j = 0; j <= order; ++j) dv[j] = D[(int64_t)j * N + e];
+            for (int i = 0; i <= order; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j <= order; ++j) acc = fma(C.RU[j * 6 + i], dv[j], acc);
+                nd[i] = acc;
+            }
+            for (int i = 0; i <= order; ++i) D[(int64_t)i * N + e] = nd[i];
+        OWN_END
+    };
+
+    for (int sysl = gid; sysl < A.n_sys; sysl += A.n_groups) {
+        const int sys = A.first + sysl;
+        __syncthreads();
+        load_sys_params(L, A.blocks, A.strengths, sys, A.pulse, P);
+        const double* y0 = A.y0 + (int64_t)sysl * N;
+        double* y_out = A.y_out + (int64_t)sysl * A.n_t * N;
+        const double rtol = A.rtol, atol = A.atol;
+        if (threadIdx.x == 0) {
+            C.t = A.t[0];
+            C.t_end = A.t[A.n_t - 1];
+            C.order = 1;
+            C.n_equal = 0;
+            C.status = 0;
+            C.k_out = 1;
+            C.steps_since_out = 0;
+            C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
+            C.tol_lin = STB_EPS_LIN * C.newton_tol * sqrtN;
+            memset(&C.st, 0, sizeof(stb_stats));
+        }
+        // D0 = y0, yk = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
+        OWN_LOOP(e)
+            double v = y0[e];
+            D[e] = v;
+            yk[e] = v;
+            y_out[L.ref_of_plane[e]] = v;
+            for (int j = 1; j < 8; ++j) D[(int64_t)j * N + e] = 0.0;
+        OWN_END
+        group_sync(g);
+        double part[2];
+        rhs_phase(yk, f, 0, 0.0, part);
+        if (threadIdx.x == 0) C.st.n_rhs += 1;
+        // ---- initial step (Hairer-Wanner, as scipy select_initial_step) -------------------
+        {
+            double v3[3] = {0.0, 0.0, 0.0};
+            __syncthreads();
+            OWN_LOOP(e)
+                double sc = atol + rtol * fabs(yk[e]);
+                scale[e] = sc;
+                double a = yk[e] / sc, b = f[e] / sc;
+                v3[0] = fma(a, a, v3[0]);
+                v3[1] = fma(b, b, v3[1]);
+                if (!isfinite(f[e])) v3[2] = 1.0;
+            OWN_END
+            block_sum<3>(v3, red, rv);
+            group_reduce(g, rv, 3);
+            double d0 = sqrt(rv[0] / N), d1 = sqrt(rv[1] / N);
+            double bad = rv[2];
+            double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            __syncthreads();
+            OWN_LOOP(e)
+                gv[e] = yk[e] + h0 * f[e];
+            OWN_END
+            group_sync(g);
+            rhs_phase(gv, wbuf, 0, 0.0, part);
+            double v1[1] = {0.0};
+            __syncthreads();
+            OWN_LOOP(e)
+                double a = (wbuf[e] - f[e]) / scale[e];
+                v1[0] = fma(a, a, v1[0]);
+            OWN_END
+            block_sum<1>(v1, red, rv);
+            group_reduce(g, rv, 1);
+            if (threadIdx.x == 0) {
+                C.st.n_rhs += 1;
+                double d2 = sqrt(rv[0] / N) / h0;
+                double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
+                                                         : sqrt(0.01 / fmax(d1, d2));
+                C.h = fmin(fmin(100.0 * h0, h1), C.t_end - C.t);
+                if (bad != 0.0 || !isfinite(C.h) || !(C.h > 0.0)) C.status = 3;
+            }
+            __syncthreads();
+            // the fields F must correspond to yk again before the first Newton iteration: they
+            // are recomputed by the first RHS of the step.  D1 = f0 * h
+            const double h = C.h;
+            OWN_LOOP(e)
+                D[(int64_t)N + e] = f[e] * h;
+            OWN_END
+        }
+        __syncthreads();
+
+        // =============================== time stepping =====================================
+        while (true) {
+            __syncthreads();
+            if (C.status != 0 || C.k_out >= A.n_t) break;
+            // ---- one step attempt ------------------------------------------------------------
+            if (threadIdx.x == 0) {
+                C.flag = 0;
+                double t_new = C.t + C.h;
+                if (t_new > C.t_end && (t_new - C.t_end) > 1e-14 * fabs(C.t_end)) {
+                    double factor = (C.t_end - C.t) / C.h;
+                    compute_RU(C.order, factor, C.RU);
+                    C.h = C.t_end - C.t;
+                    C.n_equal = 0;
+                    C.flag = 1;
+                } else if (t_new > C.t_end) {
+                    C.h = C.t_end - C.t;  // round-off sized overshoot: land exactly on t_end
+                }
+                double eps_t = 10.0 * fabs(nextafter(C.t, 1e300) - C.t);
+                if (C.h < eps_t) C.status = 2;
+                if (C.steps_since_out >= A.nsteps) C.status = 1;
+                C.c = C.h / ALPHA[C.order];
+            }
+            __syncthreads();
+            if (C.status != 0) break;
+            if (C.flag) apply_change_D(C.order);
+            __syncthreads();
+            const int order = C.order;
+            const double c = C.c;
+            // predictor, scale, psi; d = 0
+            OWN_LOOP(e)
+                double yp = 0.0, ps = 0.0;
+                for (int j = 0; j <= order; ++j) {
+                    double dj = D[(int64_t)j * N + e];
+                    yp += dj;
+                    if (j >= 1) ps = fma(GAMMA[j], dj, ps);
+                }
+                yk[e] = yp;
+                scale[e] = atol + rtol * fabs(yp);
+                psi[e] = ps / ALPHA[order];
+                dd[e] = 0.0;
+            OWN_END
+            // ---- Newton-Krylov ----------------------------------------------------------------
+            if (threadIdx.x == 0) { C.newton_it = 0; C.flag = 0; C.dy_norm_old = -1.0; }
+            __syncthreads();
+            while (true) {       // flag: 0 iterate, 1 converged, 2 failed
+                group_sync(g);   // yk complete in the whole group
+                rhs_phase(yk, f, 1, c, part);
+                double v2[2] = {part[0], part[1]};
+                block_sum<2>(v2, red, rv);
+                group_reduce(g, rv, 2);
+                if (threadIdx.x == 0) {
+                    C.st.n_rhs += 1;
+                    C.st.n_lin += 1;
+                    C.beta = sqrt(rv[0]);
+                    C.kk = 0;
+                    if (rv[1] != 0.0 || !isfinite(C.beta)) C.flag = 2;
+                    gg[0] = C.beta;
+                    C.inrm = C.beta > 0.0 ? 1.0 / C.beta : 0.0;
+                }
+                __syncthreads();
+                if (C.flag == 2) break;
+                // ---- GMRES ----------------------------------------------------------------
+                bool lin_done = !(C.beta > C.tol_lin);
+                int j = 0;
+                while (!lin_done) {
+                    const double inrm = C.inrm;
+                    // V_j = inrm * wv (own elements); then the fused operator pass
+                    double* Vj = V + (int64_t)j * N;
+                    OWN_LOOP(e)
+                        Vj[e] = inrm * wv[e];
+                    OWN_END
+                    arnoldi_phase(inrm, c);
+                    own_dots(wbuf, j + 1);
+                    group_reduce(g, rv, j + 2);
+                    const double ww = rv[j + 1];
+                    if (threadIdx.x <= (unsigned)j) H[threadIdx.x * STB_KRYLOV + j] = rv[threadIdx.x];
+                    __syncthreads();
+                    double v1[1] = {0.0};
+                    OWN_LOOP(e)
+                        double acc = wbuf[e];
+                        for (int i = 0; i <= j; ++i)
+                            acc = fma(-H[i * STB_KRYLOV + j], V[(int64_t)i * N + e], acc);
+                        wv[e] = acc;
+                        gv[e] = acc * scale[e];
+                        v1[0] = fma(acc, acc, v1[0]);
+                    OWN_END
+                    block_sum<1>(v1, red, rv);
+                    group_reduce(g, rv, 1);
+                    double hn2 = rv[0];
+                    if (hn2 < 0.01 * ww && hn2 > 0.0) {
+                        // severe cancellation: one re-orthogonalisation pass (DGKS)
+                        own_dots(wv, j + 1);
+                        group_reduce(g, rv, j + 2);
+                        if (threadIdx.x <= (unsigned)j) H[threadIdx.x * STB_KRYLOV + j] += rv[threadIdx.x];
+                        double corr[STB_KRYLOV];
+                        for (int i = 0; i <= j; ++i) corr[i] = rv[i];
+                        __syncthreads();
+                        v1[0] = 0.0;
+                        OWN_LOOP(e)
+                            double acc = wv[e];
+                            for (int i = 0; i <= j; ++i)
+                                acc = fma(-corr[i], V[(int64_t)i * N + e], acc);
+                            wv[e] = acc;
+                            gv[e] = acc * scale[e];
+                            v1[0] = fma(acc, acc, v1[0]);
+                        OWN_END
+                        block_sum<1>(v1, red, rv);
+                        group_reduce(g, rv, 1);
+                        hn2 = rv[0];
+                    }
+                    if (threadIdx.x == 0) {
+                        C.st.n_jv += 1;
+                        double hn = sqrt(hn2);
+                        double* Hc = H + j;   // column j, stride STB_KRYLOV
+                        for (int i = 0; i < j; ++i) {
+                            double a = Hc[i * STB_KRYLOV], b = Hc[(i + 1) * STB_KRYLOV];
+                            Hc[i * STB_KRYLOV] = cs[i] * a + sn[i] * b;
+                            Hc[(i + 1) * STB_KRYLOV] = -sn[i] * a + cs[i] * b;
+                        }
+                        double a = Hc[j * STB_KRYLOV];
+                        double dnm = hypot(a, hn);
+                        if (dnm == 0.0) { cs[j] = 1.0; sn[j] = 0.0; }
+                        else { cs[j] = a / dnm; sn[j] = hn / dnm; }
+                        Hc[j * STB_KRYLOV] = dnm;
+                        gg[j + 1] = -sn[j] * gg[j];
+                        gg[j] = cs[j] * gg[j];
+                        C.kk = j + 1;
+                        C.inrm = hn > 0.0 ? 1.0 / hn : 0.0;
+                        C.beta = fabs(gg[j + 1]);
+                        if (!(hn > 0.0) || !isfinite(hn)) C.beta = 0.0;
+                    }
+                    __syncthreads();
+                    ++j;
+                    lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
+                }
+                // ---- x = V y, dy = x * scale; Newton control --------------------------------
+                const int kk = C.kk;
+                if (threadIdx.x == 0) {
+                    for (int i = kk - 1; i >= 0; --i) {
+                        double acc = gg[i];
+                        for (int k = i + 1; k < kk; ++k) acc -= H[i * STB_KRYLOV + k] * yk_s[k];
+                        double hd = H[i * STB_KRYLOV + i];
+                        yk_s[i] = hd != 0.0 ? acc / hd : 0.0;
+                    }
+                }
+                __syncthreads();
+                double v1[1] = {0.0};
+                OWN_LOOP(e)
+                    double x = 0.0;
+                    for (int i = 0; i < kk; ++i) x = fma(yk_s[i], V[(int64_t)i * N + e], x);
+                    wbuf[e] = x;      // scaled Newton update
+                    v1[0] = fma(x, x, v1[0]);
+                OWN_END
+                block_sum<1>(v1, red, rv);
+                group_reduce(g, rv, 1);
+                if (threadIdx.x == 0) {
+                    double dy_norm = sqrt(rv[0] / N);
+                    const int it = C.newton_it;
+                    double rate = C.dy_norm_old > 0.0 ? dy_norm / C.dy_norm_old : -1.0;
+                    int flag = 0;
+                    if (!isfinite(dy_norm)) flag = 2;
+                    else if (rate >= 0.0 &&
+                             (rate >= 1.0 ||
+                              pow(rate, (double)(STB_NEWTON_MAXIT - it)) / (1.0 - rate) * dy_norm >
+                                  C.newton_tol))
+                        flag = 2;
+                    C.dy_norm = dy_norm;
+                    if (flag == 0) {
+                        if (dy_norm == 0.0 ||
+                            (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < C.newton_tol) ||
+                            (rate < 0.0 && dy_norm < 0.1 * C.newton_tol))
+                            flag = 1;
+                    }
+                    C.flag = flag;     // 2: do not apply the update
+                    C.dy_norm_old = dy_norm;
+                    C.newton_it = it + 1;
+                    C.n_iter = it + 1;
+                }
+                __syncthreads();
+                const int flag = C.flag;
+                if (flag != 2) {
+                    OWN_LOOP(e)
+                        double dy = wbuf[e] * scale[e];
+                        yk[e] += dy;
+                        dd[e] += dy;
+                    OWN_END
+                }
+                if (flag != 0) break;
+                if (C.newton_it >= STB_NEWTON_MAXIT) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) C.flag = 2;
+                    __syncthreads();
+                    break;
+                }
+            }
+            __syncthreads();
+            if (C.flag == 2) {
+                // Newton / Krylov failure: halve the step (scipy: factor 0.5 with current Jacobian)
+                if (threadIdx.x == 0) {
+                    C.st.n_newton_fail += 1;
+                    compute_RU(C.order, 0.5, C.RU);
+                    C.h *= 0.5;
+                    C.n_equal = 0;
+                    C.steps_since_out += 1;
+                }
+                __syncthreads();
+                apply_change_D(order);
+                continue;
+            }
+            // ---- error test --------------------------------------------------------------------
+            {
+                double v1[1] = {0.0};
+                __syncthreads();
+                OWN_LOOP(e)
+                    double sc = atol + rtol * fabs(yk[e]);
+                    scale[e] = sc;
+                    double er = ERRC[order] * dd[e] / sc;
+                    v1[0] = fma(er, er, v1[0]);
+                OWN_END
+                block_sum<1>(v1, red, rv);
+                group_reduce(g, rv, 1);
+                if (threadIdx.x == 0) {
+                    C.err_norm = sqrt(rv[0] / N);
+                    C.safety = 0.9 * (2 * STB_NEWTON_MAXIT + 1) / (2.0 * STB_NEWTON_MAXIT + C.n_iter);
+                    C.flag = 0;
+                    if (C.err_norm > 1.0 || !isfinite(C.err_norm)) {
+                        double factor = isfinite(C.err_norm)
+                            ? fmax(STB_MIN_FACTOR, C.safety * pow(C.err_norm, -1.0 / (order + 1)))
+                            : STB_MIN_FACTOR;
+                        compute_RU(order, factor, C.RU);
+                        C.h *= factor;
+                        C.n_equal = 0;
+                        C.st.n_rejected += 1;
+                        C.steps_since_out += 1;
+                        C.flag = 1;
+                    }
+                }
+                __syncthreads();
+                if (C.flag == 1) {
+                    apply_change_D(order);
+                    continue;
+                }
+            }
+            // ---- accepted: update differences, dense output, order / step selection -------------
+            const double h = C.h, t_new = C.t + C.h;
+            {
+                double v2[2] = {0.0, 0.0};
+                __syncthreads();
+                OWN_LOOP(e)
+                    double dv = dd[e];
+                    double dp1 = D[(int64_t)(order + 1) * N + e];
+                    double d2 = dv - dp1;
+                    D[(int64_t)(order + 2) * N + e] = d2;
+                    D[(int64_t)(order + 1) * N + e] = dv;
+                    double run = dv;
+                    double dord = 0.0;
+                    for (int i = order; i >= 0; --i) {
+                        run += D[(int64_t)i * N + e];
+                        D[(int64_t)i * N + e] = run;
+                        if (i == order) dord = run;
+                    }
+                    double sc = scale[e];
+                    if (order > 1) { double em = ERRC[order - 1] * dord / sc; v2[0] = fma(em, em, v2[0]); }
+                    if (order < STB_MAXORD) { double ep = ERRC[order + 1] * d2 / sc; v2[1] = fma(ep, ep, v2[1]); }
+                OWN_END
+                // dense output for every requested time in (t, t_new]
+                __syncthreads();
+                while (true) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        C.flag = 0;
+                        if (C.k_out < A.n_t) {
+                            double tq = A.t[C.k_out];
+                            if (tq <= t_new * (1.0 + 1e-15) || tq <= t_new) {
+                                C.flag = tq >= t_new ? 2 : 1;
+                                double pr = 1.0;
+                                for (int jj = 0; jj < order; ++jj) {
+                                    pr *= (tq - (t_new - h * jj)) / (h * (1 + jj));
+                                    C.p[jj + 1] = pr;
+                                }
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (C.flag == 0) break;
+                    double* row = y_out + C.k_out * (int64_t)N;
+                    const bool exact = C.flag == 2;
+                    OWN_LOOP(e)
+                        double acc = D[e];
+                        if (!exact)
+                            for (int jj = 1; jj <= order; ++jj)
+                                acc = fma(C.p[jj], D[(int64_t)jj * N + e], acc);
+                        row[L.ref_of_plane[e]] = acc;
+                    OWN_END
+                    __syncthreads();
+                    if (threadIdx.x == 0) { C.k_out += 1; C.st.n_out = C.k_out; C.steps_since_out = 0; }
+                }
+                const bool need_order = (C.n_equal + 1) >= order + 1;
+                if (need_order) {
+                    block_sum<2>(v2, red, rv);
+                    group_reduce(g, rv, 2);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    C.st.n_steps += 1;
+                    C.steps_since_out += 1;
+                    C.n_equal += 1;
+                    C.t = t_new;
+                    C.flag = 0;
+                    if (need_order) {
+                        double err_m = order > 1 ? sqrt(rv[0] / N) : INFINITY;
+                        double err_p = order < STB_MAXORD ? sqrt(rv[1] / N) : INFINITY;
+                        double fm = err_m > 0.0 ? pow(err_m, -1.0 / order) : INFINITY;
+                        double f0 = C.err_norm > 0.0 ? pow(C.err_norm, -1.0 / (order + 1)) : INFINITY;
+                        double fp = err_p > 0.0 ? pow(err_p, -1.0 / (order + 2)) : INFINITY;
+                        if (order == 1) fm = 0.0;
+                        if (order == STB_MAXORD) fp = 0.0;
+                        if (isinf(err_m)) fm = 0.0;
+                        if (isinf(err_p)) fp = 0.0;
+                        int delta = 0;
+                        double best = f0;
+                        if (fm > best) { best = fm; delta = -1; }
+                        if (fp > best) { best = fp; delta = 1; }
+                        // numpy argmax picks the first maximum: order-1 wins ties, then same order
+                        if (fm >= f0 && fm >= fp) { best = fm; delta = -1; }
+                        else if (f0 >= fp) { best = f0; delta = 0; }
+                        else { best = fp; delta = 1; }
+                        C.order = order + delta;
+                        double factor = fmin(STB_MAX_FACTOR, C.safety * best);
+                        compute_RU(C.order, factor, C.RU);
+                        C.h *= factor;
+                        C.n_equal = 0;
+                        C.flag = 1;
+                    }
+                    C.st.last_order = C.order;
+                    C.st.last_h = C.h;
+                }
+                __syncthreads();
+                if (C.flag == 1) apply_change_D(C.order);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && g.cta == 0) {
+            C.st.status = C.status;
+            C.st.t_reached = C.t;
+            C.st.n_out = C.k_out;
+            A.stats[sysl] = C.st;
+        }
+        group_sync(g);
+    }
+}

@@ -1,0 +1,136 @@
+// Standalone RHS / Jv kernels (C ABI: stb_rhs, stb_jv) and layout conversion.
+// One warp per slice (R rows), grid-stride over slices, blockIdx.y = system of the batch.
+#pragma once
+#include "stb_fields.cuh"
+
+struct OpArgs {
+    const DevLattice* L;
+    const double* blocks;
+    const double* strengths;
+    int first;       // first system
+    int pulse;
+    const double* y; // [n][N] planes
+    const double* v; // [n][N] planes (Jv)
+    const double* Fy;// [n][NF]  (Jv: fields at y, from a previous RHS pass)
+    double* out;     // [n][N]
+    double* F;       // [n][NF] (RHS: fields at y, may be null)
+};
+
+// dy = (abs +) decay y + ET (y_i * y_j): odesolver._rate_eq / _rate_eq_pulse (odesolver.py:33-71)
+__global__ void __launch_bounds__(STB_NT) k_rhs(OpArgs A) {
+    __shared__ DevLattice L;
+    __shared__ SysParams P;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
+        ((int*)&L)[i] = ((const int*)A.L)[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    load_sys_params(L, A.blocks, A.strengths, A.first + b, A.pulse, P);
+    __syncthreads();
+    const double* y = A.y + (int64_t)b * L.N;
+    double* out = A.out + (int64_t)b * L.N;
+    double* F = A.F ? A.F + (int64_t)b * L.NF : nullptr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = L.n_slices[0] + L.n_slices[1];
+    for (int task = blockIdx.x * STB_NW + warp; task < total; task += gridDim.x * STB_NW) {
+        int T = task >= L.n_slices[0];
+        int slice = T ? task - L.n_slices[0] : task;
+        double Fq[2 * STB_MAXC];
+        slice_fields(L, T, slice, y, lane, 1.0, Fq);
+        int q = slice * L.R + lane / L.lpr;
+        if ((lane % L.lpr) == 0 && q < L.n[T]) {
+            double yq[STB_MAXS], oq[STB_MAXS];
+            load_row(L, T, q, y, yq);
+            row_rhs(L, P, T, yq, Fq, oq);
+            store_row(L, T, q, out, oq);
+            if (F) {
+                double* Fp = F + L.foff[T] + q;
+                for (int k = 0; k < L.nf[T]; ++k) Fp[(int64_t)k * L.n[T]] = Fq[k];
+            }
+        }
+    }
+}
+
+// jv = J(y) v without the dense Jacobian (odesolver.py:46-62,74-80); the fields at y come from
+// the RHS pass at the same y, so one Jv streams the pair data exactly once.
+__global__ void __launch_bounds__(STB_NT) k_jv(OpArgs A) {
+    __shared__ DevLattice L;
+    __shared__ SysParams P;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
+        ((int*)&L)[i] = ((const int*)A.L)[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    load_sys_params(L, A.blocks, A.strengths, A.first + b, A.pulse, P);
+    __syncthreads();
+    const double* y = A.y + (int64_t)b * L.N;
+    const double* v = A.v + (int64_t)b * L.N;
+    const double* Fy = A.Fy + (int64_t)b * L.NF;
+    double* out = A.out + (int64_t)b * L.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int total = L.n_slices[0] + L.n_slices[1];
+    for (int task = blockIdx.x * STB_NW + warp; task < total; task += gridDim.x * STB_NW) {
+        int T = task >= L.n_slices[0];
+        int slice = T ? task - L.n_slices[0] : task;
+        double Fv[2 * STB_MAXC];
+        slice_fields(L, T, slice, v, lane, 1.0, Fv);
+        int q = slice * L.R + lane / L.lpr;
+        if ((lane % L.lpr) == 0 && q < L.n[T]) {
+            double Fq[2 * STB_MAXC], yq[STB_MAXS], vq[STB_MAXS], oq[STB_MAXS];
+            const double* Fp = Fy + L.foff[T] + q;
+            for (int k = 0; k < L.nf[T]; ++k) Fq[k] = Fp[(int64_t)k * L.n[T]];
+            load_row(L, T, q, y, yq);
+            load_row(L, T, q, v, vq);
+            row_jv(L, P, T, yq, vq, Fq, Fv, oq);
+            store_row(L, T, q, out, oq);
+        }
+    }
+}
+
+// reference (ion-major) layout <-> plane layout, n vectors of length N
+__global__ void k_ref_to_planes(const int* plane_of_ref, int N, int n, const double* ref,
+                                double* planes) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < (int64_t)N * n) {
+        int b = i / N, e = i % N;
+        planes[(int64_t)b * N + plane_of_ref[e]] = ref[i];
+    }
+}
+
+__global__ void k_planes_to_ref(const int* plane_of_ref, int N, int n, const double* planes,
+                                double* ref) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < (int64_t)N * n) {
+        int b = i / N, e = i % N;
+        ref[i] = planes[(int64_t)b * N + plane_of_ref[e]];
+    }
+}
+
+// per-state ion averages clipped at zero: Solution._calculate_avg_populations
+// (simulations.py:100-128).  y_out is [n_t][N] in reference layout for one system; one block per
+// (time row, system); out [n_t][sS+sA].
+__global__ void k_avg_populations(const DevLattice* Lg, const double* y_out, int64_t n_t,
+                                  double* avg) {
+    const DevLattice& L = *Lg;
+    int64_t row = blockIdx.x;
+    int b = blockIdx.y;
+    const double* y = y_out + ((int64_t)b * n_t + row) * L.N;
+    double* o = avg + ((int64_t)b * n_t + row) * (L.s[0] + L.s[1]);
+    __shared__ double red[32];
+    int kinds = L.s[0] + L.s[1];
+    for (int k = 0; k < kinds; ++k) {
+        int T = k >= L.s[0];
+        int st = T ? k - L.s[0] : k;
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < L.n[T]; i += blockDim.x)
+            acc += y[L.ref_of_plane[L.off[T] + st * L.n[T] + i]];
+        for (int o2 = 16; o2 > 0; o2 >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o2);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+            t = L.n[T] ? t / L.n[T] : 0.0;
+            o[k] = t > 0.0 ? t : 0.0;
+        }
+        __syncthreads();
+    }
+}

@@ -1,0 +1,203 @@
+"""`RateSystem`: one doped lattice resident on one B200 plus a batch of parameter sets.
+
+Thin Python owner of the opaque `stb_system` handle of the C ABI (`include/simetuc_b200.h`).
+It is what `precalculate.setup_microscopic_eqs` builds and what `odesolver.solve_pulse /
+solve_relax` drive; the reference has no such object because it rebuilds every matrix for
+every call (`simulations.py:1118,1214`).
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from .lattice import Lattice
+from .util import LatticeError, ion_code
+
+
+def pair_processes(energy_transfer) -> list:
+    """Two-ion processes of `cte.energy_transfer` in dict order (`precalculate.py:326-391`)."""
+    return [(name, p) for name, p in energy_transfer.items() if len(p.type) == 2]
+
+
+class RateSystem:
+    """Device-resident ET coupling of one lattice + per-system linear blocks and ET strengths."""
+
+    def __init__(self, lattice: Lattice, energy_transfer, device: int = 0,
+                 d_max: Optional[float] = None, geometry: str = 'auto'):
+        lib = _lib.require_gpu()
+        self.lib = lib
+        self.lattice = lattice
+        self.device = device
+        self.proc_names = [name for name, _ in pair_processes(energy_transfer)]
+        procs = [p for _, p in pair_processes(energy_transfer)]
+        if len(procs) > _lib.STB_MAX_PROC:
+            raise ValueError('too many energy transfer processes')
+        arr = (_lib.StbProcess * max(len(procs), 1))()
+        for k, p in enumerate(procs):
+            ii, fi, if_, ff = p.indices
+            arr[k] = _lib.StbProcess(ion_code(p.type[0]), ion_code(p.type[1]), ii, fi, if_, ff,
+                                     int(p.mult), 0, float(p.strength))
+        self._procs = arr
+        self.n_proc = len(procs)
+        ion_type = np.ascontiguousarray(lattice.ion_type, dtype=np.uint8)
+        use_dist = lattice.dist_array is not None if geometry == 'auto' else geometry == 'dist'
+        dist = pos = cell = None
+        if use_dist:
+            dist = _lib.f64(lattice.distances())
+        else:
+            pos = _lib.f64(lattice.positions)
+            cell = None if lattice.cell is None else _lib.f64(lattice.cell)
+        self.d_max = -1.0 if d_max is None else float(d_max)
+        self.handle = lib.stb_system_create(
+            device, len(ion_type), _lib.ptr(ion_type), lattice.n_S_states, lattice.n_A_states,
+            _lib.ptr(dist), _lib.ptr(pos), _lib.ptr(cell), self.d_max, self.n_proc,
+            C.cast(arr, C.c_void_p))
+        if not self.handle:
+            msg = _lib.last_error()
+            if 'states' in msg or 'process' in msg:
+                raise LatticeError(msg)
+            raise _lib.StbError(-1, msg)
+        info = (C.c_int64 * 8)()
+        _lib.check(lib.stb_system_info(self.handle, info))
+        (self.n_ions, self.n_S, self.n_A, self.N, self.n_pairs, self.stream_bytes,
+         self.n_slots, self.lanes_per_row) = [int(v) for v in info]
+        self.sS, self.sA = lattice.n_S_states, lattice.n_A_states
+        self.n_sys = 1
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.stb_system_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # pragma: no cover - interpreter shutdown
+            pass
+
+    # ------------------------------------------------------------------ lattice-side outputs
+    def ground_states(self):
+        """`(index_S_i, index_A_j, initial_population)` as `lattice.create_ground_states`."""
+        iS = np.empty(self.n_ions, dtype=np.int64)
+        iA = np.empty(self.n_ions, dtype=np.int64)
+        pop = np.empty(self.N, dtype=np.uint64)
+        _lib.check(self.lib.stb_ground_states(self.handle, _lib.ptr(iS), _lib.ptr(iA), _lib.ptr(pop)))
+        return iS, iA, pop
+
+    # ------------------------------------------------------------------ parameter batch
+    def set_batch(self, n_sys: int):
+        _lib.check(self.lib.stb_set_batch(self.handle, int(n_sys)))
+        self.n_sys = int(n_sys)
+
+    def _blk(self, blk, n):
+        if n == 0:
+            return None
+        if blk is None:
+            return np.zeros((n, n))
+        blk = _lib.f64(blk)
+        if blk.shape != (n, n):
+            raise ValueError('block must be %dx%d' % (n, n))
+        return blk
+
+    def set_decay_blocks(self, blk_S, blk_A, system: int = -1):
+        bS, bA = self._blk(blk_S, self.sS), self._blk(blk_A, self.sA)
+        _lib.check(self.lib.stb_set_blocks(self.handle, system, 0, _lib.ptr(bS), _lib.ptr(bA)))
+
+    def set_abs_blocks(self, blk_S, blk_A, system: int = -1):
+        bS, bA = self._blk(blk_S, self.sS), self._blk(blk_A, self.sA)
+        _lib.check(self.lib.stb_set_blocks(self.handle, system, 1, _lib.ptr(bS), _lib.ptr(bA)))
+
+    def set_strengths(self, strengths: Sequence[float], system: int = -1):
+        s = _lib.f64(strengths)
+        if s.shape != (self.n_proc,):
+            raise ValueError('need %d strengths' % self.n_proc)
+        rc = self.lib.stb_set_strengths(self.handle, system, _lib.ptr(s))
+        if rc != 0:
+            raise LatticeError(_lib.last_error())
+
+    # ------------------------------------------------------------------ reference-layout view
+    def num_interactions(self, system: int = 0) -> int:
+        m = self.lib.stb_num_interactions(self.handle, system)
+        if m < 0:
+            raise _lib.StbError(-1, _lib.last_error())
+        return int(m)
+
+    def export_interactions(self, system: int = 0, jac: bool = True):
+        """`(N_indices [M,2] u32, et_rows [M,4] i32, et_w [M] f64, jac_indices [2M,3] u32)` in the
+        reference's interaction order (`precalculate.py:349-392, 603-623`)."""
+        M = self.num_interactions(system)
+        N_idx = np.zeros((M, 2), dtype=np.uint32)
+        rows = np.zeros((M, 4), dtype=np.int32)
+        w = np.zeros(M, dtype=np.float64)
+        jac_idx = np.zeros((2 * M, 3), dtype=np.uint32) if jac else None
+        if M:
+            _lib.check(self.lib.stb_export_interactions(
+                self.handle, system, _lib.ptr(N_idx), _lib.ptr(rows), _lib.ptr(w), _lib.ptr(jac_idx)))
+        return N_idx, rows, w, jac_idx
+
+    def ET_matrix(self, system: int = 0):
+        """The reference's `ET_matrix [N, M]` CSR (`precalculate.py:410-412`) and `N_indices`,
+        `jac_indices`, assembled from the device export."""
+        N_idx, rows, w, jac_idx = self.export_interactions(system)
+        M = len(w)
+        if M == 0:
+            return (sp.csr_matrix((self.N, 0), dtype=np.float64),
+                    np.zeros((0, 2), dtype=np.uint32), np.zeros((0, 3), dtype=np.uint32))
+        vals = np.column_stack((-w, w, -w, w)).ravel()
+        cols = np.repeat(np.arange(M, dtype=np.int64), 4)
+        ET = sp.csr_matrix((vals, (rows.ravel().astype(np.int64), cols)), shape=(self.N, M),
+                           dtype=np.float64)
+        return ET, N_idx, jac_idx
+
+    # ------------------------------------------------------------------ operators
+    def _vecs(self, y, first, n):
+        y = _lib.f64(y)
+        if y.ndim == 1:
+            y = y[None, :]
+        if n is None:
+            n = y.shape[0]
+        if y.shape != (n, self.N):
+            raise ValueError('state array must be [%d, %d]' % (n, self.N))
+        return y, n
+
+    def rhs(self, y, pulse: bool, first: int = 0):
+        """`_rate_eq_pulse` (pulse) / `_rate_eq` for systems `first..first+len(y)`."""
+        single = np.ndim(y) == 1
+        y, n = self._vecs(y, first, None)
+        out = np.empty_like(y)
+        _lib.check(self.lib.stb_rhs(self.handle, first, n, int(bool(pulse)), _lib.ptr(y), _lib.ptr(out)))
+        return out[0] if single else out
+
+    def jv(self, y, v, pulse: bool, first: int = 0):
+        """`_jac_rate_eq[_pulse](y) @ v` without the dense Jacobian."""
+        single = np.ndim(y) == 1
+        y, n = self._vecs(y, first, None)
+        v, _ = self._vecs(v, first, n)
+        out = np.empty_like(y)
+        _lib.check(self.lib.stb_jv(self.handle, first, n, int(bool(pulse)), _lib.ptr(y), _lib.ptr(v),
+                                   _lib.ptr(out)))
+        return out[0] if single else out
+
+    def integrate(self, t, y0, pulse: bool, rtol: float = 1e-3, atol: float = 1e-15,
+                  nsteps: int = 1000, first: int = 0, want_y: bool = True, want_avg: bool = False):
+        """Integrate systems `first..first+n` over the output grid `t` (shared).  Returns
+        `(y_out [n, n_t, N] | None, avg [n, n_t, sS+sA] | None, stats list)`."""
+        t = _lib.f64(t).ravel()
+        y0, n = self._vecs(y0, first, None)
+        n_t = len(t)
+        y_out = np.zeros((n, n_t, self.N)) if want_y else None
+        avg = np.zeros((n, n_t, self.sS + self.sA)) if want_avg else None
+        stats = (_lib.StbStats * n)()
+        _lib.check(self.lib.stb_integrate(
+            self.handle, first, n, int(bool(pulse)), n_t, _lib.ptr(t), _lib.ptr(y0), float(rtol),
+            float(atol), int(nsteps), _lib.ptr(y_out), _lib.ptr(avg), C.cast(stats, C.c_void_p)))
+        return y_out, avg, [s.as_dict() for s in stats]
+
+    def last_timing(self):
+        ms = C.c_float()
+        launches = C.c_int64()
+        _lib.check(self.lib.stb_last_timing(self.handle, C.byref(ms), C.byref(launches)))
+        return float(ms.value), int(launches.value)

@@ -1,0 +1,192 @@
+"""Equation setup for the microscopic rate equations - host mirror of
+`simetuc/precalculate.py`.
+
+The per-ion-type absorption and decay blocks (`precalculate.py:79-230`) are tiny (at most
+16x16) and are computed here on the host; the O(n_ions^2) part - the interaction lists of
+`lattice.create_interaction_matrices` and the pair rates of `_create_ET_matrices`
+(`precalculate.py:235-415`) - is built on the device by `RateSystem`.
+`setup_microscopic_eqs` keeps the reference's signature and 12-tuple; the sparse matrices it
+returns are materialised from the device export for API compatibility and carry a reference to
+the device-resident `RateSystem`, which `odesolver.solve_pulse / solve_relax` use directly.
+"""
+import logging
+import os
+import time
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import lattice as lattice_mod
+from .engine import RateSystem
+from .lattice import Lattice
+from .util import LatticeError, ion_code
+
+# in-memory lattice cache: the reference caches lattices on disk under latticeData/
+# (`lattice.py:377-385`, `precalculate.py:755-791`)
+_LATTICE_CACHE: Dict[Tuple, Lattice] = {}
+_SYSTEM_CACHE: Dict[Tuple, RateSystem] = {}
+
+
+def absorption_blocks(cte) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-type absorption blocks (already multiplied by the power density), summed over the
+    processes of every active excitation (`precalculate.py:79-127`)."""
+    nS, nA = cte['states']['sensitizer_states'], cte['states']['activator_states']
+    blocks = [np.zeros((nS, nS)), np.zeros((nA, nA))]
+    for exc_list in cte['excitations'].values():
+        for exc in exc_list:
+            if exc.active is False:
+                continue
+            t = ion_code(exc.transition.ion)
+            n = (nS, nA)[t]
+            i, f = exc.transition.state_i, exc.transition.state_f
+            if n == 0 or i >= n or f >= n:
+                continue
+            one = np.zeros((n, n))
+            one[i, i] = -exc.pump_rate
+            one[i, f] = exc.degeneracy * exc.pump_rate
+            one[f, i] = exc.pump_rate
+            one[f, f] = -exc.degeneracy * exc.pump_rate
+            blocks[t] = blocks[t] + one * exc.power_dens
+    return blocks[0], blocks[1]
+
+
+def decay_blocks(cte) -> Tuple[Optional[np.ndarray], Optional[np.ndarray]]:
+    """Per-type decay blocks `(B^T - I) diag(k)` with row 0 = -column sums
+    (`precalculate.py:130-213`; branching to the ground state dropped `:153-156`)."""
+    nS, nA = cte['states']['sensitizer_states'], cte['states']['activator_states']
+    decay = cte['decay']
+    out = []
+    for t, n, bkey, kkey in ((0, nS, 'branching_S', 'decay_S'), (1, nA, 'branching_A', 'decay_A')):
+        if n == 0:
+            out.append(None)
+            continue
+        B = np.zeros((n, n))
+        for tr in decay[bkey]:
+            # the reference's activator check tests state_i twice (`precalculate.py:146`)
+            inside = (tr.state_i < n and tr.state_f < n) if t == 0 else tr.state_i < n
+            if inside:
+                B[tr.state_i, tr.state_f] = tr.branching_ratio
+        B[:, 0] = 0.0
+        k = np.zeros(n)
+        for tr in decay[kkey]:
+            if tr.state_i < n:
+                k[tr.state_i] = tr.decay_rate
+        D = (B.T - np.eye(n)) * k[None, :]
+        D[0, :] = -D.sum(axis=0)
+        out.append(D)
+    return out[0], out[1]
+
+
+def get_lifetimes(cte) -> List[float]:
+    """All lifetimes in seconds (`precalculate.py:702-709`)."""
+    return [1 / float(tr.decay_rate) for tr in list(cte['decay']['decay_S']) + list(cte['decay']['decay_A'])]
+
+
+def _block_diag(block_S, block_A, index_S_i, index_A_j):
+    blocks = []
+    for s, a in zip(index_S_i, index_A_j):
+        if s != -1 and block_S is not None and block_S.size:
+            blocks.append(sp.csr_matrix(block_S))
+        elif s == -1 and a != -1 and block_A is not None and block_A.size:
+            blocks.append(sp.csr_matrix(block_A))
+    if not blocks:
+        return sp.csr_matrix((0, 0), dtype=np.float64)
+    return sp.block_diag(blocks, format='csr', dtype=np.float64)
+
+
+def _lattice_key(cte):
+    lat = cte['lattice']
+    return (lat.get('name'), int(lat['N_uc']), float(lat['S_conc']), float(lat['A_conc']),
+            lat.get('radius'), cte['states']['sensitizer_states'],
+            cte['states']['activator_states'], cte.get('lattice_seed'))
+
+
+def get_lattice(cte, gen_lattice: bool = False, full_path: Optional[str] = None) -> Lattice:
+    """Lattice for `cte`: a file written by `Lattice.save` (`full_path`), the in-memory cache,
+    or a fresh realisation (`gen_lattice=True` or cache miss) seeded by `cte['lattice_seed']`."""
+    if full_path is not None:
+        if not os.path.exists(full_path):
+            raise FileNotFoundError(full_path)
+        lat = Lattice.load(full_path)
+        cte['states']['sensitizer_states'] = lat.n_S_states
+        cte['states']['activator_states'] = lat.n_A_states
+        return lat
+    key = _lattice_key(cte)
+    if gen_lattice or key not in _LATTICE_CACHE:
+        _LATTICE_CACHE[key] = lattice_mod.generate(cte, seed=cte.get('lattice_seed'))
+    return _LATTICE_CACHE[key]
+
+
+def check_process_states(cte):
+    """`precalculate.py:325-345`: an active pair process naming more states than exist raises
+    `LatticeError` (the reference compares with `>`; so does this)."""
+    nS, nA = cte['states']['sensitizer_states'], cte['states']['activator_states']
+    count = {0: nS, 1: nA}
+    for name, p in cte['energy_transfer'].items():
+        if len(p.type) != 2 or np.isclose(p.strength, 0.0):
+            continue
+        ii, fi, if_, ff = p.indices
+        d, a = ion_code(p.type[0]), ion_code(p.type[1])
+        if max(ii, if_) > count[d] or max(fi, ff) > count[a]:
+            raise LatticeError('The number of A or S states is lower than required by '
+                               'process {}.'.format(name))
+
+
+def build_system(cte, lat: Lattice, device: int = 0, d_max: Optional[float] = None,
+                 n_sys: int = 1) -> RateSystem:
+    """Device-resident system for `lat` with `cte`'s processes; every system of the batch gets
+    `cte`'s decay and absorption blocks."""
+    check_process_states(cte)
+    system = RateSystem(lat, cte['energy_transfer'], device=device, d_max=d_max)
+    system.set_batch(n_sys)
+    system.set_decay_blocks(*decay_blocks(cte))
+    system.set_abs_blocks(*absorption_blocks(cte))
+    return system
+
+
+def setup_microscopic_eqs(cte, gen_lattice: bool = False, full_path: Optional[str] = None,
+                          device: int = 0):
+    """Same contract as the reference (`precalculate.py:713-878`): returns
+    `(cte, initial_population, index_S_i, index_A_j, total_abs_matrix, decay_matrix, ET_matrix,
+    N_indices, jac_indices, coop_ET_matrix, coop_N_indices, coop_jac_indices)`.
+    The matrices carry `.stb = (RateSystem, system_index)`."""
+    logger = logging.getLogger(__name__)
+    start = time.time()
+    lat = get_lattice(cte, gen_lattice=gen_lattice, full_path=full_path)
+    cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
+    cte['states']['energy_states'] = lat.n_states
+    for name, p in cte['energy_transfer'].items():
+        if len(p.type) == 3 and not np.isclose(p.strength, 0.0):
+            raise NotImplementedError('cooperative (three-ion) energy transfer process %s: '
+                                      'not yet on the device path' % name)
+    key = (id(lat), tuple((n, p.indices, p.mult) for n, p in cte['energy_transfer'].items()
+                          if len(p.type) == 2), device)
+    system = _SYSTEM_CACHE.get(key)
+    if system is None or system.handle is None:
+        check_process_states(cte)
+        system = RateSystem(lat, cte['energy_transfer'], device=device)
+        _SYSTEM_CACHE.clear()          # one resident lattice per process is enough here
+        _SYSTEM_CACHE[key] = system
+    check_process_states(cte)
+    system.set_batch(1)
+    dS, dA = decay_blocks(cte)
+    aS, aA = absorption_blocks(cte)
+    system.set_decay_blocks(dS, dA)
+    system.set_abs_blocks(aS, aA)
+    system.set_strengths([p.strength for n, p in cte['energy_transfer'].items() if len(p.type) == 2]
+                         or np.zeros(0))
+    index_S_i, index_A_j, initial_population = system.ground_states()
+    total_abs_matrix = _block_diag(aS, aA, index_S_i, index_A_j)
+    decay_matrix = _block_diag(dS, dA, index_S_i, index_A_j)
+    ET_matrix, N_indices, jac_indices = system.ET_matrix(0)
+    N = system.N
+    coop_ET_matrix = sp.csr_matrix((N, 0), dtype=np.float64)
+    coop_N_indices = np.zeros((0, 3), dtype=np.uint32)
+    coop_jac_indices = np.zeros((0, 4), dtype=np.uint32)
+    for m in (total_abs_matrix, decay_matrix, ET_matrix):
+        m.stb = (system, 0)
+    logger.info('Setup finished. Total time: %.2fs.', time.time() - start)
+    return (cte, initial_population, list(index_S_i), list(index_A_j), total_abs_matrix,
+            decay_matrix, ET_matrix, N_indices, jac_indices, coop_ET_matrix, coop_N_indices,
+            coop_jac_indices)

@@ -1,0 +1,249 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the
+C ABI, against the oracle and the reference's golden vectors.
+
+Tolerances (SURVEY.md 8d parity protocol, north_star):
+  * integer lists (index_S_i, index_A_j, initial_population, N_indices, jac_indices, ET rows):
+    bit-exact;
+  * pair rates w = strength * d^-mult: relative 1e-14 (CUDA pow vs glibc pow, <= 2 ulp);
+  * RHS / Jv: |delta| <= 1e-12 * max|ref|;
+  * trajectories: |delta| <= 1e-4 * |ref| + 1e-12 against scipy LSODA at rtol 1e-8, atol 1e-15.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from simetuc_b200 import configs, lattice, precalculate
+from simetuc_b200.engine import RateSystem
+from simetuc_b200.lattice import Lattice
+from tests.helpers import GOLDEN, SMALL, load_golden, oracle_operands, pair_processes
+
+pytestmark = pytest.mark.gpu
+
+
+def make_system(g, cte, **kw):
+    lat = Lattice.from_arrays(g['ion_type'], g['dist_array'], int(g['info'][0]), int(g['info'][1]),
+                              positions=g.get('doped_lattice'))
+    et = dict(pair_processes(cte))
+    system = RateSystem(lat, et, **kw)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    return system
+
+
+def parity_metric(y, ref):
+    return float(np.max(np.abs(y - ref) / (1e-4 * np.abs(ref) + 1e-12)))
+
+
+@pytest.mark.parametrize('tag', SMALL + ['240S_108A'])
+@pytest.mark.parametrize('pname', ['test', 'sim'])
+def test_pair_lists_bit_exact(tag, pname):
+    g = load_golden(tag)
+    cte = getattr(configs, pname + '_cte')()
+    op = oracle_operands(g, cte)
+    system = make_system(g, cte)
+    iS, iA, pop = system.ground_states()
+    assert np.array_equal(iS, op['index_S_i']) and np.array_equal(iA, op['index_A_j'])
+    assert np.array_equal(pop, op['initial_population']) and pop.dtype == np.uint64
+    N_idx, rows, w, jac = system.export_interactions()
+    assert N_idx.dtype == np.uint32 and np.array_equal(N_idx, op['N_indices'])
+    assert np.array_equal(jac, op['jac_indices'])
+    ET, _, _ = system.ET_matrix()
+    ref = op['ET'].tocsr()
+    assert ET.shape == ref.shape
+    if ref.shape[1]:
+        diff = abs(ET - ref)
+        assert diff.max() <= 1e-14 * abs(ref).max()
+        refc = ref.tocsc()
+        refc.sort_indices()
+        # per-interaction rate: column r holds (-w, +w, -w, +w)
+        w_ref = np.abs(refc.data.reshape(-1, 4)).max(axis=1) if np.all(np.diff(refc.indptr) == 4) else None
+        if w_ref is not None:
+            assert np.all(np.abs(w - w_ref) <= 1e-14 * w_ref)
+    system.close()
+
+
+@pytest.mark.parametrize('tag', SMALL + ['240S_108A'])
+@pytest.mark.parametrize('pname', ['test', 'sim'])
+def test_rhs_and_jv(tag, pname):
+    g = load_golden(tag)
+    cte = getattr(configs, pname + '_cte')()
+    system = make_system(g, cte)
+    system.set_batch(3)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    y, v = g[pname + '_y'], g[pname + '_v']
+    for pulse, key in ((True, '_f_pulse'), (False, '_f_relax')):
+        f = system.rhs(y, pulse=pulse)
+        ref = g[pname + key]
+        assert np.all(np.abs(f - ref) <= 1e-12 * np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+    jv = system.jv(y, v, pulse=True)
+    ref = g[pname + '_jv_pulse']
+    assert np.all(np.abs(jv - ref) <= 1e-12 * np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+    # single-vector call, system 1 of the batch
+    f1 = system.rhs(y[1], pulse=True, first=1)
+    assert np.array_equal(f1, system.rhs(y, pulse=True)[1])
+    system.close()
+
+
+def test_golden_trajectory_2S_2A():
+    """The reference's `test_sim_dyn_2S_2A` (`test_simulations.py:76-91`) through the CUDA
+    integrator: np.allclose to the shipped golden trajectory at the golden's own tolerances."""
+    g = load_golden('sim_2S_2A')
+    cte = configs.sim_cte()
+    system = make_system(g, cte)
+    with np.load(os.path.join(GOLDEN, 'sol_2S_2A.npz')) as z:
+        t_gold, y_gold = z['t_sol'], z['y_sol']
+    tf = onp.t_simulation(cte['decay'])
+    t_pulse, t_sol = onp.time_grids(1e-8, tf, 1000)
+    _, _, pop = system.ground_states()
+    y_p, _, st_p = system.integrate(t_pulse, pop.astype(float), pulse=True, rtol=1e-3, atol=1e-15)
+    y, _, st = system.integrate(t_sol, y_p[0, -1], pulse=False, rtol=1e-3, atol=1e-15)
+    assert st_p[0]['status'] == 0 and st[0]['status'] == 0 and st[0]['n_out'] == 1000
+    assert np.array_equal(y_p[0, 0], pop.astype(float))          # row 0 verbatim
+    assert np.allclose(t_sol - t_sol[0], t_gold)
+    assert np.allclose(y[0], y_gold)
+    system.close()
+
+
+def _solve_both(g, cte, t_pulse_w, n_steps, rtol=1e-8, atol=1e-15):
+    op = oracle_operands(g, cte)
+    system = make_system(g, cte)
+    tf = onp.t_simulation(cte['decay'])
+    t_pulse, t_sol = onp.time_grids(t_pulse_w, tf, n_steps)
+    y0 = op['initial_population'].astype(float)
+    y_p, _, st_p = system.integrate(t_pulse, y0, pulse=True, rtol=rtol, atol=atol)
+    y, avg, st = system.integrate(t_sol, y_p[0, -1], pulse=False, rtol=rtol, atol=atol, want_avg=True)
+    kw = dict(rtol=rtol, atol=atol, nsteps=100000)
+    yp_ref = onp.solve_pulse(t_pulse, y0, op['abs'], op['decay'], op['ET'], op['N_indices'],
+                             op['jac_indices'], **kw)
+    y_ref = onp.solve_relax(t_sol, yp_ref[-1], op['decay'], op['ET'], op['N_indices'],
+                            op['jac_indices'], **kw)
+    system.close()
+    return op, (y_p[0], y[0], avg[0], st_p[0], st[0]), (yp_ref, y_ref)
+
+
+def test_trajectory_vs_lsoda_small():
+    g = load_golden('sim_2S_2A')
+    cte = configs.sim_cte()
+    op, (y_p, y, avg, st_p, st), (yp_ref, y_ref) = _solve_both(g, cte, 1e-8, 1000)
+    assert st['status'] == 0 and st_p['status'] == 0
+    assert parity_metric(y_p[-1], yp_ref[-1]) <= 1.0
+    assert parity_metric(y, y_ref) <= 1.0
+    # per-ion populations are conserved (columns of every operator sum to zero)
+    assert np.allclose(y[:, 0:7].sum(axis=1), 1.0, atol=1e-9)
+    avg_ref = onp.avg_populations(y_ref, op['index_S_i'], op['index_A_j'], 2, 7).T
+    big = avg_ref > 1e-9
+    assert np.all(np.abs(avg - avg_ref)[big] <= 1e-4 * avg_ref[big])
+
+
+def test_trajectory_vs_lsoda_yb_tm():
+    """Yb-Tm dynamics (config 1 shape at reduced size): 980 nm pulse then relaxation."""
+    cte = configs.yb_tm_cte(N_uc=8, S_conc=10.0, A_conc=1.0, power_dens=1e7)
+    lat = lattice.generate_arrays(cte, seed=1000)
+    g = {'ion_type': lat['ion_type'], 'dist_array': lat['dist_array'], 'info': np.array([2, 9]),
+         'doped_lattice': lat['doped_lattice']}
+    op, (y_p, y, avg, st_p, st), (yp_ref, y_ref) = _solve_both(g, cte, 1e-8, 200)
+    assert st['status'] == 0 and st_p['status'] == 0
+    assert parity_metric(y_p[-1], yp_ref[-1]) <= 1.0
+    assert parity_metric(y, y_ref) <= 1.0
+    avg_ref = onp.avg_populations(y_ref, op['index_S_i'], op['index_A_j'], 2, 9).T
+    big = avg_ref > 1e-9
+    assert np.all(np.abs(avg - avg_ref)[big] <= 1e-4 * avg_ref[big])
+
+
+def test_batch_power_sweep_matches_single():
+    """Systems of a batch are independent: a 4-power batch equals 4 single solves, and the
+    steady-state populations grow with power."""
+    cte = configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=2.0, t_pulse=None)
+    lat = lattice.generate(cte, seed=1001, with_distances=True)
+    powers = [1e2, 1e4, 1e6, 1e8]
+    system = precalculate.build_system(cte, lat, n_sys=len(powers))
+    for k, P in enumerate(powers):
+        for exc in cte['excitations']['NIR_980']:
+            exc.power_dens = P
+        system.set_abs_blocks(*precalculate.absorption_blocks(cte), system=k)
+    _, _, pop = system.ground_states()
+    t = np.linspace(0, onp.t_simulation(cte['decay']), 50)
+    y0 = np.tile(pop.astype(float), (len(powers), 1))
+    y_b, avg_b, st_b = system.integrate(t, y0, pulse=True, rtol=1e-8, atol=1e-15, want_avg=True)
+    assert all(s['status'] == 0 for s in st_b)
+    for k in (0, 3):
+        y_1, _, st_1 = system.integrate(t, y0[k], pulse=True, rtol=1e-8, atol=1e-15, first=k)
+        assert np.array_equal(y_1[0], y_b[k])
+    assert np.all(np.diff(avg_b[:, -1, 1]) > 0)       # Yb excited-state population vs power
+    system.close()
+
+
+def test_positions_route_matches_distance_route():
+    cte = configs.yb_tm_cte(N_uc=7, S_conc=15.0, A_conc=2.0)
+    lat = lattice.generate(cte, seed=7, with_distances=True)
+    et = dict(pair_processes(cte))
+    a = RateSystem(lat, et, geometry='dist')
+    b = RateSystem(lat, et, geometry='positions')
+    Na, ra, wa, _ = a.export_interactions()
+    Nb, rb, wb, _ = b.export_interactions()
+    assert np.array_equal(Na, Nb) and np.array_equal(ra, rb)
+    assert np.all(np.abs(wa - wb) <= 1e-13 * wa)
+    a.close()
+    b.close()
+
+
+def test_cutoff_neighbour_lists():
+    """d_max > 0 applies the cutoff the reference parses but never uses (settings.py:35): the
+    result must equal the oracle fed with the same filtered lists."""
+    cte = configs.yb_tm_cte(N_uc=7, S_conc=15.0, A_conc=2.0)
+    lat = lattice.generate(cte, seed=8, with_distances=True)
+    d_max = 12.0
+    et = dict(pair_processes(cte))
+    system = RateSystem(lat, et, d_max=d_max)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    dist = np.where(lat.dist_array <= d_max, lat.dist_array, 0.0)
+    g = {'ion_type': lat.ion_type, 'dist_array': dist, 'info': np.array([2, 9])}
+    op = oracle_operands(g, cte)
+    N_idx, _, _, _ = system.export_interactions()
+    assert np.array_equal(N_idx, op['N_indices'])
+    rng = np.random.default_rng(5)
+    y = rng.random(op['N'])
+    cM, cN, _ = op['coop']
+    ref = onp.rate_eq_pulse(0.0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], cM, cN)
+    f = system.rhs(y, pulse=True)
+    assert np.all(np.abs(f - ref) <= 1e-12 * np.abs(ref).max())
+    system.close()
+
+
+def test_errors():
+    from simetuc_b200.util import LatticeError
+    g = load_golden('2S_2A')
+    cte = configs.test_cte()
+    lat = Lattice.from_arrays(g['ion_type'], g['dist_array'], 2, 4)     # Tm with only 4 states
+    with pytest.raises(LatticeError):
+        RateSystem(lat, dict(pair_processes(cte)))
+    system = make_system(g, cte)
+    with pytest.raises(Exception):
+        system.rhs(np.zeros((5, system.N)), pulse=True)      # outside the batch
+    with pytest.raises(Exception):
+        system.integrate([0.0, 0.0], np.zeros(system.N), pulse=True)
+    system.close()
+
+
+def test_group_sizes_agree(monkeypatch):
+    """The integrator splits the grid into groups of G CTAs per system; results must not depend
+    on G beyond round-off of the reduction order (and G > 1 exercises the group barrier)."""
+    g = load_golden('240S_108A')
+    cte = configs.test_cte()
+    system = make_system(g, cte)
+    _, _, pop = system.ground_states()
+    t = np.array([0.0, 1e-8])
+    res = {}
+    for G in (1, 4, 16):
+        monkeypatch.setenv('STB_GROUP_CTAS', str(G))
+        y, _, st = system.integrate(t, pop.astype(float), pulse=True, rtol=1e-8, atol=1e-15)
+        assert st[0]['status'] == 0
+        res[G] = y[0, -1]
+    monkeypatch.delenv('STB_GROUP_CTAS')
+    for G in (4, 16):
+        assert np.all(np.abs(res[G] - res[1]) <= 1e-9 * np.abs(res[1]) + 1e-18)
+    system.close()
