@@ -33,7 +33,7 @@ extern "C" {
 #define STB_ENOMEM (-3)
 #define STB_ESTATE (-4)   /* call made in the wrong order (e.g. batch not set) */
 
-#define STB_MAX_STATES 16 /* states per ion type */
+#define STB_MAX_STATES 12 /* states per ion type */
 #define STB_MAX_PROC 32   /* pair ET processes */
 
 /* One pair energy-transfer process: util.py:235-292 (EneryTransferProcess).
@@ -165,6 +165,12 @@ int stb_integrate(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int6
 /* Device time (ms, CUDA events) of the last stb_integrate call's kernels, and the number of
  * kernel launches it made. */
 int stb_last_timing(const stb_system* sys, float* ms, int64_t* launches);
+
+/* Development aid: clock64 cycles per integrator phase of the last stb_integrate call (summed
+ * over systems): [0] RHS passes, [1] Krylov operator passes, [2] Krylov dot products,
+ * [3] group barriers / reductions, [4] vector updates, [5] Givens, [7] rest;
+ * out[8] = CTAs per group, out[9] = groups. */
+int stb_last_profile(const stb_system* sys, double out[10]);
 
 #ifdef __cplusplus
 }

@@ -7,9 +7,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsimetuc_b200.so')
+LIB_PATH = os.environ.get('STB_LIB') or os.path.join(_HERE, 'libsimetuc_b200.so')
 
-STB_MAX_STATES = 16
+STB_MAX_STATES = 12
 STB_MAX_PROC = 32
 
 
@@ -33,7 +33,7 @@ EXPORTS = ['stb_last_error', 'stb_device_count', 'stb_describe', 'stb_system_cre
            'stb_system_destroy', 'stb_system_info', 'stb_ground_states', 'stb_set_batch',
            'stb_set_blocks', 'stb_set_strengths', 'stb_num_interactions',
            'stb_export_interactions', 'stb_rhs', 'stb_jv', 'stb_rhs_dev', 'stb_jv_dev',
-           'stb_to_planes', 'stb_from_planes', 'stb_integrate', 'stb_last_timing']
+           'stb_to_planes', 'stb_from_planes', 'stb_integrate', 'stb_last_timing', 'stb_last_profile']
 
 _lib = None
 
@@ -85,6 +85,7 @@ def load():
     lib.stb_integrate.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int64, P, P,
                                   C.c_double, C.c_double, C.c_int64, P, P, P]
     lib.stb_last_timing.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+    lib.stb_last_profile.argtypes = [P, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 

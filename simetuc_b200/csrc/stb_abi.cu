@@ -58,6 +58,7 @@ struct stb_system {
     double* d_g[2][2][STB_MAXM] = {};
     int64_t* d_line_ptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int64_t pairs = 0, slots = 0, stream_bytes = 0;
+    std::vector<int64_t> h_line_ptr[2][2];
     // batch
     int n_sys = 0;
     std::vector<double> h_blocks, h_strengths;
@@ -67,6 +68,8 @@ struct stb_system {
     double *d_y = nullptr, *d_v = nullptr, *d_out = nullptr, *d_F = nullptr, *d_tmp = nullptr;
     int64_t scratch_n = 0;
     float last_ms = 0.f;
+    std::vector<long long> last_prof;
+    int last_G = 0, last_groups = 0;
     int64_t last_launches = 0;
     int sm_count = 148;
 };
@@ -216,7 +219,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     }
     if (n_S_states < 0 || n_A_states < 0 || n_S_states > STB_MAX_STATES ||
         n_A_states > STB_MAX_STATES) {
-        fail(STB_EINVAL, "states per ion must be in [0, 16]");
+        fail(STB_EINVAL, "states per ion must be in [0, 12]");
         return nullptr;
     }
     if (n_proc < 0 || n_proc > STB_MAX_PROC) { fail(STB_EINVAL, "too many processes"); return nullptr; }
@@ -354,6 +357,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
                 lp[sl + 1] = lp[sl] + (used ? w : 0);
             }
             int64_t lines = lp.back();
+            S->h_line_ptr[T][U] = lp;
             CKP(upload(&S->d_line_ptr[T][U], lp));
             size_t slots = std::max<int64_t>(lines * 32, 1);
             CKP(cudaMalloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
@@ -750,27 +754,66 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
     const int NMinv = L.s[0] * L.s[0] * L.n[0] + L.s[1] * L.s[1] * L.n[1];
 
     // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate, STB_NT, 0));
-    if (occ < 1) return fail(STB_ECUDA, "integrator kernel does not fit on an SM");
+    // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
     const int max_ctas = S->sm_count;   // one CTA per SM
     const int total_slices = L.n_slices[0] + L.n_slices[1];
     // a CTA wants at least ~2 slices per warp; never more CTAs per group than that allows
     int G_work = std::max(1, total_slices / (2 * STB_NW));
     int G = std::max(1, std::min(max_ctas / std::min(n, max_ctas), G_work));
-    if (const char* env = getenv("STB_GROUP_CTAS")) G = std::max(1, std::min(atoi(env), max_ctas));
+    // small systems: the gathered vector is staged in shared memory and barriers leave L1 warm;
+    // if, with a few more CTAs per group, every CTA's own pair rows also fit in shared memory,
+    // they are made resident there (the Krylov loop then runs out of shared memory)
+    const size_t smem_cap = 200 * 1024;
+    size_t stage_bytes = sizeof(double) * (size_t)N;
+    int staged = stage_bytes <= 96 * 1024;
+    if (const char* env = getenv("STB_STAGE")) staged = atoi(env) != 0 && stage_bytes <= 160 * 1024;
+    int resident = 0;
+    size_t dyn_bytes = staged ? stage_bytes : 0;
+    auto own_bytes = [&](int Gc) -> size_t {     // largest resident footprint of a CTA in a group of Gc
+        size_t worst = 0;
+        for (int c = 0; c < Gc; ++c) {
+            size_t b = 0;
+            for (int T = 0; T < 2; ++T) {
+                int lo = (int)(((int64_t)L.n_slices[T] * c) / Gc), hi = (int)(((int64_t)L.n_slices[T] * (c + 1)) / Gc);
+                for (int U = 0; U < 2; ++U) {
+                    if (!L.blk[T][U].n_slots) continue;
+                    const std::vector<int64_t>& lp = S->h_line_ptr[T][U];
+                    b += (size_t)(lp[hi] - lp[lo]) * 32 * 12;
+                }
+                b += (size_t)(hi - lo + 1) * 8 * 2;
+            }
+            worst = std::max(worst, b);
+        }
+        return worst;
+    };
+    bool want_resident = staged && L.n_mult == 1;
+    if (const char* env = getenv("STB_RESIDENT")) want_resident = want_resident && atoi(env) != 0;
+    if (const char* env = getenv("STB_GROUP_CTAS")) {
+        G = std::max(1, std::min(atoi(env), max_ctas));
+        if (want_resident && stage_bytes + own_bytes(G) + 64 <= smem_cap) resident = 1;
+    } else if (want_resident) {
+        // measured (profiles/r01_integrator_notes.md): widening the group just to become
+        // resident costs more concurrency than it gains, so residency is used when it is free
+        if (stage_bytes + own_bytes(G) + 64 <= smem_cap) resident = 1;
+    }
+    if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64;
     int n_groups = std::max(1, std::min(max_ctas / G, n));
     const int grid = n_groups * G;
+    CK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate, STB_NT, dyn_bytes));
+    if (occ < 1) return fail(STB_ECUDA, "integrator kernel does not fit on an SM");
 
     const int64_t work_stride = stb_work_doubles(N, L.NF, NMinv);
     double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_part = nullptr,
            *d_tmp = nullptr, *d_avg = nullptr;
     unsigned long long* d_bar = nullptr;
     stb_stats* d_stats = nullptr;
+    long long* d_prof = nullptr;
     size_t out_bytes = sizeof(double) * (size_t)n * n_t * N;
     auto cleanup = [&]() {
         cudaFree(d_work); cudaFree(d_y0); cudaFree(d_yout); cudaFree(d_t); cudaFree(d_part);
-        cudaFree(d_tmp); cudaFree(d_avg); cudaFree(d_bar); cudaFree(d_stats);
+        cudaFree(d_tmp); cudaFree(d_avg); cudaFree(d_bar); cudaFree(d_stats); cudaFree(d_prof);
     };
 #define CKI(call)                                                                     \
     do {                                                                              \
@@ -789,6 +832,8 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
     CKI(cudaMalloc((void**)&d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED));
     CKI(cudaMalloc((void**)&d_bar, sizeof(unsigned long long) * n_groups));
     CKI(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
+    CKI(cudaMalloc((void**)&d_prof, sizeof(long long) * 8 * n));
+    CKI(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * n, S->stream));
     CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * n_groups, S->stream));
     CKI(cudaMemsetAsync(d_yout, 0, out_bytes, S->stream));
     CKI(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
@@ -805,13 +850,14 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
     A.n_t = n_t; A.t = d_t; A.y0 = d_y0; A.rtol = rtol; A.atol = atol;
     A.nsteps = nsteps > 0 ? nsteps : 1000;
     A.y_out = d_yout; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
-    A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv;
+    A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
+    S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0, e1;
     CKI(cudaEventCreate(&e0));
     CKI(cudaEventCreate(&e1));
     CKI(cudaEventRecord(e0, S->stream));
     void* kargs[] = {&A};
-    CKI(cudaLaunchCooperativeKernel((void*)k_integrate, dim3(grid), dim3(STB_NT), kargs, 0, S->stream));
+    CKI(cudaLaunchCooperativeKernel((void*)k_integrate, dim3(grid), dim3(STB_NT), kargs, dyn_bytes, S->stream));
     CKI(cudaEventRecord(e1, S->stream));
     S->last_launches = 1;
     if (avg_out) {
@@ -823,6 +869,8 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
                             cudaMemcpyDeviceToHost, S->stream));
     }
     if (y_out) CKI(cudaMemcpyAsync(y_out, d_yout, out_bytes, cudaMemcpyDeviceToHost, S->stream));
+    S->last_prof.assign((size_t)8 * n, 0);
+    CKI(cudaMemcpyAsync(S->last_prof.data(), d_prof, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost, S->stream));
     if (stats) CKI(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
     CKI(cudaStreamSynchronize(S->stream));
     CKI(cudaEventElapsedTime(&S->last_ms, e0, e1));
@@ -836,5 +884,18 @@ extern "C" int stb_last_timing(const stb_system* S, float* ms, int64_t* launches
     if (!S) return fail(STB_EINVAL, "null system");
     if (ms) *ms = S->last_ms;
     if (launches) *launches = S->last_launches;
+    return STB_OK;
+}
+
+// Development aid: per-phase clock64 cycles of the last stb_integrate call, summed over its
+// systems: [0] RHS passes, [1] Arnoldi operator passes, [2] Krylov dot products, [3] group
+// barriers / reductions, [4] vector updates, [5] Givens, [7] rest; out[8] = CTAs per group,
+// out[9] = groups.
+extern "C" int stb_last_profile(const stb_system* S, double out[10]) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    for (int k = 0; k < 10; ++k) out[k] = 0.0;
+    for (size_t i = 0; i < S->last_prof.size(); ++i) out[i % 8] += (double)S->last_prof[i];
+    out[8] = S->last_G;
+    out[9] = S->last_groups;
     return STB_OK;
 }

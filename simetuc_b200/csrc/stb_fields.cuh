@@ -11,115 +11,174 @@
 #pragma once
 #include "stb_common.cuh"
 
+// Pair data is read exactly once per pass: bypass L1 (it is needed for the gathered state
+// vector) and keep the default L2 policy (small lattices stay L2-resident across passes).
+#ifndef STB_LD_V
+#define STB_LD_V 2
+#endif
+#if STB_LD_V == 1
 __device__ __forceinline__ double ld_stream(const double* p) { return __ldcs(p); }
 __device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) { return __ldcs(p); }
+#else
+__device__ __forceinline__ double ld_stream(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* p) {
+    uint32_t v;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#endif
 
-template <int NS, int NM>
+#ifndef STB_STREAM_V
+#define STB_STREAM_V 2
+#endif
+#ifndef STB_UN_KERNEL
+#define STB_UN_KERNEL 16  // lines in flight per lane, standalone RHS / Jv kernels (HBM-bound)
+#endif
+#ifndef STB_UN_INT
+#define STB_UN_INT 4      // ... inside the persistent integrator
+#endif
+
+// One multipolarity (the common case): NS field slots, accumulators in registers.
+template <class T_>
+__device__ __forceinline__ T_ ld_pair(const T_* p, bool nc) { return nc ? ld_stream(p) : *p; }
+
+// NC = true: pair data in global memory, read through the non-allocating path;
+// NC = false: generic loads (the pair data of the CTA's rows is resident in shared memory).
+template <int NS, int STB_UN, bool NC>
 __device__ __forceinline__ void stream_block_t(const PairBlock& B, int nU, const double* zU,
                                                int64_t l0, int64_t l1, int lane,
                                                double (&acc)[STB_MAXC]) {
-    int sc[NS], sm[NS];
+    int sc[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        sc[s] = B.slot_col[s] * nU;
-        sm[s] = B.slot_mult[s];
-    }
-    const uint32_t* col = B.col;
-    const double* g0p = B.g[0];
-    const double* g1p = (NM > 1 && B.g[1]) ? B.g[1] : B.g[0];
-    const double* g2p = (NM > 2 && B.g[2]) ? B.g[2] : B.g[0];
+    for (int s = 0; s < NS; ++s) sc[s] = B.slot_col[s] * nU;
+    const uint32_t* col = B.col + lane;
+    const double* g0p = B.g[0] + lane;
     int64_t ln = l0;
-    constexpr int UN = 4;
-    for (; ln + UN <= l1; ln += UN) {
-        uint32_t c[UN];
-        double g0[UN], g1[UN], g2[UN];
+    // full blocks: STB_UN lines in flight per lane, no predication (the HBM-bound regime)
+    for (; ln + STB_UN <= l1; ln += STB_UN) {
+        uint32_t c[STB_UN];
+        double g[STB_UN];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            int64_t idx = (ln + u) * 32 + lane;
-            c[u] = ld_stream(col + idx);
-            g0[u] = ld_stream(g0p + idx);
-            if (NM > 1) g1[u] = ld_stream(g1p + idx);
-            if (NM > 2) g2[u] = ld_stream(g2p + idx);
+        for (int u = 0; u < STB_UN; ++u) {
+            c[u] = ld_pair(col + (ln + u) * 32, NC);
+            g[u] = ld_pair(g0p + (ln + u) * 32, NC);
         }
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
+        for (int u = 0; u < STB_UN; ++u) {
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                double gg = g0[u];
-                if (NM > 1) gg = sm[s] == 0 ? g0[u] : (sm[s] == 1 || NM == 2 ? g1[u] : g2[u]);
-                acc[s] = fma(gg, zU[sc[s] + c[u]], acc[s]);
+            for (int s = 0; s < NS; ++s) acc[s] = fma(g[u], zU[sc[s] + c[u]], acc[s]);
+        }
+    }
+    // remainder in blocks of 4 clamped lines so that its loads overlap (short rows are
+    // latency-bound); lines past the end are masked when consumed
+    for (; ln < l1; ln += 4) {
+        uint32_t c[4];
+        double g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t lc = ln + u < l1 ? ln + u : l1 - 1;
+            c[u] = ld_pair(col + lc * 32, NC);
+            g[u] = ld_pair(g0p + lc * 32, NC);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double gu = ln + u < l1 ? g[u] : 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] = fma(gu, zU[sc[s] + c[u]], acc[s]);
+        }
+    }
+}
+
+// Several multipolarities: generic (runtime slot count), one line at a time.
+__device__ __forceinline__ void stream_block_multi(const PairBlock& B, int nU, const double* zU,
+                                                   int64_t l0, int64_t l1, int lane,
+                                                   double (&acc)[STB_MAXC]) {
+    const int ns = B.n_slots;
+    for (int64_t ln = l0; ln < l1; ++ln) {
+        const int64_t idx = ln * 32 + lane;
+        const uint32_t c = ld_stream(B.col + idx);
+        double g[STB_MAXM];
+#pragma unroll
+        for (int m = 0; m < STB_MAXM; ++m) g[m] = B.g[m] ? ld_stream(B.g[m] + idx) : 0.0;
+#pragma unroll
+        for (int s = 0; s < STB_MAXC; ++s) {
+            if (s < ns) {
+                const int m = B.slot_mult[s];
+                const double gg = m == 0 ? g[0] : (m == 1 ? g[1] : g[2]);
+                acc[s] = fma(gg, zU[B.slot_col[s] * nU + c], acc[s]);
             }
         }
     }
-    for (; ln < l1; ++ln) {
-        int64_t idx = ln * 32 + lane;
-        uint32_t c = ld_stream(col + idx);
-        double g0 = ld_stream(g0p + idx), g1 = 0, g2 = 0;
-        if (NM > 1) g1 = ld_stream(g1p + idx);
-        if (NM > 2) g2 = ld_stream(g2p + idx);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            double gg = g0;
-            if (NM > 1) gg = sm[s] == 0 ? g0 : (sm[s] == 1 || NM == 2 ? g1 : g2);
-            acc[s] = fma(gg, zU[sc[s] + c], acc[s]);
-        }
-    }
 }
 
-template <int NM>
-__device__ __forceinline__ void stream_block_m(const PairBlock& B, int nU, const double* zU,
-                                               int64_t l0, int64_t l1, int lane,
-                                               double (&acc)[STB_MAXC]) {
-    switch (B.n_slots) {
-        case 1: stream_block_t<1, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        case 2: stream_block_t<2, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        case 3: stream_block_t<3, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        case 4: stream_block_t<4, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        case 5: stream_block_t<5, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        case 6: stream_block_t<6, NM>(B, nU, zU, l0, l1, lane, acc); break;
-        default: break;
-    }
-}
-
-// Fields of the rows of slice `slice` of type T gathered from the plane vector z, multiplied by
-// `scale`.  On return every lane of a row holds the row's reduced sums in Fq[0..nf[T]):
-// partner-S slots first, then partner-A slots.  One (non-inlined) instance serves the RHS, Jv
-// and integrator kernels.
-__device__ __noinline__ void slice_fields(const DevLattice& L, int T, int slice, const double* z,
-                                          int lane, double scale, double* Fq) {
-    double accS[STB_MAXC], accA[STB_MAXC];
-#pragma unroll
-    for (int s = 0; s < STB_MAXC; ++s) accS[s] = accA[s] = 0.0;
-#pragma unroll
+// Fields of the rows of slice `slice` of type T gathered from the plane vector z (global memory
+// or a shared-memory copy), multiplied by `scale`.  On return every lane of a row holds the
+// row's reduced sums in Fq[0..nf[T]): partner-S slots first, then partner-A slots.  One
+// (non-inlined) instance serves the RHS, Jv and integrator kernels.
+// Return value: lane `gl` (lane index inside the row's group of lpr lanes) holds field slot gl
+// (0 for gl >= nf[T]) - the form used by the warp-cooperative epilogues.  Fq may be null.
+template <int UN, bool NC>
+__device__ __forceinline__ double slice_fields_impl(const DevLattice& L, int T, int slice,
+                                                    const double* z, int lane, double scale,
+                                                    double* Fq) {
+    int out = 0;
+    double fl = 0.0;
+    const int gl = lane & (L.lpr - 1);
     for (int U = 0; U < 2; ++U) {
         const PairBlock& B = L.blk[T][U];
-        if (B.n_slots == 0) continue;
-        int64_t l0 = B.line_ptr[slice], l1 = B.line_ptr[slice + 1];
+        const int ns = B.n_slots;
+        if (ns == 0) continue;
+        double acc[STB_MAXC];
+#pragma unroll
+        for (int s = 0; s < STB_MAXC; ++s) acc[s] = 0.0;
+        const int64_t l0 = B.line_ptr[slice], l1 = B.line_ptr[slice + 1];
         const double* zU = z + L.off[U];
-        if (U == 0) {
-            if (L.n_mult <= 1) stream_block_m<1>(B, L.n[U], zU, l0, l1, lane, accS);
-            else stream_block_m<3>(B, L.n[U], zU, l0, l1, lane, accS);
+        const int nU = L.n[U];
+        if (L.n_mult > 1) {
+            stream_block_multi(B, nU, zU, l0, l1, lane, acc);
         } else {
-            if (L.n_mult <= 1) stream_block_m<1>(B, L.n[U], zU, l0, l1, lane, accA);
-            else stream_block_m<3>(B, L.n[U], zU, l0, l1, lane, accA);
+            switch (ns) {
+                case 1: stream_block_t<1, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+                case 2: stream_block_t<2, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+                case 3: stream_block_t<3, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+                case 4: stream_block_t<4, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+                case 5: stream_block_t<5, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+                default: stream_block_t<6, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
+            }
         }
-    }
-    const int n0 = L.blk[T][0].n_slots, n1 = L.blk[T][1].n_slots;
-    for (int o = L.lpr >> 1; o > 0; o >>= 1) {
+        for (int o = L.lpr >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int s = 0; s < STB_MAXC; ++s)
+                if (s < ns) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+        }
 #pragma unroll
         for (int s = 0; s < STB_MAXC; ++s) {
-            if (s < n0) accS[s] += __shfl_xor_sync(0xffffffffu, accS[s], o);
-            if (s < n1) accA[s] += __shfl_xor_sync(0xffffffffu, accA[s], o);
+            if (s < ns) {
+                const double v = acc[s] * scale;
+                if (Fq) Fq[out + s] = v;
+                if (gl == out + s) fl = v;
+            }
         }
+        out += ns;
     }
-#pragma unroll
-    for (int s = 0; s < STB_MAXC; ++s) {
-        if (s < n0) Fq[s] = accS[s] * scale;
-    }
-#pragma unroll
-    for (int s = 0; s < STB_MAXC; ++s) {
-        if (s < n1) Fq[n0 + s] = accA[s] * scale;
-    }
+    return fl;
+}
+
+// One non-inlined instance for the persistent integrator (instruction-cache footprint).
+__device__ __noinline__ double slice_fields(const DevLattice& L, int T, int slice, const double* z,
+                                            int lane, double scale, double* Fq) {
+    return slice_fields_impl<STB_UN_INT, true>(L, T, slice, z, lane, scale, Fq);
+}
+
+// Same, for pair data resident in shared memory (generic loads).
+__device__ __noinline__ double slice_fields_resident(const DevLattice& L, int T, int slice,
+                                                     const double* z, int lane, double scale,
+                                                     double* Fq) {
+    return slice_fields_impl<STB_UN_INT, false>(L, T, slice, z, lane, scale, Fq);
 }
 
 __device__ __forceinline__ void load_row(const DevLattice& L, int T, int q, const double* z,

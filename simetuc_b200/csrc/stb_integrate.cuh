@@ -9,7 +9,7 @@
 // step/order/Newton/Givens logic redundantly from identical reduced values, so control flow is
 // uniform across the group by construction.
 #pragma once
-#include "stb_fields.cuh"
+#include "stb_coop.cuh"
 
 #define STB_KRED (STB_KRYLOV + 4)
 #define STB_NEWTON_MAXIT 4
@@ -35,6 +35,9 @@ struct IntArgs {
     unsigned long long* bar;  // [n_groups]
     double* partials;         // [n_groups][2][G][STB_KRED]
     int NMinv;                // doubles of block-Jacobi inverses per system
+    int resident;             // the CTA's pair rows are copied to shared memory once
+    int staged;               // gather vector staged in shared memory (N*8 bytes dynamic smem)
+    long long* prof;          // [n_sys][8] clock64 cycles per phase (thread 0 of CTA 0), may be null
 };
 
 __host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
@@ -50,13 +53,14 @@ struct Ctl {
     int order, n_equal, status, kk, flag, newton_it, n_iter;
     int64_t k_out, steps_since_out;
     stb_stats st;
+    long long prof[8];
 };
 
 struct GroupCtx {
     unsigned long long* counter;
     unsigned long long epoch;
     double* partials;   // [2][G][STB_KRED]
-    int G, cta, buf;
+    int G, cta, buf, relaxed;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -65,16 +69,34 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Group barrier.  Two flavours:
+//  * acquire: fence + acquire load, so that plain (L1-cached) loads issued afterwards observe
+//    the other CTAs' writes (the fence invalidates this SM's L1);
+//  * relaxed: release on arrival only.  Data written by other CTAs is then read exclusively
+//    through L2 (`__ldcg`, staging copies), so the L1 - which holds this CTA's own rows - stays
+//    warm across barriers.  Used when the gathered vector is staged in shared memory.
 __device__ __forceinline__ void group_sync(GroupCtx& g) {
     __syncthreads();
     if (g.G > 1) {
         if (threadIdx.x == 0) {
             g.epoch += 1;
-            __threadfence();
-            atomicAdd(g.counter, 1ull);
-            unsigned long long target = g.epoch * (unsigned long long)g.G;
-            while (ld_acquire_u64(g.counter) < target) { }
-            __threadfence();
+            const unsigned long long target = g.epoch * (unsigned long long)g.G;
+            if (g.relaxed) {
+                asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(g.counter), "l"(1ull)
+                             : "memory");
+                while (ld_relaxed_u64(g.counter) < target) { }
+            } else {
+                __threadfence();
+                atomicAdd(g.counter, 1ull);
+                while (ld_acquire_u64(g.counter) < target) { }
+                __threadfence();
+            }
         }
         __syncthreads();
     }
@@ -157,6 +179,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     __shared__ double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
     __shared__ double red[STB_NW * 4];
     __shared__ double rv[STB_KRED];
+    extern __shared__ double zs[];   // staged gather vector (N doubles) when A.staged
 
     const int gid = blockIdx.x / A.G;
     if (gid >= A.n_groups) return;
@@ -170,6 +193,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     g.counter = A.bar + gid;
     g.epoch = 0;
     g.buf = 0;
+    g.relaxed = A.staged;
     g.partials = A.partials + (int64_t)gid * 2 * A.G * STB_KRED;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,6 +206,59 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         r_hi[T] = min(sl_hi[T] * L.R, L.n[T]);
     }
     const int n_own_slices = (sl_hi[0] - sl_lo[0]) + (sl_hi[1] - sl_lo[1]);
+
+    // ---- small lattices: make the CTA's own pair rows resident in shared memory ------------
+    // Ownership is fixed for the whole launch and every system of the batch shares the lattice,
+    // so the (partner, g) lines of the own slices are copied once; afterwards a Krylov iteration
+    // touches global memory only for the (staged) gathered vector and the group barrier.
+    if (A.resident) {
+        double* sp = zs + N;                       // doubles first (alignment)
+        double* g_s[2][2];
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) {
+                const PairBlock& B = L.blk[T][U];
+                const int64_t base = B.n_slots ? B.line_ptr[sl_lo[T]] : 0;
+                const int64_t cnt = B.n_slots ? B.line_ptr[sl_hi[T]] - base : 0;
+                g_s[T][U] = sp;
+                for (int64_t i = threadIdx.x; i < cnt * 32; i += STB_NT) sp[i] = B.g[0][base * 32 + i];
+                sp += cnt * 32;
+            }
+        int64_t* lp_s[2][2];
+        int64_t* ip = (int64_t*)sp;
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) {
+                const PairBlock& B = L.blk[T][U];
+                const int cntp = sl_hi[T] - sl_lo[T] + 1;
+                lp_s[T][U] = ip;
+                if (B.n_slots)
+                    for (int i = threadIdx.x; i < cntp; i += STB_NT) ip[i] = B.line_ptr[sl_lo[T] + i];
+                ip += cntp;
+            }
+        uint32_t* cp = (uint32_t*)ip;
+        uint32_t* c_s[2][2];
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) {
+                const PairBlock& B = L.blk[T][U];
+                const int64_t base = B.n_slots ? B.line_ptr[sl_lo[T]] : 0;
+                const int64_t cnt = B.n_slots ? B.line_ptr[sl_hi[T]] - base : 0;
+                c_s[T][U] = cp;
+                for (int64_t i = threadIdx.x; i < cnt * 32; i += STB_NT) cp[i] = B.col[base * 32 + i];
+                cp += cnt * 32;
+            }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int T = 0; T < 2; ++T)
+                for (int U = 0; U < 2; ++U) {
+                    PairBlock& B = L.blk[T][U];
+                    if (!B.n_slots) continue;
+                    const int64_t base = B.line_ptr[sl_lo[T]];
+                    B.col = c_s[T][U] - base * 32;
+                    B.g[0] = g_s[T][U] - base * 32;
+                    B.line_ptr = lp_s[T][U] - sl_lo[T];
+                }
+        }
+        __syncthreads();
+    }
 
     double* W = A.work + (int64_t)gid * A.work_stride;
     double* D = W;                       // [8][N]
@@ -206,19 +283,70 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         ERRC[k] = KAPPA[k] * GAMMA[k] + 1.0 / (k + 1);
     }
     const double sqrtN = sqrt((double)N);
+    long long tick = clock64();
+#define PROF(k)                                              \
+    if (threadIdx.x == 0) {                                  \
+        long long now_ = clock64();                          \
+        C.prof[k] += now_ - tick;                            \
+        tick = now_;                                         \
+    }
 
     // ---- RHS phase: f = rhs(z) for own rows, fields F; optional block-Jacobi setup and
     //      preconditioned scaled residual (Newton) -------------------------------------------
     // mode 0: plain RHS (f only).  mode 1: Newton: also Minv(c), wv = Minv(c f - psi - d)/scale,
     //         gv = wv*scale; returns partial ||wv||^2 and a non-finite flag in part[].
+    // copy the gathered vector (written by all CTAs of the group) through L2 into shared memory
+    auto stage = [&](const double* z) -> const double* {
+        if (!A.staged) return z;
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += STB_NT) zs[i] = __ldcg(z + i);
+        __syncthreads();
+        return zs;
+    };
+    const int n_own_A = sl_hi[1] - sl_lo[1];
     auto rhs_phase = [&](const double* z, double* fout, int mode, double c, double (&part)[2]) {
         part[0] = 0.0;
         part[1] = 0.0;
+        const double* zg = stage(z);
         for (int task = warp; task < n_own_slices; task += STB_NW) {
-            int T = task >= (sl_hi[0] - sl_lo[0]);
-            int slice = T ? sl_lo[1] + task - (sl_hi[0] - sl_lo[0]) : sl_lo[0] + task;
+            int T = task < n_own_A;          // activator rows first (the expensive epilogues)
+            int slice = T ? sl_lo[1] + task : sl_lo[0] + task - n_own_A;
+            if (L.lpr >= 16) {      // warp-cooperative epilogue: lane j <-> state j of the ion
+                const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+                const double fl = A.resident ? slice_fields_resident(L, T, slice, zg, lane, 1.0, nullptr)
+                                             : slice_fields(L, T, slice, zg, lane, 1.0, nullptr);
+                const int q = slice * L.R + lane / W;
+                const bool valid = q < nT;
+                const bool act = valid && gl < s;
+                const int e = L.off[T] + (gl < s ? gl : 0) * nT + (valid ? q : nT - 1);
+                const double yj = gl < s ? z[e] : 0.0;
+                const double fj = coop_rhs(L, P, T, W, gl, yj, fl);
+                if (act) fout[e] = fj;
+                if (valid && gl < L.nf[T]) F[L.foff[T] + gl * nT + q] = fl;
+                if (mode == 1) {
+                    double ai[STB_MAXS];
+                    coop_block_inverse(L, P, T, W, gl, fl, c, ai);
+                    double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
+                    if (act) {
+#pragma unroll
+                        for (int b = 0; b < STB_MAXS; ++b)
+                            if (b < s) Mp[(int64_t)(gl * s + b) * nT] = ai[b];
+                    }
+                    const double rj = act ? c * fj - psi[e] - dd[e] : 0.0;
+                    const double xy = coop_apply_rows(ai, s, W, rj);
+                    if (act) {
+                        const double x = xy / scale[e];
+                        wv[e] = x;
+                        gv[e] = xy;
+                        part[0] = fma(x, x, part[0]);
+                        if (!isfinite(fj)) part[1] = 1.0;
+                    }
+                }
+                continue;
+            }
             double Fq[2 * STB_MAXC];
-            slice_fields(L, T, slice, z, lane, 1.0, Fq);
+            if (A.resident) slice_fields_resident(L, T, slice, zg, lane, 1.0, Fq);
+            else slice_fields(L, T, slice, zg, lane, 1.0, Fq);
             int q = slice * L.R + lane / L.lpr;
             if ((lane % L.lpr) == 0 && q < L.n[T]) {
                 double zq[STB_MAXS], oq[STB_MAXS];
@@ -256,11 +384,35 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
 
     // ---- Arnoldi phase: wbuf = Minv (v - c J v) / scale with v = inrm * gv ------------------
     auto arnoldi_phase = [&](double inrm, double c) {
+        const double* zg = stage(gv);
         for (int task = warp; task < n_own_slices; task += STB_NW) {
-            int T = task >= (sl_hi[0] - sl_lo[0]);
-            int slice = T ? sl_lo[1] + task - (sl_hi[0] - sl_lo[0]) : sl_lo[0] + task;
+            int T = task < n_own_A;
+            int slice = T ? sl_lo[1] + task : sl_lo[0] + task - n_own_A;
+            if (L.lpr >= 16) {
+                // M^-1 (I - cJ) v = v - c Minv k,  k = coupling of the ion to its partners' v
+                const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+                long long t0_ = clock64();
+                const double fvl = A.resident ? slice_fields_resident(L, T, slice, zg, lane, inrm, nullptr)
+                                               : slice_fields(L, T, slice, zg, lane, inrm, nullptr);
+                if (threadIdx.x == 0) C.prof[6] += clock64() - t0_;
+                const int q = slice * L.R + lane / W;
+                const bool valid = q < nT;
+                const bool act = valid && gl < s;
+                const int qc = valid ? q : nT - 1;
+                const int e = L.off[T] + (gl < s ? gl : 0) * nT + qc;
+                const double yj = gl < s ? yk[e] : 0.0;
+                const double kj = coop_coupling(L, P, T, W, gl, yj, fvl);
+                const double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + qc;
+                const int row = gl < s ? gl : 0;
+                double mk = 0.0;
+                for (int b = 0; b < s; ++b)
+                    mk = fma(Mp[(int64_t)(row * s + b) * nT], __shfl_sync(FULL, kj, b, W), mk);
+                if (act) wbuf[e] = (inrm * gv[e] - c * mk) / scale[e];
+                continue;
+            }
             double Fv[2 * STB_MAXC];
-            slice_fields(L, T, slice, gv, lane, inrm, Fv);
+            if (A.resident) slice_fields_resident(L, T, slice, zg, lane, inrm, Fv);
+            else slice_fields(L, T, slice, zg, lane, inrm, Fv);
             int q = slice * L.R + lane / L.lpr;
             if ((lane % L.lpr) == 0 && q < L.n[T]) {
                 const int nT = L.n[T], s = L.s[T];
@@ -336,6 +488,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
             C.tol_lin = STB_EPS_LIN * C.newton_tol * sqrtN;
             memset(&C.st, 0, sizeof(stb_stats));
+            for (int k = 0; k < 8; ++k) C.prof[k] = 0;
+            tick = clock64();
         }
         // D0 = y0, yk = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
         OWN_LOOP(e)
@@ -443,11 +597,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             if (threadIdx.x == 0) { C.newton_it = 0; C.flag = 0; C.dy_norm_old = -1.0; }
             __syncthreads();
             while (true) {       // flag: 0 iterate, 1 converged, 2 failed
+                PROF(7)
                 group_sync(g);   // yk complete in the whole group
+                PROF(3)
                 rhs_phase(yk, f, 1, c, part);
+                PROF(0)
                 double v2[2] = {part[0], part[1]};
                 block_sum<2>(v2, red, rv);
                 group_reduce(g, rv, 2);
+                PROF(3)
                 if (threadIdx.x == 0) {
                     C.st.n_rhs += 1;
                     C.st.n_lin += 1;
@@ -466,12 +624,17 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     const double inrm = C.inrm;
                     // V_j = inrm * wv (own elements); then the fused operator pass
                     double* Vj = V + (int64_t)j * N;
+                    PROF(7)
                     OWN_LOOP(e)
                         Vj[e] = inrm * wv[e];
                     OWN_END
+                    PROF(4)
                     arnoldi_phase(inrm, c);
+                    PROF(1)
                     own_dots(wbuf, j + 1);
+                    PROF(2)
                     group_reduce(g, rv, j + 2);
+                    PROF(3)
                     const double ww = rv[j + 1];
                     if (threadIdx.x <= (unsigned)j) H[threadIdx.x * STB_KRYLOV + j] = rv[threadIdx.x];
                     __syncthreads();
@@ -484,8 +647,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                         gv[e] = acc * scale[e];
                         v1[0] = fma(acc, acc, v1[0]);
                     OWN_END
+                    PROF(4)
                     block_sum<1>(v1, red, rv);
                     group_reduce(g, rv, 1);
+                    PROF(3)
                     double hn2 = rv[0];
                     if (hn2 < 0.01 * ww && hn2 > 0.0) {
                         // severe cancellation: one re-orthogonalisation pass (DGKS)
@@ -530,6 +695,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                         if (!(hn > 0.0) || !isfinite(hn)) C.beta = 0.0;
                     }
                     __syncthreads();
+                    PROF(5)
                     ++j;
                     lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
                 }
@@ -745,6 +911,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.st.t_reached = C.t;
             C.st.n_out = C.k_out;
             A.stats[sysl] = C.st;
+            if (A.prof) {
+                PROF(7)
+                for (int k = 0; k < 8; ++k) A.prof[(int64_t)sysl * 8 + k] = C.prof[k];
+            }
         }
         group_sync(g);
     }

@@ -1,7 +1,7 @@
 // Standalone RHS / Jv kernels (C ABI: stb_rhs, stb_jv) and layout conversion.
 // One warp per slice (R rows), grid-stride over slices, blockIdx.y = system of the batch.
 #pragma once
-#include "stb_fields.cuh"
+#include "stb_coop.cuh"
 
 struct OpArgs {
     const DevLattice* L;
@@ -17,7 +17,10 @@ struct OpArgs {
 };
 
 // dy = (abs +) decay y + ET (y_i * y_j): odesolver._rate_eq / _rate_eq_pulse (odesolver.py:33-71)
-__global__ void __launch_bounds__(STB_NT) k_rhs(OpArgs A) {
+#ifndef STB_RHS_MINB
+#define STB_RHS_MINB 1
+#endif
+__global__ void __launch_bounds__(STB_NT, STB_RHS_MINB) k_rhs(OpArgs A) {
     __shared__ DevLattice L;
     __shared__ SysParams P;
     for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
@@ -34,6 +37,18 @@ __global__ void __launch_bounds__(STB_NT) k_rhs(OpArgs A) {
     for (int task = blockIdx.x * STB_NW + warp; task < total; task += gridDim.x * STB_NW) {
         int T = task >= L.n_slices[0];
         int slice = T ? task - L.n_slices[0] : task;
+        if (L.lpr >= 16) {      // warp-cooperative epilogue: lane j <-> state j
+            const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+            const double fl = slice_fields_impl<STB_UN_KERNEL, true>(L, T, slice, y, lane, 1.0, nullptr);
+            const int q = slice * L.R + lane / W;
+            const bool valid = q < nT;
+            const int e = L.off[T] + (gl < s ? gl : 0) * nT + (valid ? q : nT - 1);
+            const double yj = gl < s ? y[e] : 0.0;
+            const double fj = coop_rhs(L, P, T, W, gl, yj, fl);
+            if (valid && gl < s) out[e] = fj;
+            if (F && valid && gl < L.nf[T]) F[L.foff[T] + gl * nT + q] = fl;
+            continue;
+        }
         double Fq[2 * STB_MAXC];
         slice_fields(L, T, slice, y, lane, 1.0, Fq);
         int q = slice * L.R + lane / L.lpr;
@@ -52,7 +67,7 @@ __global__ void __launch_bounds__(STB_NT) k_rhs(OpArgs A) {
 
 // jv = J(y) v without the dense Jacobian (odesolver.py:46-62,74-80); the fields at y come from
 // the RHS pass at the same y, so one Jv streams the pair data exactly once.
-__global__ void __launch_bounds__(STB_NT) k_jv(OpArgs A) {
+__global__ void __launch_bounds__(STB_NT, STB_RHS_MINB) k_jv(OpArgs A) {
     __shared__ DevLattice L;
     __shared__ SysParams P;
     for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
@@ -70,6 +85,19 @@ __global__ void __launch_bounds__(STB_NT) k_jv(OpArgs A) {
     for (int task = blockIdx.x * STB_NW + warp; task < total; task += gridDim.x * STB_NW) {
         int T = task >= L.n_slices[0];
         int slice = T ? task - L.n_slices[0] : task;
+        if (L.lpr >= 16) {
+            const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+            const double fvl = slice_fields_impl<STB_UN_KERNEL, true>(L, T, slice, v, lane, 1.0, nullptr);
+            const int q = slice * L.R + lane / W;
+            const bool valid = q < nT;
+            const int qc = valid ? q : nT - 1;
+            const int e = L.off[T] + (gl < s ? gl : 0) * nT + qc;
+            const double yj = gl < s ? y[e] : 0.0, vj = gl < s ? v[e] : 0.0;
+            const double fyl = gl < L.nf[T] ? Fy[L.foff[T] + gl * nT + qc] : 0.0;
+            const double oj = coop_jv(L, P, T, W, gl, yj, vj, fyl, fvl);
+            if (valid && gl < s) out[e] = oj;
+            continue;
+        }
         double Fv[2 * STB_MAXC];
         slice_fields(L, T, slice, v, lane, 1.0, Fv);
         int q = slice * L.R + lane / L.lpr;

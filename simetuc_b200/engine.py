@@ -201,3 +201,10 @@ class RateSystem:
         launches = C.c_int64()
         _lib.check(self.lib.stb_last_timing(self.handle, C.byref(ms), C.byref(launches)))
         return float(ms.value), int(launches.value)
+
+    def last_profile(self):
+        """Per-phase clock cycles of the last integrate call (development aid)."""
+        out = (C.c_double * 10)()
+        _lib.check(self.lib.stb_last_profile(self.handle, out))
+        names = ['rhs', 'arnoldi', 'dots', 'barrier', 'vector', 'givens', 'arnoldi_stream', 'rest', 'G', 'groups']
+        return dict(zip(names, [float(v) for v in out]))
