@@ -162,6 +162,16 @@ int stb_from_planes(const stb_system* sys, int32_t n, const double* y_planes_dev
 int stb_integrate(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
                   const double* t, const double* y0, double rtol, double atol, int64_t nsteps,
                   double* y_out, double* avg_out, stb_stats* stats /*[n]*/);
+/* Same with DEVICE buffers (bench.py: operands resident in HBM): t_dev [n_t], y0 in the internal
+ * plane layout [n, N] (see stb_to_planes), y_out_dev [n, n_t, N] in reference layout (may be
+ * NULL), avg_out_dev [n, n_t, sS+sA] (may be NULL).  stats is a HOST pointer. */
+int stb_integrate_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                      const double* t_dev, const double* y0_planes_dev, double rtol, double atol,
+                      int64_t nsteps, double* y_out_dev, double* avg_out_dev, stb_stats* stats);
+/* The CUDA stream (cudaStream_t) every kernel of this system is launched on, so that callers can
+ * record their own events on it; and the number of kernels launched by the library so far. */
+void* stb_stream(const stb_system* sys);
+int64_t stb_launch_count(void);
 /* Device time (ms, CUDA events) of the last stb_integrate call's kernels, and the number of
  * kernel launches it made. */
 int stb_last_timing(const stb_system* sys, float* ms, int64_t* launches);

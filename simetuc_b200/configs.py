@@ -137,7 +137,8 @@ def yb_tm_cte(N_uc=15, S_conc=5.0, A_conc=0.5, power_dens=1e7, t_pulse=1e-8,
         'no_console': True, 'no_plot': True,
         'simulation_params': {'N_steps': N_steps, 'N_steps_pulse': 2, 'atol': atol, 'rtol': rtol},
         'power_dependence': [1e6, 1e13, 8],
-        'optimization': {'processes': ['ETU1', 'ETU2', 'ETU3', 'BackET', 'EM'],
+        'optimization': {'processes': [et[k] for k in ('ETU1', 'ETU2', 'ETU3', 'BackET', 'EM')
+                                       if k in et],
                          'method': 'COBYLA'},
         'states': {'activator_ion_label': 'Tm', 'activator_states': nA,
                    'activator_states_labels': labels,

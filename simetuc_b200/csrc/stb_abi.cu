@@ -1,6 +1,7 @@
 // simetuc_b200 - C ABI implementation (host side) for include/simetuc_b200.h.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -12,6 +13,7 @@
 #include "stb_kernels.cuh"
 
 static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};   // kernels launched by this library (all handles)
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -321,6 +323,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     // ---- pass 1: row lengths ---------------------------------------------------------------------
     CKP(cudaMalloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
+    g_launches++;
     k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
     CKP(cudaGetLastError());
     S->len.resize(2 * (size_t)n);
@@ -394,6 +397,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     for (int T = 0; T < 2; ++T)
         for (int U = 0; U < 2; ++U)
             if (L.blk[T][U].n_slots == 0) FA.col[T][U] = nullptr;
+    g_launches++;
     k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
     CKP(cudaGetLastError());
     CKP(cudaStreamSynchronize(S->stream));
@@ -552,6 +556,7 @@ extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint
     if (et_w) CK(cudaMalloc((void**)&EA.et_w, sizeof(double) * M));
     if (jac_indices) CK(cudaMalloc((void**)&EA.jac, sizeof(uint32_t) * 6 * M));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
+    g_launches++;
     k_export<<<blocks, 256, 0, S->stream>>>(EA);
     CK(cudaGetLastError());
     if (N_indices) CK(cudaMemcpyAsync(N_indices, EA.N_indices, sizeof(uint32_t) * 2 * M, cudaMemcpyDeviceToHost, S->stream));
@@ -603,6 +608,7 @@ extern "C" int stb_to_planes(const stb_system* S, int32_t n, const double* y_hos
     CK(cudaMalloc((void**)&tmp, bytes));
     CK(cudaMemcpyAsync(tmp, y_host, bytes, cudaMemcpyHostToDevice, S->stream));
     int64_t tot = (int64_t)n * S->N;
+    g_launches++;
     k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, tmp, y_planes_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(S->stream));
@@ -617,6 +623,7 @@ extern "C" int stb_from_planes(const stb_system* S, int32_t n, const double* y_p
     size_t bytes = sizeof(double) * (size_t)n * S->N;
     CK(cudaMalloc((void**)&tmp, bytes));
     int64_t tot = (int64_t)n * S->N;
+    g_launches++;
     k_planes_to_ref<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, y_planes_dev, tmp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y_host, tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
@@ -629,6 +636,7 @@ static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* 
     OpArgs A;
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = nullptr; A.Fy = nullptr; A.out = out; A.F = F;
+    g_launches++;
     k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     CK(cudaGetLastError());
     return STB_OK;
@@ -639,6 +647,7 @@ static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y
     OpArgs A;
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = v; A.Fy = Fy; A.out = out; A.F = nullptr;
+    g_launches++;
     k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     CK(cudaGetLastError());
     return STB_OK;
@@ -654,8 +663,10 @@ extern "C" int stb_rhs(stb_system* S, int32_t first, int32_t n, int32_t pulse, c
     int64_t tot = (int64_t)n * S->N;
     unsigned gb = (unsigned)((tot + 255) / 256);
     CK(cudaMemcpyAsync(S->d_tmp, y, bytes, cudaMemcpyHostToDevice, S->stream));
+    g_launches++;
     k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_y);
     if ((rc = launch_rhs(S, first, n, pulse, S->d_y, S->d_out, S->d_F))) return rc;
+    g_launches++;
     k_planes_to_ref<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_out, S->d_tmp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dy, S->d_tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
@@ -674,11 +685,14 @@ extern "C" int stb_jv(stb_system* S, int32_t first, int32_t n, int32_t pulse, co
     int64_t tot = (int64_t)n * S->N;
     unsigned gb = (unsigned)((tot + 255) / 256);
     CK(cudaMemcpyAsync(S->d_tmp, y, bytes, cudaMemcpyHostToDevice, S->stream));
+    g_launches++;
     k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_y);
     CK(cudaMemcpyAsync(S->d_tmp, v, bytes, cudaMemcpyHostToDevice, S->stream));
+    g_launches++;
     k_ref_to_planes<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_tmp, S->d_v);
     if ((rc = launch_rhs(S, first, n, pulse, S->d_y, S->d_out, S->d_F))) return rc;   // fields at y
     if ((rc = launch_jv(S, first, n, pulse, S->d_y, S->d_v, S->d_F, S->d_out))) return rc;
+    g_launches++;
     k_planes_to_ref<<<gb, 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, S->d_out, S->d_tmp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(jv, S->d_tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
@@ -738,15 +752,17 @@ extern "C" int stb_jv_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse
 }
 
 // ---------------------------------------------------------------------------------------------
-extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
-                             const double* t, const double* y0, double rtol, double atol,
-                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats) {
+static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                          const double* t, const double* y0, double rtol, double atol,
+                          int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats,
+                          bool dev) {
     int rc = check_range(S, first, n);
     if (rc) return rc;
     if (n_t < 1 || !t || !y0) return fail(STB_EINVAL, "bad time grid / initial state");
     if (!(rtol > 0.0) || !(atol >= 0.0)) return fail(STB_EINVAL, "rtol must be > 0 and atol >= 0");
-    for (int64_t k = 1; k < n_t; ++k)
-        if (!(t[k] > t[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    if (!dev)
+        for (int64_t k = 1; k < n_t; ++k)
+            if (!(t[k] > t[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
     CK(cudaSetDevice(S->device));
     if ((rc = sync_params(S))) return rc;
     const int N = S->N;
@@ -825,31 +841,41 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
         }                                                                             \
     } while (0)
     CKI(cudaMalloc((void**)&d_work, sizeof(double) * (size_t)n_groups * work_stride));
-    CKI(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
-    CKI(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
-    CKI(cudaMalloc((void**)&d_yout, out_bytes));
-    CKI(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+    const bool own_yout = !(dev && y_out);
+    if (!dev) {
+        CKI(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
+        CKI(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
+        CKI(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+    }
+    if (own_yout) CKI(cudaMalloc((void**)&d_yout, out_bytes));
     CKI(cudaMalloc((void**)&d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED));
     CKI(cudaMalloc((void**)&d_bar, sizeof(unsigned long long) * n_groups));
     CKI(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
     CKI(cudaMalloc((void**)&d_prof, sizeof(long long) * 8 * n));
     CKI(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * n, S->stream));
     CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * n_groups, S->stream));
-    CKI(cudaMemsetAsync(d_yout, 0, out_bytes, S->stream));
     CKI(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     CKI(cudaMemsetAsync(d_work, 0, sizeof(double) * (size_t)n_groups * work_stride, S->stream));
-    CKI(cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
-    CKI(cudaMemcpyAsync(d_tmp, y0, sizeof(double) * (size_t)n * N, cudaMemcpyHostToDevice, S->stream));
-    int64_t tot = (int64_t)n * N;
-    k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
-    CKI(cudaGetLastError());
+    double* yout_p = own_yout ? d_yout : y_out;
+    CKI(cudaMemsetAsync(yout_p, 0, out_bytes, S->stream));
+    const double *t_p = t, *y0_p = y0;
+    if (!dev) {
+        CKI(cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
+        CKI(cudaMemcpyAsync(d_tmp, y0, sizeof(double) * (size_t)n * N, cudaMemcpyHostToDevice, S->stream));
+        int64_t tot = (int64_t)n * N;
+        g_launches++;
+        k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
+        CKI(cudaGetLastError());
+        t_p = d_t;
+        y0_p = d_y0;
+    }
 
     IntArgs A;
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.n_sys = n; A.pulse = pulse; A.G = G; A.n_groups = n_groups;
-    A.n_t = n_t; A.t = d_t; A.y0 = d_y0; A.rtol = rtol; A.atol = atol;
+    A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;
     A.nsteps = nsteps > 0 ? nsteps : 1000;
-    A.y_out = d_yout; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
+    A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0, e1;
@@ -857,18 +883,25 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
     CKI(cudaEventCreate(&e1));
     CKI(cudaEventRecord(e0, S->stream));
     void* kargs[] = {&A};
+    g_launches++;
     CKI(cudaLaunchCooperativeKernel((void*)k_integrate, dim3(grid), dim3(STB_NT), kargs, dyn_bytes, S->stream));
     CKI(cudaEventRecord(e1, S->stream));
-    S->last_launches = 1;
+    S->last_launches = dev ? 1 : 2;
     if (avg_out) {
-        CKI(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
-        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, d_yout, n_t, d_avg);
+        double* avg_p = avg_out;
+        if (!dev) {
+            CKI(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
+            avg_p = d_avg;
+        }
+        g_launches++;
+        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
         CKI(cudaGetLastError());
         S->last_launches += 1;
-        CKI(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
-                            cudaMemcpyDeviceToHost, S->stream));
+        if (!dev)
+            CKI(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
+                                cudaMemcpyDeviceToHost, S->stream));
     }
-    if (y_out) CKI(cudaMemcpyAsync(y_out, d_yout, out_bytes, cudaMemcpyDeviceToHost, S->stream));
+    if (y_out && !dev) CKI(cudaMemcpyAsync(y_out, d_yout, out_bytes, cudaMemcpyDeviceToHost, S->stream));
     S->last_prof.assign((size_t)8 * n, 0);
     CKI(cudaMemcpyAsync(S->last_prof.data(), d_prof, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost, S->stream));
     if (stats) CKI(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
@@ -879,6 +912,24 @@ extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pu
     cleanup();
     return STB_OK;
 }
+
+extern "C" int stb_integrate(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                             const double* t, const double* y0, double rtol, double atol,
+                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats) {
+    return integrate_core(S, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out, avg_out, stats, false);
+}
+
+extern "C" int stb_integrate_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
+                                 const double* t_dev, const double* y0_planes_dev, double rtol,
+                                 double atol, int64_t nsteps, double* y_out_dev, double* avg_out_dev,
+                                 stb_stats* stats) {
+    return integrate_core(S, first, n, pulse, n_t, t_dev, y0_planes_dev, rtol, atol, nsteps,
+                          y_out_dev, avg_out_dev, stats, true);
+}
+
+extern "C" void* stb_stream(const stb_system* S) { return S ? (void*)S->stream : nullptr; }
+
+extern "C" int64_t stb_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int stb_last_timing(const stb_system* S, float* ms, int64_t* launches) {
     if (!S) return fail(STB_EINVAL, "null system");

@@ -196,6 +196,29 @@ class RateSystem:
             float(atol), int(nsteps), _lib.ptr(y_out), _lib.ptr(avg), C.cast(stats, C.c_void_p)))
         return y_out, avg, [s.as_dict() for s in stats]
 
+    def integrate_dev(self, t_dev_ptr: int, n_t: int, y0_planes_ptr: int, n: int, pulse: bool,
+                      rtol: float, atol: float, nsteps: int = 1000, first: int = 0,
+                      y_out_ptr: int = 0, avg_out_ptr: int = 0):
+        """`stb_integrate_dev`: every operand is a raw device pointer (e.g. `tensor.data_ptr()`),
+        nothing is copied between host and device except the per-system statistics."""
+        stats = (_lib.StbStats * n)()
+        _lib.check(self.lib.stb_integrate_dev(
+            self.handle, first, n, int(bool(pulse)), n_t, C.c_void_p(t_dev_ptr),
+            C.c_void_p(y0_planes_ptr), float(rtol), float(atol), int(nsteps),
+            C.c_void_p(y_out_ptr or None), C.c_void_p(avg_out_ptr or None),
+            C.cast(stats, C.c_void_p)))
+        return [s.as_dict() for s in stats]
+
+    def to_planes(self, y_host, out_ptr: int):
+        """Reference-layout host vectors `[n, N]` -> plane layout in the device buffer `out_ptr`."""
+        y, n = self._vecs(y_host, 0, None)
+        _lib.check(self.lib.stb_to_planes(self.handle, n, _lib.ptr(y), C.c_void_p(out_ptr)))
+
+    @property
+    def stream(self) -> int:
+        """`cudaStream_t` (as int) all kernels of this system run on."""
+        return int(self.lib.stb_stream(self.handle) or 0)
+
     def last_timing(self):
         ms = C.c_float()
         launches = C.c_int64()

@@ -1,0 +1,176 @@
+"""GPU tests of the reference-facing Python API (`Simulations`, `odesolver`, `optimize`)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as onp
+from simetuc_b200 import configs, lattice, odesolver, optimize, precalculate
+from simetuc_b200.lattice import Lattice
+from simetuc_b200.simulations import (ConcentrationDependenceSolution, DynamicsSolution,
+                                      PowerDependenceSolution, Simulations, SteadyStateSolution)
+from tests.helpers import GOLDEN, load_golden, oracle_operands
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def lattice_file_2S_2A(tmp_path):
+    g = load_golden('sim_2S_2A')
+    lat = Lattice.from_arrays(g['ion_type'], g['dist_array'], 2, 7, positions=g['doped_lattice'],
+                              name='bNaYF4', S_conc=0.3, A_conc=0.3)
+    path = str(tmp_path / 'data_2S_2A.npz')
+    lat.save(path)
+    return path
+
+
+def test_sim_dyn_2S_2A(lattice_file_2S_2A):
+    """Port of the reference's `test_sim_dyn_2S_2A` (`test_simulations.py:76-91`)."""
+    cte = configs.sim_cte()
+    sim = Simulations(cte, full_path=lattice_file_2S_2A)
+    assert sim.cte['lattice']['S_conc'] == 0.3 and sim.cte['states']['sensitizer_states'] == 2
+    solution = sim.simulate_dynamics()
+    assert isinstance(solution, DynamicsSolution)
+    assert solution.index_A_j == [0, -1, -1, 11]
+    assert solution.index_S_i == [-1, 7, 9, -1]
+    with np.load(os.path.join(GOLDEN, 'sol_2S_2A.npz')) as z:
+        assert np.allclose(z['t_sol'], solution.t_sol)
+        assert np.allclose(z['y_sol'], solution.y_sol)
+    avg = np.array(solution.list_avg_data)
+    ref = onp.avg_populations(solution.y_sol, solution.index_S_i, solution.index_A_j, 2, 7)
+    assert np.allclose(avg, ref, rtol=1e-12, atol=0)
+    steady = solution.calculate_steady_state()
+    assert isinstance(steady, SteadyStateSolution)
+    assert np.allclose(steady.y_sol, onp.cumulative_steady_state(solution.t_sol, solution.y_sol))
+    assert solution.errors.shape == (9,) and np.all(solution.errors == 0)   # no expData here
+
+
+def test_setup_microscopic_eqs_tuple(lattice_file_2S_2A):
+    """The reference's 12-tuple (`precalculate.py:875-878`) with the reference's dtypes."""
+    cte = configs.sim_cte()
+    out = precalculate.setup_microscopic_eqs(cte, full_path=lattice_file_2S_2A)
+    assert len(out) == 12
+    (cte2, pop, iS, iA, abs_m, dec_m, ET, N_idx, jac, cET, cN, cJ) = out
+    op = oracle_operands(load_golden('sim_2S_2A'), configs.sim_cte())
+    assert pop.dtype == np.uint64 and np.array_equal(pop, op['initial_population'])
+    assert iS == op['index_S_i'].tolist() and iA == op['index_A_j'].tolist()
+    assert abs(abs_m - op['abs']).max() == 0 and abs(dec_m - op['decay']).max() == 0
+    assert np.array_equal(N_idx, op['N_indices']) and np.array_equal(jac, op['jac_indices'])
+    assert abs(ET - op['ET']).max() <= 1e-14 * abs(op['ET']).max()
+    assert cET.shape == (18, 0) and cN.shape == (0, 3) and cJ.shape == (0, 4)
+    assert cte2['ions'] == {'total': 4, 'sensitizers': 2, 'activators': 2}
+    assert cte2['states']['energy_states'] == 18
+    # RHS / dense Jacobian through the reference-named callbacks
+    y = load_golden('sim_2S_2A')['sim_y'][0]
+    f = odesolver._rate_eq_pulse(0, y, abs_m, dec_m, ET, N_idx, cET, cN)
+    ref = onp.rate_eq_pulse(0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], *op['coop'][:2])
+    assert np.all(np.abs(f - ref) <= 1e-12 * np.abs(ref).max())
+    J = odesolver._jac_rate_eq_pulse(0, y, abs_m, dec_m, ET, jac, cET, cJ)
+    Jref = onp.jac_rate_eq_pulse(0, y, op['abs'], op['decay'], op['ET'], op['jac_indices'],
+                                 op['coop'][0], op['coop'][2])
+    assert np.all(np.abs(J - Jref) <= 1e-12 * np.abs(Jref).max())
+
+
+def test_solver_mock_seam(lattice_file_2S_2A, monkeypatch):
+    """The reference's orchestration tests patch `odesolver._solve_ode` and count calls
+    (`test_simulations.py:135-160`): two calls per dynamics simulation."""
+    calls = []
+
+    def fake(t_arr, fun, fargs, jfun, jargs, y0, **kw):
+        calls.append((len(t_arr), fun.__name__))
+        return np.random.random((len(t_arr), len(np.ravel(y0))))
+
+    monkeypatch.setattr(odesolver, '_solve_ode', fake)
+    sim = Simulations(configs.sim_cte(), full_path=lattice_file_2S_2A)
+    sol = sim.simulate_dynamics()
+    assert calls == [(2, '_rate_eq_pulse'), (1000, '_rate_eq')]
+    assert sol.y_sol.shape == (1000, 18)
+
+
+def test_foreign_operands_are_rejected():
+    import scipy.sparse as sp
+    m = sp.csr_matrix(np.eye(3))
+    with pytest.raises(TypeError, match='no CPU fallback'):
+        odesolver.solve_relax(np.array([0.0, 1.0]), np.ones(3), m, m, np.zeros((0, 2), np.uint32),
+                              np.zeros((0, 3), np.uint32), sp.csr_matrix((3, 0)),
+                              np.zeros((0, 3), np.uint32), np.zeros((0, 4), np.uint32))
+
+
+def test_power_dependence_ESA_closed_form():
+    """Port of `test_sim_power_dep_ESA` (`test_simulations.py:347-407`) to the microscopic
+    equations: without energy transfer every ion is the same 3-level system and the CW steady
+    state is ES1 = GS*P/(k1+P), ES2 = GS*P^2/((k1+P)*k2) with P = pump_rate*power_dens."""
+    cte = configs.esa_cte(N_uc=6, A_conc=5.0, t_pulse=None, rtol=1e-8, atol=1e-15)
+    cte['lattice_seed'] = 3
+    sim = Simulations(cte)
+    powers = np.logspace(1, 6, 6)
+    sol = sim.simulate_power_dependence(powers)
+    assert isinstance(sol, PowerDependenceSolution) and len(sol) == 6
+    k1, k2, sigma = 1e3, 1e6, 1e-3
+    for s, power in zip(sol, powers):
+        GS, ES1, ES2 = [c[-1] for c in s.list_avg_data]
+        P = sigma * power
+        assert s.power_dens == power
+        assert np.isclose(ES1, GS * P / (k1 + P), rtol=1e-4)
+        assert np.isclose(ES2, GS * P ** 2 / ((k1 + P) * k2), rtol=1e-4)
+        assert np.allclose(s.steady_state_populations, 5.0 * np.array([GS, ES1, ES2]))
+
+
+def test_power_dependence_pulsed_matches_single_runs():
+    cte = configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=2.0)
+    cte['lattice_seed'] = 21
+    powers = [1e6, 1e9, 1e12]
+    sim = Simulations(cte)
+    batch = sim.simulate_power_dependence(powers)
+    light = Simulations(configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=2.0))
+    light.cte['lattice_seed'] = 21
+    no_y = light.simulate_power_dependence(powers, keep_y=False)
+    for k, P in enumerate(powers):
+        one = configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=2.0, power_dens=P)
+        one['lattice_seed'] = 21
+        single = Simulations(one).simulate_steady_state()
+        assert np.array_equal(single.y_sol, batch[k].y_sol)
+        assert np.allclose(batch[k].steady_state_populations, no_y[k].steady_state_populations,
+                           rtol=1e-10, atol=1e-300)
+    pops = batch.populations
+    assert pops.shape == (3, 11) and np.all(np.diff(pops[:, 1]) > 0)
+
+
+def test_concentration_dependence_and_sampling():
+    cte = configs.yb_tm_cte(N_uc=5, S_conc=5.0, A_conc=1.0)
+    cte['lattice_seed'] = 2
+    cte['simulation_params']['N_steps'] = 100
+    sim = Simulations(cte)
+    concs = [(5.0, 2.0), (20.0, 2.0)]
+    sol = sim.simulate_concentration_dependence(concs, N_uc_list=[6, 5], dynamics=True)
+    assert isinstance(sol, ConcentrationDependenceSolution) and len(sol) == 2
+    assert [tuple(c) for c in sol.concentrations] == concs
+    assert sol[0].y_sol.shape[0] == 100 and sol[0].y_sol.shape[1] != sol[1].y_sol.shape[1]
+    for s in sol:
+        ion_sums = s.y_sol[-1].sum() / (s.cte['ions']['total'])
+        assert np.isclose(ion_sums, 1.0, atol=1e-9)          # populations conserved per ion
+    avg = sim.sample_simulation(sim.simulate_dynamics, N_samples=2)
+    assert isinstance(avg, DynamicsSolution) and len(avg.list_avg_data_ofs) == 11
+
+
+def test_objective_batch_equals_sequential_objective(tmp_path, monkeypatch):
+    """`optimize.optim_fun` one candidate at a time == `objective_batch` on all candidates."""
+    cte = configs.yb_tm_cte(N_uc=5, S_conc=20.0, A_conc=2.0)
+    cte['lattice_seed'] = 4
+    cte['simulation_params']['N_steps'] = 200
+    # a synthetic "experimental" decay of Tm 3H4 so that the objective is not identically zero
+    exp_dir = tmp_path / 'expData' / 'bNaYF4'
+    exp_dir.mkdir(parents=True)
+    t = np.linspace(0, 0.02, 400)
+    curve = np.exp(-t / 1.5e-3) - np.exp(-t / 2e-4) + 0.01
+    np.savetxt(exp_dir / 'decay_Tm_3H4_exc_NIR_980_20.0Yb_2.0Tm.txt', np.column_stack((t, curve)))
+    monkeypatch.chdir(tmp_path)
+    sim = Simulations(cte)
+    base = [p.strength for p in cte['optimization']['processes']]
+    rng = np.random.default_rng(5000)
+    cands = [list(np.array(base) * 10.0 ** rng.uniform(-1, 1, len(base))) for _ in range(3)]
+    errors, sols = optimize.objective_batch(sim, cands)
+    assert errors.shape == (3, 11) and np.any(errors > 0)
+    for cand, err in zip(cands, errors):
+        seq = optimize.optim_fun(sim.simulate_dynamics, cand, sim)
+        assert np.allclose(seq, err, rtol=1e-9, atol=1e-12)
