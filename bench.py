@@ -303,8 +303,9 @@ def run_gpu(args):
     dev_ms_max, wall_ms_max, e2e_ms_max = [float(v) for v in times.tolist()]
     n_rhs = float(np.mean([p[0] for p in passes]))
     n_jv = float(np.mean([p[1] for p in passes]))
-    b_rhs = 12 * system.n_pairs + 16 * N      # compact layout: (u32 partner + f64 d^-6) per pair, y, dy
-    b_jv = 12 * system.n_pairs + 24 * N
+    bpp = system.bytes_per_pair                # 8: dense all-to-all blocks (f64 d^-6 per ordered pair)
+    b_rhs = bpp * system.n_pairs + 16 * N      # + y read, dy written once
+    b_jv = bpp * system.n_pairs + 24 * N
     kms = float(np.mean(kernel_ms))
     achieved = (n_rhs * b_rhs + n_jv * b_jv) / (kms * 1e-3) / 1e9
 
@@ -377,7 +378,7 @@ def large_lattice_roofline(device, peaks, peak_src):
             else:
                 _lib.check(system.lib.stb_jv_dev(system.handle, 0, 1, 1, y.data_ptr(), v.data_ptr(),
                                                  out.data_ptr(), rep, C.byref(ms)))
-        alg = 12 * system.n_pairs + (16 if name == 'rhs' else 24) * N
+        alg = system.bytes_per_pair * system.n_pairs + (16 if name == 'rhs' else 24) * N
         gbs = alg / (ms.value * 1e-3) / 1e9
         res[name] = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                      'frac': gbs / peaks['hbm_gbs'], 'ms_per_launch': ms.value,

@@ -93,7 +93,9 @@ stb_system* stb_system_create(int32_t device, int64_t n_ions, const uint8_t* ion
 void stb_system_destroy(stb_system* sys);
 
 /* Sizes: out[0]=n_ions, [1]=n_S, [2]=n_A, [3]=N (states), [4]=P (stored ordered pairs),
- * [5]=bytes of pair data streamed per RHS pass, [6]=padded pair slots. */
+ * [5]=bytes of pair data streamed per RHS pass, [6]=stored pair slots (padding included),
+ * [7]=lanes per row.  out[5] / out[6] = bytes per stored pair: 8 for the dense all-to-all
+ * blocks (d_max <= 0), 12 for the indexed lists of a cutoff lattice (one multipolarity). */
 int stb_system_info(const stb_system* sys, int64_t out[8]);
 
 /* index_S_i / index_A_j (int64[n_ions], -1 = other type) and initial_population

@@ -87,7 +87,8 @@ extern "C" int stb_device_count(void) {
 extern "C" int stb_describe(char* buf, int64_t buf_len) {
     snprintf(buf, (size_t)buf_len,
              "simetuc_b200 sm_100a; integrator: persistent cooperative kernel, %d threads/CTA, "
-             "GMRES(%d), BDF order<=%d; pair stream: sliced-ELL u32+f64",
+             "GMRES(%d), BDF order<=%d; pair stream: dense f64 blocks (all-to-all) / sliced-ELL u32+f64 "
+             "(cutoff)",
              STB_NT, STB_KRYLOV, STB_MAXORD);
     return STB_OK;
 }
@@ -338,6 +339,45 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     L.lpr = lpr;
     L.R = 32 / lpr;
     for (int T = 0; T < 2; ++T) L.n_slices[T] = (S->n[T] + L.R - 1) / L.R;
+    // ---- all-to-all lattices: dense blocks, no partner index (stb_common.cuh) --------------------
+    bool dense = !(d_max > 0.0);
+    if (const char* env = getenv("STB_DENSE")) dense = dense && atoi(env) != 0;
+    L.dense = dense ? 1 : 0;
+    for (int U = 0; U < 2; ++U) L.ld[U] = (S->n[U] + 31) & ~31;
+    if (dense) {
+        FillDenseArgs FD;
+        memset(&FD, 0, sizeof(FD));
+        FD.G = G;
+        FD.type = S->d_type;
+        FD.local_idx = S->d_local_idx;
+        FD.n_mult = L.n_mult;
+        for (int m = 0; m < L.n_mult; ++m) FD.mults[m] = L.mults[m];
+        S->pairs = 0;
+        S->slots = 0;
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) {
+                FD.ld[U] = L.ld[U];
+                L.blk[T][U].col = nullptr;
+                L.blk[T][U].line_ptr = nullptr;
+                if (L.blk[T][U].n_slots == 0 || S->n[T] == 0 || S->n[U] == 0) continue;
+                const size_t cells = (size_t)S->n[T] * L.ld[U];
+                for (int m = 0; m < L.n_mult; ++m) {
+                    CKP(cudaMalloc((void**)&S->d_g[T][U][m], cells * sizeof(double)));
+                    CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, cells * sizeof(double), S->stream));
+                    L.blk[T][U].g[m] = S->d_g[T][U][m];
+                    FD.g[T][U][m] = S->d_g[T][U][m];
+                }
+                S->slots += (int64_t)cells;
+            }
+        for (int q = 0; q < n; ++q)
+            for (int U = 0; U < 2; ++U)
+                if (L.blk[S->type[q]][U].n_slots > 0) S->pairs += S->len[(size_t)U * n + q];
+        S->stream_bytes = S->slots * 8 * (int64_t)L.n_mult;
+        g_launches++;
+        k_fill_dense<<<blocks, 256, 0, S->stream>>>(FD);
+        CKP(cudaGetLastError());
+        CKP(cudaStreamSynchronize(S->stream));
+    } else {
     // ---- slice line pointers ---------------------------------------------------------------------
     std::vector<int> ion_of_local[2];
     for (int T = 0; T < 2; ++T) ion_of_local[T].resize(S->n[T]);
@@ -401,6 +441,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
     CKP(cudaGetLastError());
     CKP(cudaStreamSynchronize(S->stream));
+    }
     cudaFree(d_geo);
     L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
     CKP(cudaMalloc((void**)&S->dL, sizeof(DevLattice)));
@@ -802,7 +843,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         }
         return worst;
     };
-    bool want_resident = staged && L.n_mult == 1;
+    bool want_resident = staged && L.n_mult == 1 && !L.dense;
     if (const char* env = getenv("STB_RESIDENT")) want_resident = want_resident && atoi(env) != 0;
     if (const char* env = getenv("STB_GROUP_CTAS")) {
         G = std::max(1, std::min(atoi(env), max_ctas));

@@ -116,6 +116,36 @@ __global__ void k_fill_pairs(FillArgs A) {
     }
 }
 
+struct FillDenseArgs {
+    Geo G;
+    const uint8_t* type;
+    const int* local_idx;
+    int n_mult;
+    int mults[STB_MAXM];
+    int ld[2];
+    double* g[2][2][STB_MAXM];  // [T][U][m] -> [n_T][ld[U]], zero-initialised; null = unused block
+};
+
+// dense all-to-all blocks: g[T][U][ql * ld[U] + kl] = d(q,k)^-mult, one warp per ion row
+__global__ void k_fill_dense(FillDenseArgs A) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const Geo& G = A.G;
+    for (int q = warp; q < G.n; q += nwarps) {
+        const int T = A.type[q] != 0;
+        const int64_t ql = A.local_idx[q];
+        for (int k = lane; k < G.n; k += 32) {
+            const int U = A.type[k] != 0;
+            if (A.g[T][U][0] == nullptr) continue;
+            const double d = geo_dist(G, q, k);
+            if (!geo_pair(G, d)) continue;
+            const int64_t idx = ql * A.ld[U] + A.local_idx[k];
+            for (int mm = 0; mm < A.n_mult; ++mm)
+                A.g[T][U][mm][idx] = pow(d, -(double)A.mults[mm]);
+        }
+    }
+}
+
 struct ExportArgs {
     const DevLattice* L;
     const uint8_t* type;
@@ -155,10 +185,32 @@ __global__ void k_export(ExportArgs A) {
                     continue;
                 int mi = 0;
                 for (int m = 0; m < L.n_mult; ++m) if (L.mults[m] == pr.mult) mi = m;
-                for (int e = lane; e < cnt; e += 32) {
-                    int64_t line = B.line_ptr[slice] + e / L.lpr;
-                    int64_t idx = line * 32 + rl * L.lpr + e % L.lpr;
-                    int gk = A.gs_of_local[U][B.col[idx]];
+                // dense blocks: the partner list is every column with a non-zero rate, compacted
+                // in ascending order (np.nonzero(dist), lattice.py:335); sliced-ELL: stored lists
+                const int span = L.dense ? ((L.n[U] + 31) & ~31) : ((cnt + 31) & ~31);
+                int seen = 0;
+                for (int e0 = 0; e0 < span; e0 += 32) {
+                    int e = e0 + lane;
+                    int64_t idx = 0;
+                    int kl = 0;
+                    bool ok;
+                    if (L.dense) {
+                        idx = (int64_t)ql * L.ld[U] + e;
+                        ok = e < L.n[U] && B.g[0][idx] != 0.0;
+                        kl = e;
+                        const unsigned m = __ballot_sync(0xffffffffu, ok);
+                        e = seen + __popc(m & ((1u << lane) - 1u));
+                        seen += __popc(m);
+                    } else {
+                        ok = e < cnt;
+                        if (ok) {
+                            int64_t line = B.line_ptr[slice] + e / L.lpr;
+                            idx = line * 32 + rl * L.lpr + e % L.lpr;
+                            kl = B.col[idx];
+                        }
+                    }
+                    if (!ok) continue;
+                    int gk = A.gs_of_local[U][kl];
                     double w = B.g[mi][idx] * pr.strength;   // dist**(-mult)*strength (:289)
                     int64_t o = r + e;
                     if (A.N_indices) {

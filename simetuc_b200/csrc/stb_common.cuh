@@ -10,6 +10,11 @@
 //     (partner index u32, d^-mult f64) in a sliced-ELL block: a slice is R = 32/lpr consecutive
 //     rows of one type handled by one warp, `lpr` lanes cooperate on a row, and the slice is
 //     stored as lines of 32 entries so that lane L reads entry [line*32 + L]: fully coalesced.
+//   * all-to-all lattices (no cutoff: the reference's semantics, lattice.py:335) need no partner
+//     index at all: the partners of a row are ALL ions of type U, so a block is the DENSE matrix
+//     g[q * ld[U] + k] = d(q,k)^-mult (0 on the diagonal, for coincident ions and in the padding
+//     of a row to ld[U] = round_up(n[U], 32)): 8 bytes per ordered pair instead of 12, and the
+//     gather of the partner populations becomes a contiguous read.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,9 +31,9 @@
 #define STB_NW (STB_NT / 32)
 
 struct PairBlock {
-    const uint32_t* col;         // [lines*32] partner index, type-local
-    const double* g[STB_MAXM];   // [lines*32] d^-mult
-    const int64_t* line_ptr;     // [n_slices(T)+1]
+    const uint32_t* col;         // [lines*32] partner index, type-local (null: dense block)
+    const double* g[STB_MAXM];   // [lines*32] d^-mult, or dense [n[T]][ld[U]]
+    const int64_t* line_ptr;     // [n_slices(T)+1] (sliced-ELL only)
     int n_slots;
     int slot_col[STB_MAXC];      // partner state whose population is accumulated
     int slot_mult[STB_MAXC];     // which g[]
@@ -45,6 +50,8 @@ struct DevLattice {
     int n_ions, N, NF;
     int n[2], s[2], off[2];      // ions / states / plane offset per type
     int lpr, R;                  // lanes per row, rows per slice (R*lpr == 32)
+    int dense;                   // 1: dense all-to-all blocks (no partner index), 0: sliced-ELL
+    int ld[2];                   // dense: row pitch of a block over partners of type U
     int n_slices[2];
     int n_mult, mults[STB_MAXM];
     int n_proc;

@@ -115,6 +115,66 @@ __device__ __forceinline__ void stream_block_multi(const PairBlock& B, int nU, c
     }
 }
 
+// ---- dense all-to-all blocks: g[q * ld + k], partner k = column index, no index stream ------
+// A row is read by its `lpr` lanes, lane gl takes k = gl, gl + lpr, ...; the gathered
+// populations z[sc + k] are contiguous across the lanes.  Padding (k >= nU) holds g = 0 and the
+// population index is clamped.
+template <int NS, int STB_UN>
+__device__ __forceinline__ void stream_dense_t(const PairBlock& B, int nU, int ld, int lpr,
+                                               const double* zU, int q, int gl,
+                                               double (&acc)[STB_MAXC]) {
+    int sc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) sc[s] = B.slot_col[s] * nU;
+    const double* gp = B.g[0] + (int64_t)q * ld + gl;
+    const int nl = ld / lpr, kmax = nU - 1;
+    int i = 0;
+    for (; i + STB_UN <= nl; i += STB_UN) {
+        double g[STB_UN];
+#pragma unroll
+        for (int u = 0; u < STB_UN; ++u) g[u] = ld_stream(gp + (i + u) * lpr);
+#pragma unroll
+        for (int u = 0; u < STB_UN; ++u) {
+            const int k = min(gl + (i + u) * lpr, kmax);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] = fma(g[u], zU[sc[s] + k], acc[s]);
+        }
+    }
+    for (; i < nl; i += 4) {
+        double g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = ld_stream(gp + (i + u < nl ? i + u : nl - 1) * lpr);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double gu = i + u < nl ? g[u] : 0.0;
+            const int k = min(gl + (i + u) * lpr, kmax);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) acc[s] = fma(gu, zU[sc[s] + k], acc[s]);
+        }
+    }
+}
+
+__device__ __forceinline__ void stream_dense_multi(const PairBlock& B, int nU, int ld, int lpr,
+                                                   const double* zU, int q, int gl,
+                                                   double (&acc)[STB_MAXC]) {
+    const int ns = B.n_slots, kmax = nU - 1;
+    for (int k0 = gl; k0 < ld; k0 += lpr) {
+        const int64_t idx = (int64_t)q * ld + k0;
+        const int k = min(k0, kmax);
+        double g[STB_MAXM];
+#pragma unroll
+        for (int m = 0; m < STB_MAXM; ++m) g[m] = B.g[m] ? ld_stream(B.g[m] + idx) : 0.0;
+#pragma unroll
+        for (int s = 0; s < STB_MAXC; ++s) {
+            if (s < ns) {
+                const int m = B.slot_mult[s];
+                const double gg = m == 0 ? g[0] : (m == 1 ? g[1] : g[2]);
+                acc[s] = fma(gg, zU[B.slot_col[s] * nU + k], acc[s]);
+            }
+        }
+    }
+}
+
 // Fields of the rows of slice `slice` of type T gathered from the plane vector z (global memory
 // or a shared-memory copy), multiplied by `scale`.  On return every lane of a row holds the
 // row's reduced sums in Fq[0..nf[T]): partner-S slots first, then partner-A slots.  One
@@ -135,9 +195,26 @@ __device__ __forceinline__ double slice_fields_impl(const DevLattice& L, int T, 
         double acc[STB_MAXC];
 #pragma unroll
         for (int s = 0; s < STB_MAXC; ++s) acc[s] = 0.0;
-        const int64_t l0 = B.line_ptr[slice], l1 = B.line_ptr[slice + 1];
         const double* zU = z + L.off[U];
         const int nU = L.n[U];
+        if (L.dense) {
+            if (nU > 0) {
+                const int q = min(slice * L.R + lane / L.lpr, L.n[T] - 1);
+                if (L.n_mult > 1) {
+                    stream_dense_multi(B, nU, L.ld[U], L.lpr, zU, q, gl, acc);
+                } else {
+                    switch (ns) {
+                        case 1: stream_dense_t<1, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                        case 2: stream_dense_t<2, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                        case 3: stream_dense_t<3, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                        case 4: stream_dense_t<4, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                        case 5: stream_dense_t<5, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                        default: stream_dense_t<6, UN>(B, nU, L.ld[U], L.lpr, zU, q, gl, acc); break;
+                    }
+                }
+            }
+        } else {
+        const int64_t l0 = B.line_ptr[slice], l1 = B.line_ptr[slice + 1];
         if (L.n_mult > 1) {
             stream_block_multi(B, nU, zU, l0, l1, lane, acc);
         } else {
@@ -149,6 +226,7 @@ __device__ __forceinline__ double slice_fields_impl(const DevLattice& L, int T, 
                 case 5: stream_block_t<5, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
                 default: stream_block_t<6, UN, NC>(B, nU, zU, l0, l1, lane, acc); break;
             }
+        }
         }
         for (int o = L.lpr >> 1; o > 0; o >>= 1) {
 #pragma unroll

@@ -65,6 +65,8 @@ class RateSystem:
          self.n_slots, self.lanes_per_row) = [int(v) for v in info]
         self.sS, self.sA = lattice.n_S_states, lattice.n_A_states
         self.n_sys = 1
+        #: bytes streamed per stored pair: 8 (dense all-to-all blocks) or 4 + 8 per multipolarity
+        self.bytes_per_pair = self.stream_bytes // self.n_slots if self.n_slots else 0
 
     # ------------------------------------------------------------------ lifetime
     def close(self):

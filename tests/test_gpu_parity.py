@@ -247,3 +247,25 @@ def test_group_sizes_agree(monkeypatch):
     for G in (4, 16):
         assert np.all(np.abs(res[G] - res[1]) <= 1e-9 * np.abs(res[1]) + 1e-18)
     system.close()
+
+
+def test_dense_and_indexed_formats_agree(monkeypatch):
+    """All-to-all lattices are stored as dense blocks (8 B per ordered pair, no partner index);
+    STB_DENSE=0 forces the indexed sliced-ELL lists used for cutoff lattices.  Both must give the
+    same interaction export (bit-exact) and the same RHS / Jv up to summation order."""
+    g = load_golden('240S_108A')
+    cte = configs.test_cte()
+    a = make_system(g, cte)
+    monkeypatch.setenv('STB_DENSE', '0')
+    b = make_system(g, cte)
+    monkeypatch.delenv('STB_DENSE')
+    assert a.bytes_per_pair == 8 and b.bytes_per_pair == 12 and a.n_pairs == b.n_pairs
+    for x, y in zip(a.export_interactions(), b.export_interactions()):
+        assert np.array_equal(x, y)
+    ya, va = g['test_y'], g['test_v']
+    fa, fb = a.rhs(ya[0], pulse=True), b.rhs(ya[0], pulse=True)
+    assert np.all(np.abs(fa - fb) <= 1e-13 * np.abs(fb).max())
+    ja, jb = a.jv(ya[0], va[0], pulse=True), b.jv(ya[0], va[0], pulse=True)
+    assert np.all(np.abs(ja - jb) <= 1e-13 * np.abs(jb).max())
+    a.close()
+    b.close()
