@@ -10,6 +10,7 @@
 
 #include "stb_build.cuh"
 #include "stb_integrate.cuh"
+#include "stb_integrate_cl.cuh"
 #include "stb_kernels.cuh"
 
 static thread_local std::string g_err;
@@ -793,6 +794,237 @@ extern "C" int stb_jv_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cluster integrator (small lattices): launch plan and driver.
+struct ClPlan {
+    int G = 0, n_clusters = 0, resmask = 0, v_smem = 0, d_smem = 0;
+    size_t dyn_bytes = 0;
+    double resident_frac = 0.0;
+};
+
+static cudaError_t cl_max_clusters(int G, size_t dyn_bytes, int sm_count, int* out) {
+    cudaError_t e = cudaFuncSetAttribute(k_integrate_cl, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dyn_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(sm_count / G * G));
+    cfg.blockDim = dim3(STB_NT);
+    cfg.dynamicSmemBytes = dyn_bytes;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = (unsigned)G;
+    at.val.clusterDim.y = 1;
+    at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(out, k_integrate_cl, &cfg);
+}
+
+// Picks the cluster size and what lives in shared memory; false = use the cooperative-grid
+// integrator (large lattices, cutoff lists, several multipolarities).
+static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
+    const DevLattice& L = S->hL;
+    if (!L.dense || L.n_mult != 1) return false;
+    if (const char* env = getenv("STB_CLUSTER")) if (atoi(env) == 0) return false;
+    int forced = 0;
+    if (const char* env = getenv("STB_GROUP_CTAS")) {
+        forced = atoi(env);
+        if (forced != 1 && forced != 2 && forced != 4 && forced != 8) return false;
+    }
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, k_integrate_cl) != cudaSuccess) { cudaGetLastError(); return false; }
+    const size_t cap = 232448 - fa.sharedSizeBytes - 64;   // 227 KB per CTA
+    int want_res = 1;
+    if (const char* env = getenv("STB_RESIDENT")) want_res = atoi(env) != 0;
+    ClPlan best;
+    double best_score = -1.0;
+    for (int G = 8; G >= 1; G >>= 1) {
+        if (forced && G != forced) continue;
+        ClLayout Y;
+        cl_layout(L, G, 0, 0, 0, Y);
+        if ((Y.cntp[0] + Y.cntp[1]) / CL_RG > CL_MAXRG) continue;
+        if ((size_t)Y.total * 8 > cap) continue;
+        // shared memory goes first to the pair rows (largest block first), then to the Krylov
+        // basis, then to the difference array
+        int mask = 0, v_smem = 0, d_smem = 0;
+        int64_t all = 0, res = 0;
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) all += cl_block_doubles(L, Y, T, U);
+        bool used[4] = {false, false, false, false};
+        for (int round = 0; round < 4 && want_res; ++round) {
+            int pick = -1, pick_sz = 0;
+            for (int b = 0; b < 4; ++b) {
+                int sz = cl_block_doubles(L, Y, b >> 1, b & 1);
+                if (!used[b] && sz > pick_sz) { pick = b; pick_sz = sz; }
+            }
+            if (pick < 0) break;
+            used[pick] = true;
+            ClLayout Z;
+            cl_layout(L, G, mask | (1 << pick), 0, 0, Z);
+            if ((size_t)Z.total * 8 <= cap) { mask |= 1 << pick; res += pick_sz; }
+        }
+        {
+            ClLayout Z;
+            cl_layout(L, G, mask, 1, 0, Z);
+            if ((size_t)Z.total * 8 <= cap) v_smem = 1;
+            cl_layout(L, G, mask, v_smem, 1, Z);
+            if ((size_t)Z.total * 8 <= cap) d_smem = 1;
+        }
+        cl_layout(L, G, mask, v_smem, d_smem, Y);
+        const size_t bytes = (size_t)Y.total * sizeof(double);
+        int maxc = 0;
+        cudaError_t e = cl_max_clusters(G, bytes, S->sm_count, &maxc);
+        if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
+        // rounds of the batch x time of one system (falls with G, less than linearly; streaming
+        // the pair rows from L2 instead of shared memory roughly doubles a pass)
+        const int ncl = std::min(maxc, n);
+        const double rounds = std::ceil((double)n / ncl);
+        const double rf = all > 0 ? (double)res / (double)all : 1.0;
+        const double t_sys = (2.0 - rf) * (0.35 + 1.0 / G);
+        const double score = 1.0 / (rounds * t_sys);
+        if (score > best_score) {
+            best_score = score;
+            best.G = G; best.n_clusters = ncl; best.resmask = mask;
+            best.v_smem = v_smem; best.d_smem = d_smem; best.dyn_bytes = bytes;
+            best.resident_frac = rf;
+        }
+    }
+    if (best_score < 0.0) return false;
+    plan = best;
+    return true;
+}
+
+static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, int32_t n, int32_t pulse,
+                             int64_t n_t, const double* t, const double* y0, double rtol, double atol,
+                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats, bool dev) {
+    const int N = S->N;
+    const DevLattice& L = S->hL;
+    ClLayout Y;
+    cl_layout(L, plan.G, plan.resmask, plan.v_smem, plan.d_smem, Y);
+    const int64_t work_stride = (int64_t)(STB_KRYLOV + 1 + 8) * Y.PO;
+    double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_tmp = nullptr,
+           *d_avg = nullptr;
+    int* d_next = nullptr;
+    long long* d_prof = nullptr;
+    stb_stats* d_stats = nullptr;
+    const size_t out_bytes = sizeof(double) * (size_t)n * n_t * N;
+    auto cleanup = [&]() {
+        cudaFree(d_work); cudaFree(d_y0); cudaFree(d_yout); cudaFree(d_t); cudaFree(d_tmp);
+        cudaFree(d_avg); cudaFree(d_next); cudaFree(d_stats); cudaFree(d_prof);
+    };
+#define CKC(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            cleanup();                                                                \
+            return e_ == cudaErrorMemoryAllocation ? STB_ENOMEM : STB_ECUDA;          \
+        }                                                                             \
+    } while (0)
+    CKC(cudaMalloc((void**)&d_work, sizeof(double) * (size_t)plan.n_clusters * plan.G * work_stride));
+    const bool own_yout = !(dev && y_out);
+    if (!dev) {
+        CKC(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
+        CKC(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
+        CKC(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+    }
+    if (own_yout) CKC(cudaMalloc((void**)&d_yout, out_bytes));
+    CKC(cudaMalloc((void**)&d_next, sizeof(int)));
+    CKC(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
+    CKC(cudaMalloc((void**)&d_prof, sizeof(long long) * 16));
+    CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16, S->stream));
+    CKC(cudaMemsetAsync(d_next, 0, sizeof(int), S->stream));
+    CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
+    double* yout_p = own_yout ? d_yout : y_out;
+    CKC(cudaMemsetAsync(yout_p, 0, out_bytes, S->stream));
+    const double *t_p = t, *y0_p = y0;
+    if (!dev) {
+        CKC(cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
+        CKC(cudaMemcpyAsync(d_tmp, y0, sizeof(double) * (size_t)n * N, cudaMemcpyHostToDevice, S->stream));
+        int64_t tot = (int64_t)n * N;
+        g_launches++;
+        k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
+        CKC(cudaGetLastError());
+        t_p = d_t;
+        y0_p = d_y0;
+    }
+    ClArgs A;
+    memset(&A, 0, sizeof(A));
+    A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
+    A.first = first; A.n_sys = n; A.pulse = pulse; A.G = plan.G;
+    A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
+    A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;
+    A.nsteps = nsteps > 0 ? nsteps : 1000;
+    A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
+    A.next_sys = d_next;
+    A.prof = d_prof;
+    S->last_G = plan.G; S->last_groups = plan.n_clusters;
+    if (getenv("STB_VERBOSE"))
+        fprintf(stderr, "[stb] cluster integrator: n=%d G=%d clusters=%d resmask=%x (%.0f%% of pair rows "
+                "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d\n", n, plan.G, plan.n_clusters,
+                plan.resmask, 100.0 * plan.resident_frac, plan.v_smem, plan.d_smem, plan.dyn_bytes, Y.PO);
+    cudaEvent_t e0, e1;
+    CKC(cudaEventCreate(&e0));
+    CKC(cudaEventCreate(&e1));
+    CKC(cudaEventRecord(e0, S->stream));
+    {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(plan.n_clusters * plan.G));
+        cfg.blockDim = dim3(STB_NT);
+        cfg.dynamicSmemBytes = plan.dyn_bytes;
+        cfg.stream = S->stream;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = (unsigned)plan.G;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        g_launches++;
+        CKC(cudaFuncSetAttribute(k_integrate_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dyn_bytes));
+        CKC(cudaLaunchKernelEx(&cfg, k_integrate_cl, A));
+    }
+    CKC(cudaEventRecord(e1, S->stream));
+    S->last_launches = dev ? 1 : 2;
+    if (avg_out) {
+        double* avg_p = avg_out;
+        if (!dev) {
+            CKC(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
+            avg_p = d_avg;
+        }
+        g_launches++;
+        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
+        CKC(cudaGetLastError());
+        S->last_launches += 1;
+        if (!dev)
+            CKC(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
+                                cudaMemcpyDeviceToHost, S->stream));
+    }
+    if (y_out && !dev) CKC(cudaMemcpyAsync(y_out, d_yout, out_bytes, cudaMemcpyDeviceToHost, S->stream));
+    S->last_prof.assign((size_t)8 * n, 0);
+    if (stats) CKC(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
+    CKC(cudaStreamSynchronize(S->stream));
+    CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
+    if (getenv("STB_VERBOSE")) {
+        long long pr[16];
+        CKC(cudaMemcpy(pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
+        static const char* names[16] = {"stream", "stream_sync", "combine", "yk_barrier", "rhs_epilogue",
+                                        "block_inv", "residual", "beta_reduce", "arnoldi_epi", "dots",
+                                        "dots_reduce", "orth_push", "v_barrier", "newton_tail", "step_ctl",
+                                        "loop_head"};
+        double tot = 0;
+        for (int k = 0; k < 16; ++k) tot += (double)pr[k];
+        fprintf(stderr, "[stb] %.3f ms; last system of cluster 0, kcycles:", S->last_ms);
+        for (int k = 0; k < 16; ++k) fprintf(stderr, " %s=%.0f(%.0f%%)", names[k], pr[k] / 1e3, 100.0 * pr[k] / std::max(tot, 1.0));
+        fprintf(stderr, "\n");
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cleanup();
+    return STB_OK;
+}
+
 static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
                           const double* t, const double* y0, double rtol, double atol,
                           int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats,
@@ -810,7 +1042,13 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     const DevLattice& L = S->hL;
     const int NMinv = L.s[0] * L.s[0] * L.n[0] + L.s[1] * L.s[1] * L.n[1];
 
-    // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
+    // ---- small lattices: one thread-block cluster per system (stb_integrate_cl.cuh) ------------
+    {
+        ClPlan plan;
+        if (cl_choose(S, n, plan))
+            return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
+                                     avg_out, stats, dev);
+    }
     // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
     const int max_ctas = S->sm_count;   // one CTA per SM
     const int total_slices = L.n_slices[0] + L.n_slices[1];

@@ -1,0 +1,1220 @@
+// Cluster integrator: the stiff integrator of stb_integrate.cuh (same BDF / Newton-Krylov /
+// block-Jacobi algorithm, same constants) re-laid for SMALL lattices, where a solve is bound by
+// the latency of one Krylov iteration and not by memory bandwidth.  Replaces
+// odesolver._solve_ode (odesolver.py:85-137) for every system whose working set fits on a few
+// SMs - the power / concentration / optimiser sweeps of BASELINE.json.
+//
+//   * one ODE system = one THREAD-BLOCK CLUSTER of G CTAs (G = 1, 2, 4, 8).  CTAs of a cluster
+//     exchange the gathered state vector and the partial dot products through distributed
+//     shared memory (st.shared::cluster) and synchronise with the hardware cluster barrier:
+//     no global-memory atomics, no cooperative launch, no L2 round trip per exchange.
+//   * a CTA owns a fixed set of ion rows.  Their dense pair rows are copied ONCE per launch into
+//     shared memory (k-pair interleaved: one LDS.128 = two partners of one row); every hot
+//     vector of the Newton-Krylov iteration lives in shared memory too.
+//   * the pair pass maps a warp to 8 rows x 4 partner-pair lanes; the 16 warps take equal
+//     shares of the CTA's (row group, partner step) work list, split at arbitrary points, and
+//     combine partial fields deterministically (fixed warp order).
+//   * per-ion work (block matvec, ET rate terms, block-Jacobi apply) is thread-per-state.
+//   * one cluster barrier per reduction, two per Krylov iteration: dot products and ||w||^2
+//     travel together (the new basis vector's norm follows from Pythagoras, re-orthogonalised
+//     explicitly only on cancellation), ||dy|| of a Newton update is the norm of the GMRES
+//     coefficients, the error test and the order selection share one reduction.
+#pragma once
+#include "stb_integrate.cuh"
+
+#define CL_RG 8            // rows per row group
+#define CL_MAXRG 256       // row groups per CTA
+#define CL_MAXG 8
+
+struct ClLayout {          // offsets in doubles into dynamic shared memory
+    int NZ;                // gathered vector, padded planes
+    int ldz[2], zoff[2];
+    int cntm[2], cntp[2];  // max own rows per type (over the ranks), rounded up to CL_RG
+    int PO;                // pitch of own-compact vectors
+    int nkp[2], nst[2];    // partner pairs / warp steps (4 pairs) per partner type
+    int zy, zv, dd, psi, scl, fv, tw, kv, minv, F, Pp, part, info, V, D, gres;
+    int gres_off[2][2];    // resident pair rows of block [T][U], relative to gres (-1: streamed)
+    int nfm;               // field slots per row, max over the types
+    int foff[2], moff[2];
+    int64_t total;         // doubles
+};
+
+__host__ __device__ inline int cl_pow2ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// doubles of the shared-memory copy of a CTA's rows of block [T][U] (0: block unused)
+__host__ __device__ inline int cl_block_doubles(const DevLattice& L, const ClLayout& Y, int T, int U) {
+    if (L.blk[T][U].n_slots <= 0 || L.n[T] <= 0 || L.n[U] <= 0) return 0;
+    return Y.nst[U] * 4 * Y.cntp[T] * 2;
+}
+
+// Layout shared by the host (sizing, feasibility) and the kernel.  v_smem / d_smem / resident say
+// whether the Krylov basis, the difference array and the pair rows live in shared memory.
+__host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmask, int v_smem,
+                                          int d_smem, ClLayout& Y) {
+    for (int U = 0; U < 2; ++U) {
+        Y.ldz[U] = (L.n[U] + 1) & ~1;
+        Y.nkp[U] = Y.ldz[U] / 2;
+        Y.nst[U] = (Y.nkp[U] + 3) / 4;
+        Y.cntm[U] = (L.n[U] + G - 1) / G;
+        Y.cntp[U] = (Y.cntm[U] + CL_RG - 1) / CL_RG * CL_RG;
+    }
+    Y.zoff[0] = 0;
+    Y.zoff[1] = L.s[0] * Y.ldz[0];
+    Y.NZ = ((Y.zoff[1] + L.s[1] * Y.ldz[1] + 8) + 1) & ~1;     // + slack for padded partner steps
+    const int n_own = L.s[0] * Y.cntm[0] + L.s[1] * Y.cntm[1];
+    Y.PO = (n_own + 31) & ~31;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    Y.zy = take(Y.NZ);
+    Y.zv = take(Y.NZ);
+    Y.dd = take(Y.PO);
+    Y.psi = take(Y.PO);
+    Y.scl = take(Y.PO);
+    Y.fv = take(Y.PO);
+    Y.tw = take(Y.PO);
+    Y.kv = take(Y.PO);
+    Y.moff[0] = 0;
+    Y.moff[1] = L.s[0] * L.s[0] * Y.cntm[0];
+    Y.minv = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);
+    Y.nfm = L.nf[0] > L.nf[1] ? L.nf[0] : L.nf[1];
+    if (Y.nfm < 1) Y.nfm = 1;
+    Y.foff[0] = 0;
+    Y.foff[1] = L.nf[0] * Y.cntp[0];
+    Y.F = take(Y.foff[1] + L.nf[1] * Y.cntp[1]);
+    Y.Pp = take(STB_NW * 2 * Y.nfm * CL_RG);
+    Y.part = take(2 * CL_MAXG * STB_KRED);
+    Y.info = take(Y.PO);                       // two int tables of PO entries
+    Y.V = v_smem ? take((STB_KRYLOV + 1) * Y.PO) : -1;
+    Y.D = d_smem ? take(8 * Y.PO) : -1;
+    Y.gres = o;
+    int r = 0;
+    for (int T = 0; T < 2; ++T)
+        for (int U = 0; U < 2; ++U) {
+            Y.gres_off[T][U] = -1;
+            if (!((resmask >> (2 * T + U)) & 1)) continue;
+            Y.gres_off[T][U] = r;
+            r += cl_block_doubles(L, Y, T, U);
+        }
+    o += r;
+    Y.total = o;
+}
+
+struct ClArgs {
+    const DevLattice* L;
+    const double* blocks;
+    const double* strengths;
+    int first, n_sys, pulse;
+    int G;
+    int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
+    int64_t n_t;
+    const double* t;
+    const double* y0;          // [n_sys][N] planes
+    double rtol, atol;
+    int64_t nsteps;
+    double* y_out;             // [n_sys][n_t][N] reference layout
+    stb_stats* stats;
+    double* work;              // [n_clusters][G][work_stride]: spilled V / D
+    int64_t work_stride;
+    int* next_sys;             // work counter (dynamic assignment of systems to clusters)
+    long long* prof;           // [16] clock64 cycles per phase (cluster 0, rank 0, thread 0); may be null
+};
+
+__device__ __forceinline__ uint32_t cl_smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ uint32_t cl_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_st_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void cl_st_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cl_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                     : "memory");
+}
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ double2 cl_ld_nc2(const double* p) {
+    double2 v;
+    asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// Fields of 8 rows x (partner pairs kk, kk+4, ...) over warp steps [s0, s1) of one block.
+//   RES: pair rows resident in shared memory, layout [pair][own row][2];
+//   else: global dense block, row-major, pitch ld (even), read through the non-allocating path.
+template <int NS, bool RES>
+__device__ __forceinline__ void cl_stream(const double* gb, int64_t pitch, int row, const double* zU,
+                                          int ldz, const int* slot_col, int nkp, int kk, int s0,
+                                          int s1, double (&acc)[STB_MAXC]) {
+    const double* zs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) zs[s] = zU + slot_col[s] * ldz;
+    const int kmax = nkp - 1;
+    int st = s0;
+    for (; st + 4 <= s1; st += 4) {
+        double2 g[4];
+        int kz[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int kp = (st + u) * 4 + kk;
+            if (RES) {
+                g[u] = *reinterpret_cast<const double2*>(gb + ((int64_t)kp * pitch + row) * 2);
+                kz[u] = 2 * kp;
+            } else {
+                const int kc = min(kp, kmax);
+                g[u] = cl_ld_nc2(gb + (int64_t)row * pitch + 2 * kp);
+                kz[u] = 2 * kc;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const double2 z = *reinterpret_cast<const double2*>(zs[s] + kz[u]);
+                acc[s] = fma(g[u].x, z.x, acc[s]);
+                acc[s] = fma(g[u].y, z.y, acc[s]);
+            }
+        }
+    }
+    for (; st < s1; ++st) {
+        const int kp = st * 4 + kk;
+        double2 g;
+        int kz;
+        if (RES) {
+            g = *reinterpret_cast<const double2*>(gb + ((int64_t)kp * pitch + row) * 2);
+            kz = 2 * kp;
+        } else {
+            g = cl_ld_nc2(gb + (int64_t)row * pitch + 2 * kp);
+            kz = 2 * min(kp, kmax);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const double2 z = *reinterpret_cast<const double2*>(zs[s] + kz);
+            acc[s] = fma(g.x, z.x, acc[s]);
+            acc[s] = fma(g.y, z.y, acc[s]);
+        }
+    }
+}
+
+template <bool RES>
+__device__ __forceinline__ void cl_stream_ns(int ns, const double* gb, int64_t pitch, int row,
+                                             const double* zU, int ldz, const int* slot_col, int nkp,
+                                             int kk, int s0, int s1, double (&acc)[STB_MAXC]) {
+    switch (ns) {
+        case 1: cl_stream<1, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        case 2: cl_stream<2, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        case 3: cl_stream<3, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        case 4: cl_stream<4, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        case 5: cl_stream<5, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        default: cl_stream<6, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+    }
+}
+
+struct ClConst {           // per-CTA constants that are indexed dynamically: shared, not local memory
+    int r_lo[2], cnt[2], ob[2], nrg[2];
+    int stp[2][2], cst[2][2], ST[2], WT[2], Wt[2];
+    const double* gsrc[2][2];
+    long long gpitch[2][2];
+    int gres_on[2][2];
+    double GAMMA[6], ALPHA[6], ERRC[6];
+    double Rs[36], Us[36];
+};
+
+// RU = R(order, factor) . R(order, 1) with caller-provided scratch (thread 0)
+__device__ __forceinline__ void cl_compute_RU(int order, double factor, double* RU, double* R, double* U) {
+    compute_R(order, factor, R);
+    compute_R(order, 1.0, U);
+    const int n = order + 1;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc += R[i * 6 + k] * U[k * 6 + j];
+            RU[i * 6 + j] = acc;
+        }
+}
+
+struct ClShared {
+    DevLattice L;
+    ClConst K;
+    SysParams P;
+    Ctl C;
+    ClLayout Y;
+    double H[(STB_KRYLOV + 1) * STB_KRYLOV];
+    double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
+    double red[STB_NW * 4];
+    double rv[STB_KRED];
+    int wb_g[STB_NW + 1], wb_t[STB_NW + 1];      // work-list boundaries of the warps
+    int part_rg[STB_NW + 2], n_part;             // row groups shared by several warps
+    short rg_w0[CL_MAXRG], rg_w1[CL_MAXRG];
+    short tl_ptr[2][STB_MAXS + 1];               // rate terms touching state a of type T
+    short tl_ent[2][2 * STB_MAXT];               // term index | sign bit (0x4000: +, i.e. b == a)
+    int cur_sys;
+    long long prof[16];
+};
+
+__global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
+    extern __shared__ __align__(16) double dyn[];
+    __shared__ ClShared S;
+    DevLattice& L = S.L;
+    SysParams& P = S.P;
+    Ctl& C = S.C;
+    ClLayout& Y = S.Y;
+
+    const int G = A.G;
+    const int rank = G > 1 ? (int)cl_rank() : 0;
+    const int cid = blockIdx.x / G;
+    const int n_clusters = gridDim.x / G;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < (int)(sizeof(DevLattice) / 4); i += STB_NT) ((int*)&L)[i] = ((const int*)A.L)[i];
+    __syncthreads();
+    if (tid == 0) cl_layout(L, G, A.resmask, A.v_smem, A.d_smem, Y);
+    __syncthreads();
+    const int N = L.N;
+
+    long long tick = clock64();
+    if (tid == 0) for (int k = 0; k < 16; ++k) S.prof[k] = 0;
+#define CLPROF(k)                                            \
+    if (tid == 0) {                                          \
+        const long long now_ = clock64();                    \
+        S.prof[k] += now_ - tick;                            \
+        tick = now_;                                         \
+    }
+    // ---- ownership ---------------------------------------------------------------------------
+    ClConst& K = S.K;
+    int (&r_lo)[2] = K.r_lo;
+    int (&cnt)[2] = K.cnt;
+    int (&ob)[2] = K.ob;
+    int (&nrg)[2] = K.nrg;
+    int (&stp)[2][2] = K.stp;
+    int (&cst)[2][2] = K.cst;
+    int (&ST)[2] = K.ST;
+    int (&WT)[2] = K.WT;
+    int (&Wt)[2] = K.Wt;
+    const double* (&gsrc)[2][2] = K.gsrc;
+    long long (&gpitch)[2][2] = K.gpitch;
+    int (&gres_on)[2][2] = K.gres_on;
+    double (&GAMMA)[6] = K.GAMMA;
+    double (&ALPHA)[6] = K.ALPHA;
+    double (&ERRC)[6] = K.ERRC;
+    if (tid == 0) {
+        for (int T = 0; T < 2; ++T) {
+            r_lo[T] = (int)(((int64_t)L.n[T] * rank) / G);
+            cnt[T] = (int)(((int64_t)L.n[T] * (rank + 1)) / G) - r_lo[T];
+            nrg[T] = (cnt[T] + CL_RG - 1) / CL_RG;
+        }
+        ob[0] = 0;
+        ob[1] = L.s[0] * cnt[0];
+        // work list of the pair pass: row groups of type 0 first; a row group of type T has
+        // nst[0] (if block [T][0] is used) + nst[1] steps; a step of block [T][U] costs about
+        // 2 + 3 * n_slots instruction slots
+        for (int T = 0; T < 2; ++T) {
+            for (int U = 0; U < 2; ++U) {
+                const bool used = L.blk[T][U].n_slots > 0 && L.n[U] > 0;
+                stp[T][U] = used ? Y.nst[U] : 0;
+                cst[T][U] = 2 + 3 * L.blk[T][U].n_slots;
+                gsrc[T][U] = L.blk[T][U].g[0] ? L.blk[T][U].g[0] + (int64_t)r_lo[T] * L.ld[U] : nullptr;
+                gpitch[T][U] = L.ld[U];
+                gres_on[T][U] = Y.gres_off[T][U] >= 0 && used && cnt[T] > 0;
+            }
+            ST[T] = stp[T][0] + stp[T][1];
+            WT[T] = stp[T][0] * cst[T][0] + stp[T][1] * cst[T][1];
+            Wt[T] = cl_pow2ceil(max(L.s[T], 1));
+        }
+        const double KAPPA[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
+        GAMMA[0] = 0.0;
+        for (int k = 1; k <= 5; ++k) GAMMA[k] = GAMMA[k - 1] + 1.0 / k;
+        for (int k = 0; k <= 5; ++k) {
+            ALPHA[k] = (1.0 - KAPPA[k]) * GAMMA[k];
+            ERRC[k] = KAPPA[k] * GAMMA[k] + 1.0 / (k + 1);
+        }
+    }
+    __syncthreads();
+    const int n_own = ob[1] + L.s[1] * cnt[1];
+    const int NRG = nrg[0] + nrg[1];
+
+    double* zy = dyn + Y.zy;
+    double* zv = dyn + Y.zv;
+    double* dd = dyn + Y.dd;
+    double* psi = dyn + Y.psi;
+    double* scl = dyn + Y.scl;
+    double* fv = dyn + Y.fv;
+    double* tw = dyn + Y.tw;
+    double* kv = dyn + Y.kv;
+    double* Minv = dyn + Y.minv;
+    double* F = dyn + Y.F;
+    double* Pp = dyn + Y.Pp;
+    double* part = dyn + Y.part;
+    int* own_ez = (int*)(dyn + Y.info);         // index into the gathered (padded plane) vector
+    int* own_inf = own_ez + Y.PO;               // T << 30 | a << 24 | own row i
+    double* wk = A.work + ((int64_t)cid * G + rank) * A.work_stride;
+    double* V = A.v_smem ? dyn + Y.V : wk;                                   // [KRYLOV+1][PO]
+    double* D = A.d_smem ? dyn + Y.D : wk + (A.v_smem ? 0 : (int64_t)(STB_KRYLOV + 1) * Y.PO);
+    const int PO = Y.PO;
+
+    for (int i = tid; i < 2 * Y.NZ; i += STB_NT) zy[i] = 0.0;     // zy and zv are contiguous
+    for (int i = tid; i < Y.Pp - Y.F; i += STB_NT) F[i] = 0.0;    // fields of unused slots stay 0
+    for (int k = tid; k < n_own; k += STB_NT) {
+        const int T = k >= ob[1];
+        const int kk_ = k - ob[T];
+        const int a = kk_ / cnt[T], i = kk_ % cnt[T];
+        own_ez[k] = Y.zoff[T] + a * Y.ldz[T] + r_lo[T] + i;
+        own_inf[k] = (T << 30) | (a << 24) | i;
+    }
+
+    // ---- rate terms by state -----------------------------------------------------------------
+    if (tid == 0) {
+        for (int T = 0; T < 2; ++T) {
+            const TermTable& tt = L.terms[T];
+            int n = 0;
+            for (int a = 0; a <= L.s[T]; ++a) {
+                S.tl_ptr[T][a] = (short)n;
+                if (a == L.s[T]) break;
+                for (int t = 0; t < tt.n_terms; ++t) {
+                    if (tt.a[t] == a) S.tl_ent[T][n++] = (short)t;
+                    if (tt.b[t] == a) S.tl_ent[T][n++] = (short)(t | 0x4000);
+                }
+            }
+        }
+    }
+
+    // ---- work list of the pair pass: (row group, partner step), equal cost per warp ----------
+    if (tid <= STB_NW) {
+        const int64_t Ctot = (int64_t)nrg[0] * WT[0] + (int64_t)nrg[1] * WT[1];
+        int64_t x = Ctot * tid / STB_NW;
+        int g = 0, t = 0;
+        if (tid == STB_NW || Ctot == 0) {
+            g = NRG;
+        } else {
+            int T = 0;
+            if (WT[0] > 0 && x < (int64_t)nrg[0] * WT[0]) {
+                g = (int)(x / WT[0]);
+                x -= (int64_t)g * WT[0];
+            } else {
+                x -= (int64_t)nrg[0] * WT[0];
+                T = 1;
+                const int gi = WT[1] > 0 ? (int)(x / WT[1]) : 0;
+                x -= (int64_t)gi * WT[1];
+                g = nrg[0] + gi;
+            }
+            const int64_t c0 = (int64_t)stp[T][0] * cst[T][0];
+            t = x < c0 ? (int)(x / cst[T][0]) : stp[T][0] + (int)((x - c0) / cst[T][1]);
+        }
+        S.wb_g[tid] = g;
+        S.wb_t[tid] = t;
+    }
+    __syncthreads();
+    if (tid < NRG && tid < CL_MAXRG) {
+        const int g = tid;
+        int w0 = 0, w1 = 0;
+        const int Tg = g >= nrg[0];
+        for (int w = 0; w < STB_NW; ++w) {
+            const bool le0 = S.wb_g[w] < g || (S.wb_g[w] == g && S.wb_t[w] <= 0);
+            const bool ltS = S.wb_g[w] < g || (S.wb_g[w] == g && S.wb_t[w] < ST[Tg]);
+            if (le0) w0 = w;
+            if (ltS) w1 = w;
+        }
+        S.rg_w0[g] = (short)w0;
+        S.rg_w1[g] = (short)w1;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int g = 0; g < NRG; ++g)
+            if (S.rg_w0[g] != S.rg_w1[g]) S.part_rg[n++] = g;
+        S.n_part = n;
+    }
+    const int my_ga = S.wb_g[warp], my_ta = S.wb_t[warp];
+    const int my_gb = S.wb_g[warp + 1], my_tb = S.wb_t[warp + 1];
+
+    // ---- pair rows of the own ions -> shared memory, [pair][own row][2] -----------------------
+    {
+        double* gres = dyn + Y.gres;
+        for (int T = 0; T < 2; ++T)
+            for (int U = 0; U < 2; ++U) {
+                if (!gres_on[T][U]) continue;
+                double* dst = gres + Y.gres_off[T][U];
+                const int cp = Y.cntp[T], kcols = Y.nst[U] * 8;       // padded partner columns
+                const double* src = gsrc[T][U];
+                for (int idx = tid; idx < cp * kcols; idx += STB_NT) {
+                    const int i = idx / kcols, k = idx % kcols;
+                    double v = 0.0;
+                    if (i < cnt[T] && k < L.n[U]) v = src[(int64_t)i * L.ld[U] + k];
+                    dst[((int64_t)(k >> 1) * cp + i) * 2 + (k & 1)] = v;
+                }
+            }
+        __syncthreads();
+        if (tid == 0)
+            for (int T = 0; T < 2; ++T)
+                for (int U = 0; U < 2; ++U)
+                    if (gres_on[T][U]) {
+                        gsrc[T][U] = gres + Y.gres_off[T][U];
+                        gpitch[T][U] = Y.cntp[T];
+                    }
+    }
+    __syncthreads();
+
+    // every CTA of the cluster must be running before its shared memory is written remotely
+    if (G > 1) cl_barrier();
+    // remote bases of the exchange buffers
+    uint32_t rb_zy[CL_MAXG], rb_zv[CL_MAXG], rb_part[CL_MAXG];
+#pragma unroll
+    for (int r = 0; r < CL_MAXG; ++r) {
+        const uint32_t rr = r < G ? r : 0;
+        if (G > 1) {
+            rb_zy[r] = cl_mapa(cl_smem_u32(zy), rr);
+            rb_zv[r] = cl_mapa(cl_smem_u32(zv), rr);
+            rb_part[r] = cl_mapa(cl_smem_u32(part), rr);
+        } else {
+            rb_zy[r] = rb_zv[r] = rb_part[r] = 0;
+        }
+    }
+    int pbuf = 0;
+
+    auto sync_all = [&]() {
+        if (G > 1) cl_barrier();
+        else __syncthreads();
+    };
+    // own element -> every CTA of the cluster
+    auto push = [&](const uint32_t (&rb)[CL_MAXG], double* local, int ez, double v) {
+        if (G > 1) {
+#pragma unroll
+            for (int r = 0; r < CL_MAXG; ++r)
+                if (r < G) cl_st_f64(rb[r] + (uint32_t)ez * 8u, v);
+        } else {
+            local[ez] = v;
+        }
+    };
+    // thread i < K holds the CTA's partial `mine` of value i: on return S.rv[i] = cluster total,
+    // summed in rank order (deterministic, identical in every CTA).  Contains the barrier.
+    auto reduce_post = [&](int K, double mine) {
+        if (G == 1) {
+            if (tid < K) S.rv[tid] = mine;
+            __syncthreads();
+            return;
+        }
+        if (tid < K) {
+#pragma unroll
+            for (int r = 0; r < CL_MAXG; ++r)
+                if (r < G) cl_st_f64(rb_part[r] + (uint32_t)(((pbuf * CL_MAXG + rank) * STB_KRED + tid) * 8), mine);
+        }
+        cl_barrier();
+        if (tid < K) {
+            double acc = 0.0;
+            for (int r = 0; r < G; ++r) acc += part[(pbuf * CL_MAXG + r) * STB_KRED + tid];
+            S.rv[tid] = acc;
+        }
+        pbuf ^= 1;
+        __syncthreads();
+    };
+    // block partial sums of K per-thread values, then the cluster reduction
+    auto reduce_vals = [&](int K, const double* v) {
+        double x[3];
+        for (int k = 0; k < K; ++k) {
+            x[k] = v[k];
+            for (int o = 16; o > 0; o >>= 1) x[k] += __shfl_xor_sync(0xffffffffu, x[k], o);
+        }
+        if (lane == 0)
+            for (int k = 0; k < K; ++k) S.red[warp * 4 + k] = x[k];
+        __syncthreads();
+        double mine = 0.0;
+        if (tid < K)
+            for (int w = 0; w < STB_NW; ++w) mine += S.red[w * 4 + tid];
+        reduce_post(K, mine);
+    };
+
+    // ---- pair pass: F[slot][row] = mult * sum_k g(row, k) z[col_slot][k] for the own rows --------
+    const int rr = lane & 7, kk = lane >> 3;
+    auto fields_pass = [&](const double* z, double mult) {
+        int g = my_ga, t0 = my_ta;
+        while (g < NRG && (g < my_gb || (g == my_gb && t0 < my_tb))) {
+            const int T = g >= nrg[0];
+            const int gi = T ? g - nrg[0] : g;
+            const int tend = g == my_gb ? my_tb : ST[T];
+            const int i = min(gi * CL_RG + rr, cnt[T] - 1);
+            double a0[STB_MAXC], a1[STB_MAXC];
+#pragma unroll
+            for (int s = 0; s < STB_MAXC; ++s) { a0[s] = 0.0; a1[s] = 0.0; }
+            const int ns0 = L.blk[T][0].n_slots, ns1 = L.blk[T][1].n_slots;
+            {
+                const int s0 = t0, s1 = min(tend, stp[T][0]);
+                if (s0 < s1) {
+                    if (gres_on[T][0])
+                        cl_stream_ns<true>(ns0, gsrc[T][0], gpitch[T][0], i, z + Y.zoff[0], Y.ldz[0],
+                                           L.blk[T][0].slot_col, Y.nkp[0], kk, s0, s1, a0);
+                    else
+                        cl_stream_ns<false>(ns0, gsrc[T][0], gpitch[T][0], i, z + Y.zoff[0], Y.ldz[0],
+                                            L.blk[T][0].slot_col, Y.nkp[0], kk, s0, s1, a0);
+                }
+            }
+            {
+                const int s0 = max(t0, stp[T][0]) - stp[T][0], s1 = tend - stp[T][0];
+                if (s0 < s1) {
+                    if (gres_on[T][1])
+                        cl_stream_ns<true>(ns1, gsrc[T][1], gpitch[T][1], i, z + Y.zoff[1], Y.ldz[1],
+                                           L.blk[T][1].slot_col, Y.nkp[1], kk, s0, s1, a1);
+                    else
+                        cl_stream_ns<false>(ns1, gsrc[T][1], gpitch[T][1], i, z + Y.zoff[1], Y.ldz[1],
+                                            L.blk[T][1].slot_col, Y.nkp[1], kk, s0, s1, a1);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < STB_MAXC; ++s) {
+                if (s < ns0) {
+                    a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], 8);
+                    a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], 16);
+                }
+                if (s < ns1) {
+                    a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], 8);
+                    a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], 16);
+                }
+            }
+            const bool full = t0 == 0 && tend == ST[T];
+            double* dst;
+            int pitch;
+            if (full) {
+                dst = F + Y.foff[T] + gi * CL_RG + rr;
+                pitch = Y.cntp[T];
+            } else {
+                dst = Pp + ((warp * 2 + (g != my_ga ? 1 : 0)) * Y.nfm) * CL_RG + rr;
+                pitch = CL_RG;
+            }
+            if (kk == 0) {
+#pragma unroll
+                for (int s = 0; s < STB_MAXC; ++s) {
+                    if (s < ns0) dst[s * pitch] = a0[s] * mult;
+                    if (s < ns1) dst[(ns0 + s) * pitch] = a1[s] * mult;
+                }
+            }
+            ++g;
+            t0 = 0;
+        }
+        CLPROF(0)
+        __syncthreads();
+        CLPROF(1)
+        // row groups shared by several warps: sum the partial fields in warp order
+        const int np = S.n_part;
+        for (int idx = tid; idx < np * Y.nfm * CL_RG; idx += STB_NT) {
+            const int g2 = S.part_rg[idx / (Y.nfm * CL_RG)];
+            const int s = (idx / CL_RG) % Y.nfm, r = idx % CL_RG;
+            const int T = g2 >= nrg[0];
+            if (s >= L.nf[T]) continue;
+            double acc = 0.0;
+            for (int w = S.rg_w0[g2]; w <= S.rg_w1[g2]; ++w) {
+                // empty share of warp w in this row group?
+                const int ag = S.wb_g[w], at = S.wb_t[w], bg = S.wb_g[w + 1], bt = S.wb_t[w + 1];
+                const int lo = ag < g2 ? 0 : at;
+                const int hi = bg > g2 ? ST[T] : bt;
+                if (hi <= lo) continue;
+                acc += Pp[((w * 2 + (g2 != ag ? 1 : 0)) * Y.nfm + s) * CL_RG + r];
+            }
+            const int gi = T ? g2 - nrg[0] : g2;
+            F[Y.foff[T] + s * Y.cntp[T] + gi * CL_RG + r] = acc;
+        }
+        __syncthreads();
+        CLPROF(2)
+    };
+
+    // rate terms of element (T, a, i): sum_t C_t y_q[a_t] F[slot_t][i] ([b_t == a] - [a_t == a])
+    auto term_sum = [&](int T, int a, int i, const double* y /*gathered*/) -> double {
+        const TermTable& tt = L.terms[T];
+        const double* yq = y + Y.zoff[T] + r_lo[T] + i;
+        const double* Fq = F + Y.foff[T] + i;
+        double acc = 0.0;
+        for (int n = S.tl_ptr[T][a]; n < S.tl_ptr[T][a + 1]; ++n) {
+            const int e = S.tl_ent[T][n];
+            const int t = e & 0x3fff;
+            const double rate = P.C[tt.proc[t]] * yq[tt.a[t] * Y.ldz[T]] * Fq[tt.fslot[t] * Y.cntp[T]];
+            acc += (e & 0x4000) ? rate : -rate;
+        }
+        return acc;
+    };
+    auto lin_sum = [&](int T, int a, int i, const double* y) -> double {
+        const double* yq = y + Y.zoff[T] + r_lo[T] + i;
+        const double* lr = P.lin[T] + a * L.s[T];
+        double acc = 0.0;
+        for (int b = 0; b < L.s[T]; ++b) acc = fma(lr[b], yq[b * Y.ldz[T]], acc);
+        return acc;
+    };
+    // x_a = sum_b Minv[a][b] r_b for own element (T, a, i), r = own-compact vector
+    auto minv_apply = [&](int T, int a, int i, const double* r) -> double {
+        const int s = L.s[T];
+        const double* Mp = Minv + Y.moff[T] + (a * s) * Y.cntm[T] + i;
+        const double* rq = r + ob[T] + i;
+        double acc = 0.0;
+        for (int b = 0; b < s; ++b) acc = fma(Mp[b * Y.cntm[T]], rq[b * cnt[T]], acc);
+        return acc;
+    };
+
+    // f = rhs(z) for the own elements (odesolver.py:33-43, 65-71); fields stay in F
+    auto rhs_pass = [&](const double* z, double* fout) {
+        fields_pass(z, 1.0);
+        for (int k = tid; k < n_own; k += STB_NT) {
+            const int inf = own_inf[k];
+            const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+            fout[k] = lin_sum(T, a, i, z) + term_sum(T, a, i, z);
+        }
+    };
+
+    // block-Jacobi: Minv = (I - c (Lin_T + sum_t C_t F[slot_t] (e_b - e_a) e_a^T))^-1 per own ion,
+    // W = pow2 >= s lanes per ion, Gauss-Jordan without pivoting (column-diagonally-dominant
+    // M-matrix), rows in registers, pivot rows by shuffle (as coop_block_inverse).
+    const int inv0 = (cnt[0] * Wt[0] + 31) & ~31;          // thread span of type 0, warp aligned
+    const int inv_tot = inv0 + ((cnt[1] * Wt[1] + 31) & ~31);
+    auto block_inverses = [&](double c) {
+        for (int base = 0; base < inv_tot; base += STB_NT) {
+            const int m = base + tid;
+            if (m - lane >= inv_tot) break;                  // warp-uniform
+            const int T = m >= inv0;
+            const int W = Wt[T], s = L.s[T];
+            const int mm = T ? m - inv0 : m;
+            const int ion = mm / W, gl = mm & (W - 1);
+            const bool valid = ion < cnt[T] && s > 0;
+            const int i = valid ? ion : 0;
+            const double* lin = P.lin[T];
+            const TermTable& tt = L.terms[T];
+            const int row = gl < s ? gl : 0;
+            double a[STB_MAXS], ai[STB_MAXS];
+#pragma unroll
+            for (int k = 0; k < STB_MAXS; ++k) {
+                a[k] = (k < s && cnt[T] > 0) ? -c * lin[row * s + k] : 0.0;
+                ai[k] = k == gl ? 1.0 : 0.0;
+                if (k == gl) a[k] += 1.0;
+            }
+            if (cnt[T] > 0) {
+                for (int t = 0; t < tt.n_terms; ++t) {
+                    const double kq = c * P.C[tt.proc[t]] * F[Y.foff[T] + tt.fslot[t] * Y.cntp[T] + i];
+                    const int ta = tt.a[t], tb = tt.b[t];
+#pragma unroll
+                    for (int k = 0; k < STB_MAXS; ++k)
+                        if (k == ta) a[k] += (gl == ta ? kq : 0.0) - (gl == tb ? kq : 0.0);
+                }
+            }
+            for (int col = 0; col < s; ++col) {
+                double acol = 0.0;
+#pragma unroll
+                for (int k = 0; k < STB_MAXS; ++k) acol = k == col ? a[k] : acol;
+                const double piv = __shfl_sync(0xffffffffu, acol, col, W);
+                const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+                const bool mine = gl == col;
+                const double mlt = mine ? 0.0 : acol;
+#pragma unroll
+                for (int k = 0; k < STB_MAXS; ++k) {
+                    if (k < s) {
+                        const double pa = __shfl_sync(0xffffffffu, a[k], col, W) * inv;
+                        const double pi = __shfl_sync(0xffffffffu, ai[k], col, W) * inv;
+                        a[k] = mine ? pa : fma(-mlt, pa, a[k]);
+                        ai[k] = mine ? pi : fma(-mlt, pi, ai[k]);
+                    }
+                }
+            }
+            if (valid && gl < s) {
+                double* Mp = Minv + Y.moff[T] + (gl * s) * Y.cntm[T] + i;
+#pragma unroll
+                for (int b = 0; b < STB_MAXS; ++b)
+                    if (b < s) Mp[b * Y.cntm[T]] = ai[b];
+            }
+        }
+    };
+
+    auto apply_change_D = [&](int order) {
+        for (int k = tid; k < n_own; k += STB_NT) {
+            double dv[6], nd[6];
+            for (int j = 0; j <= order; ++j) dv[j] = D[j * PO + k];
+            for (int i = 0; i <= order; ++i) {
+                double acc = 0.0;
+                for (int j = 0; j <= order; ++j) acc = fma(C.RU[j * 6 + i], dv[j], acc);
+                nd[i] = acc;
+            }
+            for (int i = 0; i <= order; ++i) D[i * PO + k] = nd[i];
+        }
+    };
+
+    const double sqrtN = sqrt((double)N);
+    const double rtol = A.rtol, atol = A.atol;
+
+    // =================================== systems ============================================
+    while (true) {
+        // next system of the batch (dynamic: solves differ in their number of steps)
+        __syncthreads();
+        if (rank == 0 && tid == 0) {
+            const int nxt = atomicAdd(A.next_sys, 1);
+            if (G > 1) {
+                for (int r = 0; r < G; ++r) cl_st_u32(cl_mapa(cl_smem_u32(&S.cur_sys), r), (uint32_t)nxt);
+            } else {
+                S.cur_sys = nxt;
+            }
+        }
+        sync_all();
+        const int sysl = S.cur_sys;
+        if (sysl >= A.n_sys) break;
+        const int sys = A.first + sysl;
+        load_sys_params(L, A.blocks, A.strengths, sys, A.pulse, P);
+        const double* y0 = A.y0 + (int64_t)sysl * N;
+        double* y_out = A.y_out + (int64_t)sysl * A.n_t * N;
+        if (tid == 0) {
+            C.t = A.t[0];
+            C.t_end = A.t[A.n_t - 1];
+            C.order = 1;
+            C.n_equal = 0;
+            C.status = 0;
+            C.k_out = 1;
+            C.steps_since_out = 0;
+            C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
+            C.tol_lin = STB_EPS_LIN * C.newton_tol * sqrtN;
+            memset(&C.st, 0, sizeof(stb_stats));
+        }
+        // D0 = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
+        for (int k = tid; k < n_own; k += STB_NT) {
+            const int inf = own_inf[k];
+            const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+            const int e = L.off[T] + a * L.n[T] + r_lo[T] + i;
+            const double v = y0[e];
+            D[k] = v;
+            for (int j = 1; j < 8; ++j) D[j * PO + k] = 0.0;
+            y_out[L.ref_of_plane[e]] = v;
+            push(rb_zy, zy, own_ez[k], v);
+        }
+        sync_all();
+        rhs_pass(zy, fv);
+        // ---- initial step (Hairer-Wanner, as scipy select_initial_step) -----------------------
+        {
+            double v3[3] = {0.0, 0.0, 0.0};
+            for (int k = tid; k < n_own; k += STB_NT) {
+                const double y = zy[own_ez[k]];
+                const double sc = atol + rtol * fabs(y);
+                scl[k] = sc;
+                const double a = y / sc, b = fv[k] / sc;
+                v3[0] = fma(a, a, v3[0]);
+                v3[1] = fma(b, b, v3[1]);
+                if (!isfinite(fv[k])) v3[2] = 1.0;
+            }
+            reduce_vals(3, v3);
+            const double d0 = sqrt(S.rv[0] / N), d1 = sqrt(S.rv[1] / N);
+            const double bad = S.rv[2];
+            const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+            __syncthreads();
+            for (int k = tid; k < n_own; k += STB_NT)
+                push(rb_zv, zv, own_ez[k], zy[own_ez[k]] + h0 * fv[k]);
+            sync_all();
+            rhs_pass(zv, tw);
+            double v1[1] = {0.0};
+            for (int k = tid; k < n_own; k += STB_NT) {
+                const double a = (tw[k] - fv[k]) / scl[k];
+                v1[0] = fma(a, a, v1[0]);
+            }
+            reduce_vals(1, v1);
+            if (tid == 0) {
+                C.st.n_rhs += 2;
+                const double d2 = sqrt(S.rv[0] / N) / h0;
+                const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3)
+                                                               : sqrt(0.01 / fmax(d1, d2));
+                C.h = fmin(fmin(100.0 * h0, h1), C.t_end - C.t);
+                if (bad != 0.0 || !isfinite(C.h) || !(C.h > 0.0)) C.status = 3;
+            }
+            __syncthreads();
+            const double h = C.h;
+            for (int k = tid; k < n_own; k += STB_NT) D[PO + k] = fv[k] * h;
+        }
+        __syncthreads();
+
+        // =============================== time stepping =====================================
+        while (true) {
+            __syncthreads();
+            CLPROF(14)
+            if (C.status != 0 || C.k_out >= A.n_t) break;
+            if (tid == 0) {
+                C.flag = 0;
+                const double t_new = C.t + C.h;
+                if (t_new > C.t_end && (t_new - C.t_end) > 1e-14 * fabs(C.t_end)) {
+                    const double factor = (C.t_end - C.t) / C.h;
+                    cl_compute_RU(C.order, factor, C.RU, K.Rs, K.Us);
+                    C.h = C.t_end - C.t;
+                    C.n_equal = 0;
+                    C.flag = 1;
+                } else if (t_new > C.t_end) {
+                    C.h = C.t_end - C.t;
+                }
+                const double eps_t = 10.0 * fabs(nextafter(C.t, 1e300) - C.t);
+                if (C.h < eps_t) C.status = 2;
+                if (C.steps_since_out >= A.nsteps) C.status = 1;
+                C.c = C.h / ALPHA[C.order];
+            }
+            __syncthreads();
+            if (C.status != 0) break;
+            if (C.flag) apply_change_D(C.order);
+            const int order = C.order;
+            const double c = C.c;
+            // predictor, scale, psi; d = 0; the predicted state goes to every CTA of the cluster
+            for (int k = tid; k < n_own; k += STB_NT) {
+                double yp = 0.0, ps = 0.0;
+                for (int j = 0; j <= order; ++j) {
+                    const double dj = D[j * PO + k];
+                    yp += dj;
+                    if (j >= 1) ps = fma(GAMMA[j], dj, ps);
+                }
+                scl[k] = atol + rtol * fabs(yp);
+                psi[k] = ps / ALPHA[order];
+                dd[k] = 0.0;
+                push(rb_zy, zy, own_ez[k], yp);
+            }
+            if (tid == 0) { C.newton_it = 0; C.flag = 0; C.dy_norm_old = -1.0; }
+            // ---- Newton-Krylov ------------------------------------------------------------------
+            while (true) {       // flag: 0 iterate, 1 converged, 2 failed
+                CLPROF(15)
+                sync_all();      // y_k complete in every CTA
+                CLPROF(3)
+                rhs_pass(zy, fv);
+                __syncthreads();
+                CLPROF(4)
+                block_inverses(c);
+                __syncthreads();
+                CLPROF(5)
+                // tw = Minv (c f - psi - d) / scale; the unscaled vector goes to zv
+                {
+                    for (int k = tid; k < n_own; k += STB_NT) kv[k] = c * fv[k] - psi[k] - dd[k];
+                    __syncthreads();
+                    double v2[2] = {0.0, 0.0};
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        const int inf = own_inf[k];
+                        const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+                        const double xy = minv_apply(T, a, i, kv);
+                        const double x = xy / scl[k];
+                        tw[k] = x;
+                        push(rb_zv, zv, own_ez[k], xy);
+                        v2[0] = fma(x, x, v2[0]);
+                        if (!isfinite(fv[k])) v2[1] = 1.0;
+                    }
+                    CLPROF(6)
+                    reduce_vals(2, v2);
+                    CLPROF(7)
+                }
+                if (tid == 0) {
+                    C.st.n_rhs += 1;
+                    C.st.n_lin += 1;
+                    C.beta = sqrt(S.rv[0]);
+                    C.kk = 0;
+                    if (S.rv[1] != 0.0 || !isfinite(C.beta)) C.flag = 2;
+                    S.gg[0] = C.beta;
+                    C.inrm = C.beta > 0.0 ? 1.0 / C.beta : 0.0;
+                }
+                __syncthreads();
+                if (C.flag == 2) break;
+                // ---- GMRES: V_0 = tw / beta; zv holds the direction, scaled by `zmul` ----------
+                bool lin_done = !(C.beta > C.tol_lin);
+                int j = 0;
+                double zmul = C.inrm;
+                if (!lin_done)
+                    for (int k = tid; k < n_own; k += STB_NT) V[k] = tw[k] * zmul;
+                while (!lin_done) {
+                    // w = Minv (I - cJ) v / scale = V_j - c Minv k(v) / scale, k = inter-ion coupling
+                    CLPROF(15)
+                    fields_pass(zv, zmul);
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        const int inf = own_inf[k];
+                        const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+                        kv[k] = term_sum(T, a, i, zy);
+                    }
+                    __syncthreads();
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        const int inf = own_inf[k];
+                        const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+                        tw[k] = V[j * PO + k] - c * minv_apply(T, a, i, kv) / scl[k];
+                    }
+                    __syncthreads();
+                    CLPROF(8)
+                    // h_i = <w, V_i> (i <= j), ww = <w, w>: warp i takes dot i
+                    const int K = j + 2;
+                    for (int i = warp; i < K; i += STB_NW) {
+                        const double* Vi = i <= j ? V + i * PO : tw;
+                        double acc = 0.0;
+                        for (int k = lane; k < n_own; k += 32) acc = fma(tw[k], Vi[k], acc);
+                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        if (lane == 0) S.rv[i] = acc;
+                    }
+                    __syncthreads();
+                    CLPROF(9)
+                    reduce_post(K, tid < K ? S.rv[tid] : 0.0);
+                    CLPROF(10)
+                    const double ww = S.rv[j + 1];
+                    double hn2 = ww;
+                    for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
+                    if (tid <= j) S.H[tid * STB_KRYLOV + j] = S.rv[tid];
+                    // orthogonalise the own elements
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        double acc = tw[k];
+                        for (int i = 0; i <= j; ++i) acc = fma(-S.rv[i], V[i * PO + k], acc);
+                        tw[k] = acc;
+                    }
+                    if (!(hn2 > 0.01 * ww)) {
+                        // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
+                        __syncthreads();
+                        for (int i = warp; i < K; i += STB_NW) {
+                            const double* Vi = i <= j ? V + i * PO : tw;
+                            double acc = 0.0;
+                            for (int k = lane; k < n_own; k += 32) acc = fma(tw[k], Vi[k], acc);
+                            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                            if (lane == 0) S.rv[i] = acc;
+                        }
+                        __syncthreads();
+                        reduce_post(K, tid < K ? S.rv[tid] : 0.0);
+                        const double w2 = S.rv[j + 1];
+                        hn2 = w2;
+                        for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
+                        if (tid <= j) S.H[tid * STB_KRYLOV + j] += S.rv[tid];
+                        for (int k = tid; k < n_own; k += STB_NT) {
+                            double acc = tw[k];
+                            for (int i = 0; i <= j; ++i) acc = fma(-S.rv[i], V[i * PO + k], acc);
+                            tw[k] = acc;
+                        }
+                        if (!(hn2 > 0.01 * w2)) {
+                            double v1[1] = {0.0};
+                            for (int k = tid; k < n_own; k += STB_NT) v1[0] = fma(tw[k], tw[k], v1[0]);
+                            reduce_vals(1, v1);
+                            hn2 = S.rv[0];
+                        }
+                    }
+                    const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
+                    const double ihn = hn > 0.0 ? 1.0 / hn : 0.0;
+                    __syncthreads();     // H column complete, S.rv free
+                    if (tid == 0) {
+                        C.st.n_jv += 1;
+                        double* Hc = S.H + j;   // column j, stride STB_KRYLOV
+                        for (int i = 0; i < j; ++i) {
+                            const double a = Hc[i * STB_KRYLOV], b = Hc[(i + 1) * STB_KRYLOV];
+                            Hc[i * STB_KRYLOV] = S.cs[i] * a + S.sn[i] * b;
+                            Hc[(i + 1) * STB_KRYLOV] = -S.sn[i] * a + S.cs[i] * b;
+                        }
+                        const double a = Hc[j * STB_KRYLOV];
+                        const double dnm = hypot(a, hn);
+                        if (dnm == 0.0) { S.cs[j] = 1.0; S.sn[j] = 0.0; }
+                        else { S.cs[j] = a / dnm; S.sn[j] = hn / dnm; }
+                        Hc[j * STB_KRYLOV] = dnm;
+                        S.gg[j + 1] = -S.sn[j] * S.gg[j];
+                        S.gg[j] = S.cs[j] * S.gg[j];
+                        C.kk = j + 1;
+                        C.beta = fabs(S.gg[j + 1]);
+                        if (!(hn > 0.0) || !isfinite(hn)) C.beta = 0.0;
+                    }
+                    // V_{j+1} = w / ||w||; its unscaled form is the next direction
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        const double v = tw[k] * ihn;
+                        V[(j + 1) * PO + k] = v;
+                        push(rb_zv, zv, own_ez[k], v * scl[k]);
+                    }
+                    zmul = 1.0;
+                    CLPROF(11)
+                    sync_all();
+                    CLPROF(12)
+                    ++j;
+                    lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
+                }
+                // ---- x = V y; dy = x * scale; ||x|| = ||y|| (orthonormal basis) --------------------
+                const int nk = C.kk;
+                if (tid == 0) {
+                    double y2 = 0.0;
+                    for (int i = nk - 1; i >= 0; --i) {
+                        double acc = S.gg[i];
+                        for (int k = i + 1; k < nk; ++k) acc -= S.H[i * STB_KRYLOV + k] * S.yk_s[k];
+                        const double hd = S.H[i * STB_KRYLOV + i];
+                        S.yk_s[i] = hd != 0.0 ? acc / hd : 0.0;
+                        y2 = fma(S.yk_s[i], S.yk_s[i], y2);
+                    }
+                    const double dy_norm = sqrt(y2 / N);
+                    const int it = C.newton_it;
+                    const double rate = C.dy_norm_old > 0.0 ? dy_norm / C.dy_norm_old : -1.0;
+                    int flag = 0;
+                    if (!isfinite(dy_norm)) flag = 2;
+                    else if (rate >= 0.0 &&
+                             (rate >= 1.0 ||
+                              pow(rate, (double)(STB_NEWTON_MAXIT - it)) / (1.0 - rate) * dy_norm >
+                                  C.newton_tol))
+                        flag = 2;
+                    C.dy_norm = dy_norm;
+                    if (flag == 0) {
+                        if (dy_norm == 0.0 ||
+                            (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < C.newton_tol) ||
+                            (rate < 0.0 && dy_norm < 0.1 * C.newton_tol))
+                            flag = 1;
+                    }
+                    C.dy_norm_old = dy_norm;
+                    C.newton_it = it + 1;
+                    C.n_iter = it + 1;
+                    if (flag == 0 && C.newton_it >= STB_NEWTON_MAXIT) flag = 2;
+                    C.flag = flag;     // 2: do not apply the update
+                }
+                __syncthreads();
+                const int flag = C.flag;
+                // a failed iteration (diverging, or out of iterations) is discarded with the step
+                if (flag != 2) {
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        double x = 0.0;
+                        for (int i = 0; i < nk; ++i) x = fma(S.yk_s[i], V[i * PO + k], x);
+                        const double dy = x * scl[k];
+                        const double yn = zy[own_ez[k]] + dy;
+                        dd[k] += dy;
+                        if (flag == 0) push(rb_zy, zy, own_ez[k], yn);   // next iteration needs it
+                        else zy[own_ez[k]] = yn;
+                    }
+                }
+                if (flag != 0) break;
+            }
+            __syncthreads();
+            if (C.flag == 2) {
+                // Newton / Krylov failure: halve the step (scipy: factor 0.5 with current Jacobian)
+                if (tid == 0) {
+                    C.st.n_newton_fail += 1;
+                    cl_compute_RU(C.order, 0.5, C.RU, K.Rs, K.Us);
+                    C.h *= 0.5;
+                    C.n_equal = 0;
+                    C.steps_since_out += 1;
+                }
+                __syncthreads();
+                apply_change_D(order);
+                continue;
+            }
+            CLPROF(13)
+            // ---- error test and order selection share one reduction -------------------------------
+            {
+                double v3[3] = {0.0, 0.0, 0.0};
+                for (int k = tid; k < n_own; k += STB_NT) {
+                    const double sc = atol + rtol * fabs(zy[own_ez[k]]);
+                    scl[k] = sc;
+                    const double dv = dd[k];
+                    const double er = ERRC[order] * dv / sc;
+                    v3[0] = fma(er, er, v3[0]);
+                    if (order > 1) {
+                        const double em = ERRC[order - 1] * (D[order * PO + k] + dv) / sc;
+                        v3[1] = fma(em, em, v3[1]);
+                    }
+                    if (order < STB_MAXORD) {
+                        const double ep = ERRC[order + 1] * (dv - D[(order + 1) * PO + k]) / sc;
+                        v3[2] = fma(ep, ep, v3[2]);
+                    }
+                }
+                reduce_vals(3, v3);
+                if (tid == 0) {
+                    C.err_norm = sqrt(S.rv[0] / N);
+                    C.safety = 0.9 * (2 * STB_NEWTON_MAXIT + 1) / (2.0 * STB_NEWTON_MAXIT + C.n_iter);
+                    C.flag = 0;
+                    if (C.err_norm > 1.0 || !isfinite(C.err_norm)) {
+                        const double factor = isfinite(C.err_norm)
+                            ? fmax(STB_MIN_FACTOR, C.safety * pow(C.err_norm, -1.0 / (order + 1)))
+                            : STB_MIN_FACTOR;
+                        cl_compute_RU(order, factor, C.RU, K.Rs, K.Us);
+                        C.h *= factor;
+                        C.n_equal = 0;
+                        C.st.n_rejected += 1;
+                        C.steps_since_out += 1;
+                        C.flag = 1;
+                    }
+                }
+                __syncthreads();
+                if (C.flag == 1) {
+                    apply_change_D(order);
+                    continue;
+                }
+            }
+            const double err_m2 = S.rv[1], err_p2 = S.rv[2];
+            // ---- accepted: update differences, dense output, order / step selection -------------
+            const double h = C.h, t_new = C.t + C.h;
+            for (int k = tid; k < n_own; k += STB_NT) {
+                const double dv = dd[k];
+                const double dp1 = D[(order + 1) * PO + k];
+                D[(order + 2) * PO + k] = dv - dp1;
+                D[(order + 1) * PO + k] = dv;
+                double run = dv;
+                for (int i = order; i >= 0; --i) {
+                    run += D[i * PO + k];
+                    D[i * PO + k] = run;
+                }
+            }
+            while (true) {     // dense output for every requested time in (t, t_new]
+                __syncthreads();
+                if (tid == 0) {
+                    C.flag = 0;
+                    if (C.k_out < A.n_t) {
+                        const double tq = A.t[C.k_out];
+                        if (tq <= t_new * (1.0 + 1e-15) || tq <= t_new) {
+                            C.flag = tq >= t_new ? 2 : 1;
+                            double pr = 1.0;
+                            for (int jj = 0; jj < order; ++jj) {
+                                pr *= (tq - (t_new - h * jj)) / (h * (1 + jj));
+                                C.p[jj + 1] = pr;
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (C.flag == 0) break;
+                double* row = y_out + C.k_out * (int64_t)N;
+                const bool exact = C.flag == 2;
+                for (int k = tid; k < n_own; k += STB_NT) {
+                    const int inf = own_inf[k];
+                    const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+                    double acc = D[k];
+                    if (!exact)
+                        for (int jj = 1; jj <= order; ++jj) acc = fma(C.p[jj], D[jj * PO + k], acc);
+                    row[L.ref_of_plane[L.off[T] + a * L.n[T] + r_lo[T] + i]] = acc;
+                }
+                __syncthreads();
+                if (tid == 0) { C.k_out += 1; C.st.n_out = C.k_out; C.steps_since_out = 0; }
+            }
+            if (tid == 0) {
+                const bool need_order = (C.n_equal + 1) >= order + 1;
+                C.st.n_steps += 1;
+                C.steps_since_out += 1;
+                C.n_equal += 1;
+                C.t = t_new;
+                C.flag = 0;
+                if (need_order) {
+                    const double err_m = order > 1 ? sqrt(err_m2 / N) : INFINITY;
+                    const double err_p = order < STB_MAXORD ? sqrt(err_p2 / N) : INFINITY;
+                    double fm = err_m > 0.0 ? pow(err_m, -1.0 / order) : INFINITY;
+                    const double f0 = C.err_norm > 0.0 ? pow(C.err_norm, -1.0 / (order + 1)) : INFINITY;
+                    double fp = err_p > 0.0 ? pow(err_p, -1.0 / (order + 2)) : INFINITY;
+                    if (order == 1) fm = 0.0;
+                    if (order == STB_MAXORD) fp = 0.0;
+                    if (isinf(err_m)) fm = 0.0;
+                    if (isinf(err_p)) fp = 0.0;
+                    int delta;
+                    double best;
+                    // numpy argmax picks the first maximum: order-1 wins ties, then same order
+                    if (fm >= f0 && fm >= fp) { best = fm; delta = -1; }
+                    else if (f0 >= fp) { best = f0; delta = 0; }
+                    else { best = fp; delta = 1; }
+                    C.order = order + delta;
+                    const double factor = fmin(STB_MAX_FACTOR, C.safety * best);
+                    cl_compute_RU(C.order, factor, C.RU, K.Rs, K.Us);
+                    C.h *= factor;
+                    C.n_equal = 0;
+                    C.flag = 1;
+                }
+                C.st.last_order = C.order;
+                C.st.last_h = C.h;
+            }
+            __syncthreads();
+            if (C.flag == 1) apply_change_D(C.order);
+        }
+        __syncthreads();
+        CLPROF(14)
+        if (tid == 0 && rank == 0 && cid == 0 && A.prof)
+            for (int k = 0; k < 16; ++k) A.prof[k] = S.prof[k];
+        if (tid == 0 && rank == 0) {
+            C.st.status = C.status;
+            C.st.t_reached = C.t;
+            C.st.n_out = C.k_out;
+            A.stats[sysl] = C.st;
+        }
+    }
+}
