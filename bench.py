@@ -255,6 +255,8 @@ def run_gpu(args):
         step_device()
     barrier()
     sampler = ClockSampler(local)
+    if os.environ.get('BENCH_NO_SAMPLER'):          # diagnosis only: does NVML polling cost time?
+        sampler.nv = None
     sampler.start()
     launches0 = system.lib.stb_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

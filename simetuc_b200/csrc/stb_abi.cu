@@ -75,7 +75,34 @@ struct stb_system {
     int last_G = 0, last_groups = 0;
     int64_t last_launches = 0;
     int sm_count = 148;
+    // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
+    // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
+    enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR, WS_COUNT };
+    void* ws_ptr[WS_COUNT] = {};
+    size_t ws_cap[WS_COUNT] = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
+
+// grow-only workspace slot of the handle
+static cudaError_t ws_get(stb_system* S, int slot, size_t bytes, void** out) {
+    bytes = std::max<size_t>(bytes, 16);
+    if (bytes > S->ws_cap[slot]) {
+        if (S->ws_ptr[slot]) cudaFree(S->ws_ptr[slot]);
+        S->ws_ptr[slot] = nullptr;
+        S->ws_cap[slot] = 0;
+        cudaError_t e = cudaMalloc(&S->ws_ptr[slot], bytes);
+        if (e != cudaSuccess) return e;
+        S->ws_cap[slot] = bytes;
+    }
+    *out = S->ws_ptr[slot];
+    return cudaSuccess;
+}
+static cudaError_t ws_events(stb_system* S) {
+    if (S->ev0) return cudaSuccess;
+    cudaError_t e = cudaEventCreate(&S->ev0);
+    if (e != cudaSuccess) return e;
+    return cudaEventCreate(&S->ev1);
+}
 
 extern "C" const char* stb_last_error(void) { return g_err.c_str(); }
 
@@ -145,6 +172,9 @@ extern "C" void stb_system_destroy(stb_system* S) {
     cudaFree(S->d_out);
     cudaFree(S->d_F);
     cudaFree(S->d_tmp);
+    for (int k = 0; k < stb_system::WS_COUNT; ++k) cudaFree(S->ws_ptr[k]);
+    if (S->ev0) cudaEventDestroy(S->ev0);
+    if (S->ev1) cudaEventDestroy(S->ev1);
     if (S->stream) cudaStreamDestroy(S->stream);
     delete S;
 }
@@ -908,10 +938,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     long long* d_prof = nullptr;
     stb_stats* d_stats = nullptr;
     const size_t out_bytes = sizeof(double) * (size_t)n * n_t * N;
-    auto cleanup = [&]() {
-        cudaFree(d_work); cudaFree(d_y0); cudaFree(d_yout); cudaFree(d_t); cudaFree(d_tmp);
-        cudaFree(d_avg); cudaFree(d_next); cudaFree(d_stats); cudaFree(d_prof);
-    };
+    auto cleanup = [&]() {};   // every buffer is a workspace slot of the handle
 #define CKC(call)                                                                     \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -921,17 +948,19 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
             return e_ == cudaErrorMemoryAllocation ? STB_ENOMEM : STB_ECUDA;          \
         }                                                                             \
     } while (0)
-    CKC(cudaMalloc((void**)&d_work, sizeof(double) * (size_t)plan.n_clusters * plan.G * work_stride));
+#define WSC(slot, ptr, bytes) CKC(ws_get(S, stb_system::slot, (bytes), (void**)&(ptr)))
+    WSC(WS_WORK, d_work, sizeof(double) * (size_t)plan.n_clusters * plan.G * work_stride);
     const bool own_yout = !(dev && y_out);
     if (!dev) {
-        CKC(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
-        CKC(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
-        CKC(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+        WSC(WS_Y0, d_y0, sizeof(double) * (size_t)n * N);
+        WSC(WS_TMP, d_tmp, sizeof(double) * (size_t)n * N);
+        WSC(WS_T, d_t, sizeof(double) * n_t);
     }
-    if (own_yout) CKC(cudaMalloc((void**)&d_yout, out_bytes));
-    CKC(cudaMalloc((void**)&d_next, sizeof(int)));
-    CKC(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
-    CKC(cudaMalloc((void**)&d_prof, sizeof(long long) * 16));
+    if (own_yout) WSC(WS_YOUT, d_yout, out_bytes);
+    WSC(WS_NEXT, d_next, sizeof(int));
+    WSC(WS_STATS, d_stats, sizeof(stb_stats) * n);
+    WSC(WS_PROF, d_prof, sizeof(long long) * 16);
+    CKC(ws_events(S));
     CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16, S->stream));
     CKC(cudaMemsetAsync(d_next, 0, sizeof(int), S->stream));
     CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
@@ -963,9 +992,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         fprintf(stderr, "[stb] cluster integrator: n=%d G=%d clusters=%d resmask=%x (%.0f%% of pair rows "
                 "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d\n", n, plan.G, plan.n_clusters,
                 plan.resmask, 100.0 * plan.resident_frac, plan.v_smem, plan.d_smem, plan.dyn_bytes, Y.PO);
-    cudaEvent_t e0, e1;
-    CKC(cudaEventCreate(&e0));
-    CKC(cudaEventCreate(&e1));
+    cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKC(cudaEventRecord(e0, S->stream));
     {
         cudaLaunchConfig_t cfg;
@@ -990,7 +1017,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     if (avg_out) {
         double* avg_p = avg_out;
         if (!dev) {
-            CKC(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
+            WSC(WS_AVG, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]));
             avg_p = d_avg;
         }
         g_launches++;
@@ -1019,9 +1046,6 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         for (int k = 0; k < 16; ++k) fprintf(stderr, " %s=%.0f(%.0f%%)", names[k], pr[k] / 1e3, 100.0 * pr[k] / std::max(tot, 1.0));
         fprintf(stderr, "\n");
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cleanup();
     return STB_OK;
 }
 
@@ -1106,10 +1130,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     stb_stats* d_stats = nullptr;
     long long* d_prof = nullptr;
     size_t out_bytes = sizeof(double) * (size_t)n * n_t * N;
-    auto cleanup = [&]() {
-        cudaFree(d_work); cudaFree(d_y0); cudaFree(d_yout); cudaFree(d_t); cudaFree(d_part);
-        cudaFree(d_tmp); cudaFree(d_avg); cudaFree(d_bar); cudaFree(d_stats); cudaFree(d_prof);
-    };
+    auto cleanup = [&]() {};   // every buffer is a workspace slot of the handle
 #define CKI(call)                                                                     \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -1119,18 +1140,20 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
             return e_ == cudaErrorMemoryAllocation ? STB_ENOMEM : STB_ECUDA;          \
         }                                                                             \
     } while (0)
-    CKI(cudaMalloc((void**)&d_work, sizeof(double) * (size_t)n_groups * work_stride));
+#define WSI(slot, ptr, bytes) CKI(ws_get(S, stb_system::slot, (bytes), (void**)&(ptr)))
+    WSI(WS_WORK, d_work, sizeof(double) * (size_t)n_groups * work_stride);
     const bool own_yout = !(dev && y_out);
     if (!dev) {
-        CKI(cudaMalloc((void**)&d_y0, sizeof(double) * (size_t)n * N));
-        CKI(cudaMalloc((void**)&d_tmp, sizeof(double) * (size_t)n * N));
-        CKI(cudaMalloc((void**)&d_t, sizeof(double) * n_t));
+        WSI(WS_Y0, d_y0, sizeof(double) * (size_t)n * N);
+        WSI(WS_TMP, d_tmp, sizeof(double) * (size_t)n * N);
+        WSI(WS_T, d_t, sizeof(double) * n_t);
     }
-    if (own_yout) CKI(cudaMalloc((void**)&d_yout, out_bytes));
-    CKI(cudaMalloc((void**)&d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED));
-    CKI(cudaMalloc((void**)&d_bar, sizeof(unsigned long long) * n_groups));
-    CKI(cudaMalloc((void**)&d_stats, sizeof(stb_stats) * n));
-    CKI(cudaMalloc((void**)&d_prof, sizeof(long long) * 8 * n));
+    if (own_yout) WSI(WS_YOUT, d_yout, out_bytes);
+    WSI(WS_PART, d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED);
+    WSI(WS_BAR, d_bar, sizeof(unsigned long long) * n_groups);
+    WSI(WS_STATS, d_stats, sizeof(stb_stats) * n);
+    WSI(WS_PROF, d_prof, sizeof(long long) * 8 * n);
+    CKI(ws_events(S));
     CKI(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * n, S->stream));
     CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * n_groups, S->stream));
     CKI(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
@@ -1157,9 +1180,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
     S->last_G = G; S->last_groups = n_groups;
-    cudaEvent_t e0, e1;
-    CKI(cudaEventCreate(&e0));
-    CKI(cudaEventCreate(&e1));
+    cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKI(cudaEventRecord(e0, S->stream));
     void* kargs[] = {&A};
     g_launches++;
@@ -1169,7 +1190,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     if (avg_out) {
         double* avg_p = avg_out;
         if (!dev) {
-            CKI(cudaMalloc((void**)&d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1])));
+            WSI(WS_AVG, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]));
             avg_p = d_avg;
         }
         g_launches++;
@@ -1186,9 +1207,6 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     if (stats) CKI(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
     CKI(cudaStreamSynchronize(S->stream));
     CKI(cudaEventElapsedTime(&S->last_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cleanup();
     return STB_OK;
 }
 
