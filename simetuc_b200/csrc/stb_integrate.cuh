@@ -15,7 +15,15 @@
 #define STB_NEWTON_MAXIT 4
 #define STB_MIN_FACTOR 0.2
 #define STB_MAX_FACTOR 10.0
-#define STB_EPS_LIN 0.05
+// Linear (GMRES) tolerance: preconditioned residual, RMS over the states in units of the error
+// test (1 = the local error bound).  The Newton update of a step is accepted with this residual,
+// so it plays the role of LSODA's corrector tolerance (conit ~ 0.07 of the error bound).
+#define STB_LIN_RMS 2e-3
+// The Newton convergence rate is carried across steps (LSODA / CVODE `crate`): a step whose first
+// update already satisfies 1.5 * min(1, crate) * ||dy|| < newton_tol is accepted without a second
+// residual evaluation; every STB_VERIFY_EVERY such steps a second iteration is forced, which
+// re-measures the rate from the true nonlinear residual.
+#define STB_VERIFY_EVERY 16
 
 struct IntArgs {
     const DevLattice* L;
@@ -47,14 +55,47 @@ __host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
 
 struct Ctl {
     double t, h, t_end, c, newton_tol, tol_lin;
-    double beta, inrm, dy_norm, dy_norm_old, err_norm, safety;
+    double beta, inrm, dy_norm, dy_norm_old, err_norm, safety, crate;
     double RU[(STB_MAXORD + 1) * (STB_MAXORD + 1)];
     double p[STB_MAXORD + 1];
-    int order, n_equal, status, kk, flag, newton_it, n_iter;
+    int order, n_equal, status, kk, flag, newton_it, n_iter, since_verify;
     int64_t k_out, steps_since_out;
     stb_stats st;
     long long prof[8];
 };
+
+// Newton control after an update of scaled RMS norm dy_norm (thread 0).  Returns 0: iterate,
+// 1: converged, 2: failed (diverging).  The tests are scipy BDF's (solve_bdf_system) plus the
+// carried-rate acceptance described at STB_VERIFY_EVERY.
+__device__ __forceinline__ int newton_decide(Ctl& C, double dy_norm) {
+    const int it = C.newton_it;
+    const double rate = C.dy_norm_old > 0.0 ? dy_norm / C.dy_norm_old : -1.0;
+    if (rate >= 0.0 && isfinite(rate)) {
+        C.crate = fmax(0.2 * C.crate, rate);
+        C.since_verify = 0;
+    }
+    int flag = 0;
+    if (!isfinite(dy_norm)) flag = 2;
+    else if (rate >= 0.0 &&
+             (rate >= 1.0 ||
+              pow(rate, (double)(STB_NEWTON_MAXIT - it)) / (1.0 - rate) * dy_norm > C.newton_tol))
+        flag = 2;
+    C.dy_norm = dy_norm;
+    if (flag == 0) {
+        if (dy_norm == 0.0 || (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < C.newton_tol) ||
+            (rate < 0.0 && dy_norm < 0.1 * C.newton_tol)) {
+            flag = 1;
+        } else if (rate < 0.0 && C.since_verify < STB_VERIFY_EVERY &&
+                   1.5 * fmin(1.0, C.crate) * dy_norm < C.newton_tol) {
+            flag = 1;
+            C.since_verify += 1;
+        }
+    }
+    C.dy_norm_old = dy_norm;
+    C.newton_it = it + 1;
+    C.n_iter = it + 1;
+    return flag;
+}
 
 struct GroupCtx {
     unsigned long long* counter;
@@ -486,7 +527,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.k_out = 1;
             C.steps_since_out = 0;
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
-            C.tol_lin = STB_EPS_LIN * C.newton_tol * sqrtN;
+            C.tol_lin = STB_LIN_RMS * sqrtN;
+            C.crate = 1.0;
+            C.since_verify = 0;
             memset(&C.st, 0, sizeof(stb_stats));
             for (int k = 0; k < 8; ++k) C.prof[k] = 0;
             tick = clock64();
@@ -720,27 +763,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 block_sum<1>(v1, red, rv);
                 group_reduce(g, rv, 1);
                 if (threadIdx.x == 0) {
-                    double dy_norm = sqrt(rv[0] / N);
-                    const int it = C.newton_it;
-                    double rate = C.dy_norm_old > 0.0 ? dy_norm / C.dy_norm_old : -1.0;
-                    int flag = 0;
-                    if (!isfinite(dy_norm)) flag = 2;
-                    else if (rate >= 0.0 &&
-                             (rate >= 1.0 ||
-                              pow(rate, (double)(STB_NEWTON_MAXIT - it)) / (1.0 - rate) * dy_norm >
-                                  C.newton_tol))
-                        flag = 2;
-                    C.dy_norm = dy_norm;
-                    if (flag == 0) {
-                        if (dy_norm == 0.0 ||
-                            (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < C.newton_tol) ||
-                            (rate < 0.0 && dy_norm < 0.1 * C.newton_tol))
-                            flag = 1;
-                    }
-                    C.flag = flag;     // 2: do not apply the update
-                    C.dy_norm_old = dy_norm;
-                    C.newton_it = it + 1;
-                    C.n_iter = it + 1;
+                    C.flag = newton_decide(C, sqrt(rv[0] / N));     // 2: do not apply the update
                 }
                 __syncthreads();
                 const int flag = C.flag;

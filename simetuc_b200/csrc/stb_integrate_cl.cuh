@@ -771,7 +771,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             C.k_out = 1;
             C.steps_since_out = 0;
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
-            C.tol_lin = STB_EPS_LIN * C.newton_tol * sqrtN;
+            C.tol_lin = STB_LIN_RMS * sqrtN;
+            C.crate = 1.0;
+            C.since_verify = 0;
             memset(&C.st, 0, sizeof(stb_stats));
         }
         // D0 = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
@@ -1030,26 +1032,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                         S.yk_s[i] = hd != 0.0 ? acc / hd : 0.0;
                         y2 = fma(S.yk_s[i], S.yk_s[i], y2);
                     }
-                    const double dy_norm = sqrt(y2 / N);
-                    const int it = C.newton_it;
-                    const double rate = C.dy_norm_old > 0.0 ? dy_norm / C.dy_norm_old : -1.0;
-                    int flag = 0;
-                    if (!isfinite(dy_norm)) flag = 2;
-                    else if (rate >= 0.0 &&
-                             (rate >= 1.0 ||
-                              pow(rate, (double)(STB_NEWTON_MAXIT - it)) / (1.0 - rate) * dy_norm >
-                                  C.newton_tol))
-                        flag = 2;
-                    C.dy_norm = dy_norm;
-                    if (flag == 0) {
-                        if (dy_norm == 0.0 ||
-                            (rate >= 0.0 && rate / (1.0 - rate) * dy_norm < C.newton_tol) ||
-                            (rate < 0.0 && dy_norm < 0.1 * C.newton_tol))
-                            flag = 1;
-                    }
-                    C.dy_norm_old = dy_norm;
-                    C.newton_it = it + 1;
-                    C.n_iter = it + 1;
+                    int flag = newton_decide(C, sqrt(y2 / N));
                     if (flag == 0 && C.newton_it >= STB_NEWTON_MAXIT) flag = 2;
                     C.flag = flag;     // 2: do not apply the update
                 }

@@ -89,7 +89,8 @@ def gmres(A, b, Minv, tol, maxit, stats):
 
 
 def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=None,
-          max_steps=200000, krylov_max=30, eps_lin=0.05, verbose=False):
+          max_steps=200000, krylov_max=30, eps_lin=0.05, verbose=False, carry_rate=False,
+          verify_every=0):
     """Integrate y' = fun(y) and return y at t_arr (dense output by BDF interpolation).
     jv_factory(y) -> (v -> J(y) v); precond_factory(y, c) -> (r -> M^-1 r), M ~ I - c J."""
     st = Stats()
@@ -122,6 +123,10 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
     n_equal = 0
     newton_tol = max(10 * np.finfo(float).eps / rtol, min(0.03, rtol ** 0.5))
     k_out = 1
+    crate = 1.0              # Newton convergence rate carried across steps (LSODA / CVODE practice)
+    since_verify = 0
+    st.krylov_by_it = [[] for _ in range(NEWTON_MAXITER)]
+    st.rates = []
     while k_out < len(t_arr) and st.nsteps < max_steps:
         # ---- one accepted step
         step_accepted = False
@@ -159,9 +164,14 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
                 x, kk, ok = gmres(A, res, Minv, tol_lin, krylov_max, st)
                 st.nlin += 1
                 st.krylov_hist.append(kk)
+                st.krylov_by_it[it].append(kk)
                 dy = x * scale
                 dy_norm = rms(x)
                 rate = None if dy_norm_old is None else dy_norm / dy_norm_old
+                if rate is not None:
+                    crate = max(0.2 * crate, rate)
+                    st.rates.append(rate)
+                    since_verify = 0
                 if rate is not None and (rate >= 1 or
                                          rate ** (NEWTON_MAXITER - it) / (1 - rate) * dy_norm > newton_tol):
                     break
@@ -170,6 +180,11 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
                 if dy_norm == 0 or (rate is not None and rate / (1 - rate) * dy_norm < newton_tol) \
                         or (rate is None and dy_norm < 0.1 * newton_tol):
                     converged = True
+                    break
+                if carry_rate and rate is None and (verify_every == 0 or since_verify < verify_every) \
+                        and 1.5 * min(1.0, crate) * dy_norm < newton_tol:
+                    converged = True
+                    since_verify += 1
                     break
                 dy_norm_old = dy_norm
             if not converged:

@@ -86,23 +86,29 @@ def compare(y, yref, label):
         label, err.max(), (np.abs(y - yref) / np.abs(yref))[np.abs(yref) > 1e-9].max()))
 
 
-def run(op, cte, t_pulse_w, rtol=1e-8, atol=1e-15, n_steps=1000, do_ref=True, krylov_max=30):
+def run(op, cte, t_pulse_w, rtol=1e-8, atol=1e-15, n_steps=1000, do_ref=True, krylov_max=30, ref=None, **kw_solve):
     tf = onp.t_simulation(cte['decay'])
     t_pulse, t_sol = onp.time_grids(t_pulse_w, tf, n_steps)
     y0 = op['initial_population'].astype(float)
     res = {}
     t0 = time.time()
     fun, jvf, pf = make_problem(op, True)
-    yp, st1 = proto_bdf.solve(fun, jvf, pf, t_pulse, y0, rtol, atol, krylov_max=krylov_max)
+    yp, st1 = proto_bdf.solve(fun, jvf, pf, t_pulse, y0, rtol, atol, krylov_max=krylov_max, **kw_solve)
     fun, jvf, pf = make_problem(op, False)
-    ys, st2 = proto_bdf.solve(fun, jvf, pf, t_sol, yp[-1], rtol, atol, krylov_max=krylov_max)
+    ys, st2 = proto_bdf.solve(fun, jvf, pf, t_sol, yp[-1], rtol, atol, krylov_max=krylov_max, **kw_solve)
     print('proto: %.1fs' % (time.time() - t0))
     for name, st in (('pulse', st1), ('relax', st2)):
         kh = np.array(st.krylov_hist)
         print(' %s: steps %d rej %d newton_fail %d nfev %d njv %d lin solves %d  krylov/solve mean %.1f max %d' % (
             name, st.nsteps, st.nrej, st.nnewt_fail, st.nfev, st.njv, st.nlin,
             kh.mean() if len(kh) else 0, kh.max() if len(kh) else 0))
-    if do_ref:
+        print('   krylov by newton it:', [(len(k), round(float(np.mean(k)), 2)) for k in st.krylov_by_it if k],
+              ' rates: n %d max %.2g median %.2g' % (len(st.rates), max(st.rates, default=0), np.median(st.rates) if st.rates else 0))
+    if ref is not None:
+        compare(yp[-1], ref[0], 'pulse end')
+        compare(ys, ref[1], 'relax')
+        res['ref'] = ref
+    elif do_ref:
         t0 = time.time()
         kw = dict(rtol=rtol, atol=atol, nsteps=100000)
         yp_ref = onp.solve_pulse(t_pulse, y0, op['abs'], op['decay'], op['ET'], op['N_indices'],
@@ -112,7 +118,7 @@ def run(op, cte, t_pulse_w, rtol=1e-8, atol=1e-15, n_steps=1000, do_ref=True, kr
         print('lsoda: %.1fs' % (time.time() - t0))
         compare(yp[-1], yp_ref[-1], 'pulse end')
         compare(ys, ys_ref, 'relax')
-        res['ref'] = ys_ref
+        res['ref'] = (yp_ref[-1], ys_ref)
     res['y'] = ys
     return res
 
