@@ -894,11 +894,19 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
             if ((size_t)Z.total * 8 <= cap) { mask |= 1 << pick; res += pick_sz; }
         }
         {
+            // then the first 8 Krylov basis vectors (touched in every iteration), then the BDF
+            // difference array (touched once per step), then the rest of the basis
             ClLayout Z;
-            cl_layout(L, G, mask, 1, 0, Z);
-            if ((size_t)Z.total * 8 <= cap) v_smem = 1;
+            for (int c = 8; c >= 1 && !v_smem; --c) {
+                cl_layout(L, G, mask, c, 0, Z);
+                if ((size_t)Z.total * 8 <= cap) v_smem = c;
+            }
             cl_layout(L, G, mask, v_smem, 1, Z);
             if ((size_t)Z.total * 8 <= cap) d_smem = 1;
+            for (int c = STB_KRYLOV + 1; c > v_smem; --c) {
+                cl_layout(L, G, mask, c, d_smem, Z);
+                if ((size_t)Z.total * 8 <= cap) { v_smem = c; break; }
+            }
         }
         cl_layout(L, G, mask, v_smem, d_smem, Y);
         const size_t bytes = (size_t)Y.total * sizeof(double);

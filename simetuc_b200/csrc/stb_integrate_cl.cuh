@@ -35,6 +35,7 @@ struct ClLayout {          // offsets in doubles into dynamic shared memory
     int zy, zv, dd, psi, scl, fv, tw, kv, minv, F, Pp, part, info, V, D, gres;
     int gres_off[2][2];    // resident pair rows of block [T][U], relative to gres (-1: streamed)
     int nfm;               // field slots per row, max over the types
+    int nsm;               // field slots of one block, max over the blocks
     int foff[2], moff[2];
     int64_t total;         // doubles
 };
@@ -44,10 +45,11 @@ __host__ __device__ inline int cl_pow2ceil(int v) { int p = 1; while (p < v) p <
 // doubles of the shared-memory copy of a CTA's rows of block [T][U] (0: block unused)
 __host__ __device__ inline int cl_block_doubles(const DevLattice& L, const ClLayout& Y, int T, int U) {
     if (L.blk[T][U].n_slots <= 0 || L.n[T] <= 0 || L.n[U] <= 0) return 0;
-    return Y.nst[U] * 4 * Y.cntp[T] * 2;
+    return Y.nst[U] * 4 * Y.cntm[T] * 2;        // rows of the fullest rank, no row-group padding
 }
 
-// Layout shared by the host (sizing, feasibility) and the kernel.  v_smem / d_smem / resident say
+// Layout shared by the host (sizing, feasibility) and the kernel.  v_smem (number of leading
+// Krylov basis vectors) / d_smem / resident say
 // whether the Krylov basis, the difference array and the pair rows live in shared memory.
 __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmask, int v_smem,
                                           int d_smem, ClLayout& Y) {
@@ -81,10 +83,14 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.foff[0] = 0;
     Y.foff[1] = L.nf[0] * Y.cntp[0];
     Y.F = take(Y.foff[1] + L.nf[1] * Y.cntp[1]);
-    Y.Pp = take(STB_NW * 2 * Y.nfm * CL_RG);
-    Y.part = take(2 * CL_MAXG * STB_KRED);
+    Y.nsm = 1;
+    for (int T = 0; T < 2; ++T)
+        for (int U = 0; U < 2; ++U)
+            if (L.blk[T][U].n_slots > Y.nsm) Y.nsm = L.blk[T][U].n_slots;
+    Y.Pp = take(STB_NW * 2 * Y.nsm * CL_RG);
+    Y.part = take(2 * G * STB_KRED);
     Y.info = take(Y.PO);                       // two int tables of PO entries
-    Y.V = v_smem ? take((STB_KRYLOV + 1) * Y.PO) : -1;
+    Y.V = v_smem > 0 ? take(v_smem * Y.PO) : -1;       // the first v_smem basis vectors
     Y.D = d_smem ? take(8 * Y.PO) : -1;
     Y.gres = o;
     int r = 0;
@@ -148,83 +154,120 @@ __device__ __forceinline__ double2 cl_ld_nc2(const double* p) {
     return v;
 }
 
-// Fields of 8 rows x (partner pairs kk, kk+4, ...) over warp steps [s0, s1) of one block.
-//   RES: pair rows resident in shared memory, layout [pair][own row][2];
+// One piece of the pair pass: fields of 8 rows x (partner pairs kk, kk+4, ...) over the warp
+// steps [s0, s1) of one block, reduced over the 4 partner lanes of a row and stored (scaled by
+// mult) at dst[slot * dpitch] by the lane kk == 0.  NS (field slots of the block) is a
+// compile-time constant: no predicated slots anywhere in the piece.
+//   RES: pair rows resident in shared memory, layout [pair][own row][2], addressed as offsets
+//        into the dynamic shared array (the compiler then emits LDS.128, not generic loads);
 //   else: global dense block, row-major, pitch ld (even), read through the non-allocating path.
 template <int NS, bool RES>
-__device__ __forceinline__ void cl_stream(const double* gb, int64_t pitch, int row, const double* zU,
-                                          int ldz, const int* slot_col, int nkp, int kk, int s0,
-                                          int s1, double (&acc)[STB_MAXC]) {
-    const double* zs[NS];
+__device__ __forceinline__ void cl_piece(const double* dynb, int g_off, const double* gb,
+                                         int64_t pitch, int row, int z_off, int ldz,
+                                         const int* slot_col, int nkp, int kk, int s0, int s1,
+                                         double mult, double* dst, int dpitch) {
+    double acc[NS];
+    int zo[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) zs[s] = zU + slot_col[s] * ldz;
-    const int kmax = nkp - 1;
-    int st = s0;
-    for (; st + 4 <= s1; st += 4) {
-        double2 g[4];
-        int kz[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int kp = (st + u) * 4 + kk;
-            if (RES) {
-                g[u] = *reinterpret_cast<const double2*>(gb + ((int64_t)kp * pitch + row) * 2);
-                kz[u] = 2 * kp;
-            } else {
-                const int kc = min(kp, kmax);
-                g[u] = cl_ld_nc2(gb + (int64_t)row * pitch + 2 * kp);
-                kz[u] = 2 * kc;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+    for (int s = 0; s < NS; ++s) {
+        acc[s] = 0.0;
+        zo[s] = z_off + slot_col[s] * ldz;
+    }
+    if (RES) {
+        const int cp = (int)pitch;
+        int go = g_off + (kk * cp + row) * 2 + s0 * 8 * cp;      // [pair = st * 4 + kk][row][2]
+        const int gstep = 8 * cp;
+        int zk = 8 * s0 + 2 * kk;
+#pragma unroll 4
+        for (int st = s0; st < s1; ++st) {
+            const double2 g = *reinterpret_cast<const double2*>(dynb + go);
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const double2 z = *reinterpret_cast<const double2*>(zs[s] + kz[u]);
-                acc[s] = fma(g[u].x, z.x, acc[s]);
-                acc[s] = fma(g[u].y, z.y, acc[s]);
+                const double2 z = *reinterpret_cast<const double2*>(dynb + zo[s] + zk);
+                acc[s] = fma(g.x, z.x, acc[s]);
+                acc[s] = fma(g.y, z.y, acc[s]);
+            }
+            go += gstep;
+            zk += 8;
+        }
+    } else {
+        const int kmax = nkp - 1;
+        const double* gr = gb + (int64_t)row * pitch;
+#pragma unroll 4
+        for (int st = s0; st < s1; ++st) {
+            const int kp = st * 4 + kk;
+            const double2 g = cl_ld_nc2(gr + 2 * kp);
+            const int zk = 2 * min(kp, kmax);
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const double2 z = *reinterpret_cast<const double2*>(dynb + zo[s] + zk);
+                acc[s] = fma(g.x, z.x, acc[s]);
+                acc[s] = fma(g.y, z.y, acc[s]);
             }
         }
     }
-    for (; st < s1; ++st) {
-        const int kp = st * 4 + kk;
-        double2 g;
-        int kz;
-        if (RES) {
-            g = *reinterpret_cast<const double2*>(gb + ((int64_t)kp * pitch + row) * 2);
-            kz = 2 * kp;
-        } else {
-            g = cl_ld_nc2(gb + (int64_t)row * pitch + 2 * kp);
-            kz = 2 * min(kp, kmax);
-        }
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const double2 z = *reinterpret_cast<const double2*>(zs[s] + kz);
-            acc[s] = fma(g.x, z.x, acc[s]);
-            acc[s] = fma(g.y, z.y, acc[s]);
-        }
+    for (int s = 0; s < NS; ++s) {
+        acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 8);
+        acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 16);
+    }
+    if (kk == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) dst[s * dpitch] = acc[s] * mult;
     }
 }
 
 template <bool RES>
-__device__ __forceinline__ void cl_stream_ns(int ns, const double* gb, int64_t pitch, int row,
-                                             const double* zU, int ldz, const int* slot_col, int nkp,
-                                             int kk, int s0, int s1, double (&acc)[STB_MAXC]) {
+__device__ __forceinline__ void cl_piece_ns(int ns, const double* dynb, int g_off, const double* gb,
+                                            int64_t pitch, int row, int z_off, int ldz,
+                                            const int* slot_col, int nkp, int kk, int s0, int s1,
+                                            double mult, double* dst, int dpitch) {
+#define CL_PIECE(NS_) cl_piece<NS_, RES>(dynb, g_off, gb, pitch, row, z_off, ldz, slot_col, nkp, kk, s0, s1, mult, dst, dpitch)
     switch (ns) {
-        case 1: cl_stream<1, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
-        case 2: cl_stream<2, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
-        case 3: cl_stream<3, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
-        case 4: cl_stream<4, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
-        case 5: cl_stream<5, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
-        default: cl_stream<6, RES>(gb, pitch, row, zU, ldz, slot_col, nkp, kk, s0, s1, acc); break;
+        case 1: CL_PIECE(1); break;
+        case 2: CL_PIECE(2); break;
+        case 3: CL_PIECE(3); break;
+        case 4: CL_PIECE(4); break;
+        case 5: CL_PIECE(5); break;
+        default: CL_PIECE(6); break;
+    }
+#undef CL_PIECE
+}
+
+#define CL_MAXCOMB ((STB_NW - 1) * STB_MAXC * CL_RG)   // a warp boundary splits at most one segment
+
+// In-place Gauss-Jordan inverse of an s x s block (s <= SM) held one row per lane, W lanes per
+// block; no pivoting (I - c J_qq is a column-diagonally-dominant M-matrix).  Entries k >= s of a
+// row must be 0.  Pivot-row elements travel by shuffle; nothing is indexed dynamically.
+template <int SM>
+__device__ __forceinline__ void cl_gj_inplace(double (&a)[STB_MAXS], int s, int W, int gl) {
+#pragma unroll
+    for (int col = 0; col < SM; ++col) {
+        if (col < s) {
+            const double piv = __shfl_sync(0xffffffffu, a[col], col, W);
+            const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+            const bool mine = gl == col;
+            const double f = a[col];
+#pragma unroll
+            for (int k = 0; k < SM; ++k) {
+                if (k != col) {
+                    const double pr = __shfl_sync(0xffffffffu, a[k], col, W) * inv;
+                    a[k] = mine ? pr : fma(-f, pr, a[k]);
+                }
+            }
+            a[col] = mine ? inv : -f * inv;
+        }
     }
 }
 
 struct ClConst {           // per-CTA constants that are indexed dynamically: shared, not local memory
     int r_lo[2], cnt[2], ob[2], nrg[2];
     int stp[2][2], cst[2][2], ST[2], WT[2], Wt[2];
-    const double* gsrc[2][2];
+    const double* gsrc[2][2];  // streamed blocks: global rows of the CTA
     long long gpitch[2][2];
     int gres_on[2][2];
+    int goff[2][2];            // resident blocks: offset into the dynamic shared array
+    int rgpos[2];              // work-list position (steps) of the first row group of a type
     double GAMMA[6], ALPHA[6], ERRC[6];
     double Rs[36], Us[36];
 };
@@ -249,12 +292,15 @@ struct ClShared {
     Ctl C;
     ClLayout Y;
     double H[(STB_KRYLOV + 1) * STB_KRYLOV];
-    double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
+    double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV], rd[STB_KRYLOV];
     double red[STB_NW * 4];
     double rv[STB_KRED];
     int wb_g[STB_NW + 1], wb_t[STB_NW + 1];      // work-list boundaries of the warps
-    int part_rg[STB_NW + 2], n_part;             // row groups shared by several warps
-    short rg_w0[CL_MAXRG], rg_w1[CL_MAXRG];
+    int wpos[STB_NW + 1];                        // the same as linear step positions
+    // pieces of segments shared by several warps are summed in warp order:
+    // entry = dst (16) | w0 (4) | w1 (4) | slot of w0 (1) | field slot (3) | row (3)
+    unsigned comb[CL_MAXCOMB];
+    int n_comb;
     short tl_ptr[2][STB_MAXS + 1];               // rate terms touching state a of type T
     short tl_ent[2][2 * STB_MAXT];               // term index | sign bit (0x4000: +, i.e. b == a)
     int cur_sys;
@@ -358,12 +404,17 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     int* own_ez = (int*)(dyn + Y.info);         // index into the gathered (padded plane) vector
     int* own_inf = own_ez + Y.PO;               // T << 30 | a << 24 | own row i
     double* wk = A.work + ((int64_t)cid * G + rank) * A.work_stride;
-    double* V = A.v_smem ? dyn + Y.V : wk;                                   // [KRYLOV+1][PO]
-    double* D = A.d_smem ? dyn + Y.D : wk + (A.v_smem ? 0 : (int64_t)(STB_KRYLOV + 1) * Y.PO);
     const int PO = Y.PO;
+    // Krylov basis [KRYLOV+1][PO]: the first nvs vectors in shared memory (a linear solve rarely
+    // needs more), the rest spilled to the work area; difference array D [8][PO]
+    const int nvs = A.v_smem;
+    auto Vrow = [&](int i) -> double* {
+        return i < nvs ? dyn + Y.V + i * PO : wk + (int64_t)(i - nvs) * PO;
+    };
+    double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(STB_KRYLOV + 1) * PO;
 
     for (int i = tid; i < 2 * Y.NZ; i += STB_NT) zy[i] = 0.0;     // zy and zv are contiguous
-    for (int i = tid; i < Y.Pp - Y.F; i += STB_NT) F[i] = 0.0;    // fields of unused slots stay 0
+    for (int i = tid; i < Y.part - Y.F; i += STB_NT) F[i] = 0.0;  // unused field slots and pieces of idle warps stay 0
     for (int k = tid; k < n_own; k += STB_NT) {
         const int T = k >= ob[1];
         const int kk_ = k - ob[T];
@@ -414,26 +465,47 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         S.wb_t[tid] = t;
     }
     __syncthreads();
-    if (tid < NRG && tid < CL_MAXRG) {
-        const int g = tid;
-        int w0 = 0, w1 = 0;
-        const int Tg = g >= nrg[0];
-        for (int w = 0; w < STB_NW; ++w) {
-            const bool le0 = S.wb_g[w] < g || (S.wb_g[w] == g && S.wb_t[w] <= 0);
-            const bool ltS = S.wb_g[w] < g || (S.wb_g[w] == g && S.wb_t[w] < ST[Tg]);
-            if (le0) w0 = w;
-            if (ltS) w1 = w;
-        }
-        S.rg_w0[g] = (short)w0;
-        S.rg_w1[g] = (short)w1;
+    // linear step positions of the warp boundaries; segments (row group, block) cut by a boundary
+    // get one combine entry per (field slot, row)
+    if (tid == 0) {
+        K.rgpos[0] = 0;
+        K.rgpos[1] = nrg[0] * ST[0];
+        S.n_comb = 0;
     }
     __syncthreads();
-    if (tid == 0) {
-        int n = 0;
-        for (int g = 0; g < NRG; ++g)
-            if (S.rg_w0[g] != S.rg_w1[g]) S.part_rg[n++] = g;
-        S.n_part = n;
+    if (tid <= STB_NW) {
+        const int g = S.wb_g[tid];
+        const int T = g >= nrg[0];
+        S.wpos[tid] = g >= NRG ? nrg[0] * ST[0] + nrg[1] * ST[1]
+                               : K.rgpos[T] + (g - (T ? nrg[0] : 0)) * ST[T] + S.wb_t[tid];
     }
+    __syncthreads();
+    for (int sg = tid; sg < 2 * NRG; sg += STB_NT) {
+        const int g = sg >> 1, U = sg & 1;
+        const int T = g >= nrg[0];
+        const int gi = T ? g - nrg[0] : g;
+        const int a0 = K.rgpos[T] + gi * ST[T] + (U ? stp[T][0] : 0), b0 = a0 + stp[T][U];
+        if (b0 <= a0) continue;
+        int w0 = -1, w1 = -1;
+        for (int w = 0; w < STB_NW; ++w)
+            if (max(S.wpos[w], a0) < min(S.wpos[w + 1], b0)) {
+                if (w0 < 0) w0 = w;
+                w1 = w;
+            }
+        if (w0 < 0 || w1 == w0) continue;              // one warp: written to F directly
+        // slot of w0's piece: 0 if this segment holds the first step of w0's range
+        const int sl0 = S.wpos[w0] >= a0 ? 0 : 1;
+        const int ns = L.blk[T][U].n_slots;
+        const int base = atomicAdd(&S.n_comb, ns * CL_RG);
+        const int sb = U ? L.blk[T][0].n_slots : 0;     // first field slot of the block in F
+        for (int q = 0; q < ns * CL_RG; ++q) {
+            const int sl = q / CL_RG, r = q % CL_RG;
+            const unsigned dst = (unsigned)(Y.foff[T] + (sb + sl) * Y.cntp[T] + gi * CL_RG + r);
+            if (base + q < CL_MAXCOMB)
+                S.comb[base + q] = dst | (w0 << 16) | (w1 << 20) | (sl0 << 24) | (sl << 25) | (r << 28);
+        }
+    }
+    __syncthreads();
     const int my_ga = S.wb_g[warp], my_ta = S.wb_t[warp];
     const int my_gb = S.wb_g[warp + 1], my_tb = S.wb_t[warp + 1];
 
@@ -444,7 +516,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             for (int U = 0; U < 2; ++U) {
                 if (!gres_on[T][U]) continue;
                 double* dst = gres + Y.gres_off[T][U];
-                const int cp = Y.cntp[T], kcols = Y.nst[U] * 8;       // padded partner columns
+                const int cp = Y.cntm[T], kcols = Y.nst[U] * 8;       // padded partner columns
                 const double* src = gsrc[T][U];
                 for (int idx = tid; idx < cp * kcols; idx += STB_NT) {
                     const int i = idx / kcols, k = idx % kcols;
@@ -458,8 +530,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             for (int T = 0; T < 2; ++T)
                 for (int U = 0; U < 2; ++U)
                     if (gres_on[T][U]) {
-                        gsrc[T][U] = gres + Y.gres_off[T][U];
-                        gpitch[T][U] = Y.cntp[T];
+                        K.goff[T][U] = Y.gres + Y.gres_off[T][U];
+                        gpitch[T][U] = Y.cntm[T];
                     }
     }
     __syncthreads();
@@ -506,12 +578,12 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         if (tid < K) {
 #pragma unroll
             for (int r = 0; r < CL_MAXG; ++r)
-                if (r < G) cl_st_f64(rb_part[r] + (uint32_t)(((pbuf * CL_MAXG + rank) * STB_KRED + tid) * 8), mine);
+                if (r < G) cl_st_f64(rb_part[r] + (uint32_t)(((pbuf * G + rank) * STB_KRED + tid) * 8), mine);
         }
         cl_barrier();
         if (tid < K) {
             double acc = 0.0;
-            for (int r = 0; r < G; ++r) acc += part[(pbuf * CL_MAXG + r) * STB_KRED + tid];
+            for (int r = 0; r < G; ++r) acc += part[(pbuf * G + r) * STB_KRED + tid];
             S.rv[tid] = acc;
         }
         pbuf ^= 1;
@@ -535,66 +607,36 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
 
     // ---- pair pass: F[slot][row] = mult * sum_k g(row, k) z[col_slot][k] for the own rows --------
     const int rr = lane & 7, kk = lane >> 3;
-    auto fields_pass = [&](const double* z, double mult) {
-        int g = my_ga, t0 = my_ta;
+    // zb: offset of the gathered vector (Y.zy or Y.zv) in the dynamic shared array
+    auto fields_pass = [&](int zb, double mult) {
+        int g = my_ga, t0 = my_ta, piece = 0;
         while (g < NRG && (g < my_gb || (g == my_gb && t0 < my_tb))) {
             const int T = g >= nrg[0];
             const int gi = T ? g - nrg[0] : g;
             const int tend = g == my_gb ? my_tb : ST[T];
             const int i = min(gi * CL_RG + rr, cnt[T] - 1);
-            double a0[STB_MAXC], a1[STB_MAXC];
 #pragma unroll
-            for (int s = 0; s < STB_MAXC; ++s) { a0[s] = 0.0; a1[s] = 0.0; }
-            const int ns0 = L.blk[T][0].n_slots, ns1 = L.blk[T][1].n_slots;
-            {
-                const int s0 = t0, s1 = min(tend, stp[T][0]);
-                if (s0 < s1) {
-                    if (gres_on[T][0])
-                        cl_stream_ns<true>(ns0, gsrc[T][0], gpitch[T][0], i, z + Y.zoff[0], Y.ldz[0],
-                                           L.blk[T][0].slot_col, Y.nkp[0], kk, s0, s1, a0);
-                    else
-                        cl_stream_ns<false>(ns0, gsrc[T][0], gpitch[T][0], i, z + Y.zoff[0], Y.ldz[0],
-                                            L.blk[T][0].slot_col, Y.nkp[0], kk, s0, s1, a0);
+            for (int U = 0; U < 2; ++U) {
+                const int lo = U ? stp[T][0] : 0;
+                const int s0 = max(t0, lo) - lo, s1 = min(tend, lo + stp[T][U]) - lo;
+                if (s0 >= s1) continue;
+                const int ns = L.blk[T][U].n_slots;
+                double* dst;
+                int dpitch;
+                if (s0 == 0 && s1 == stp[T][U]) {
+                    dst = F + Y.foff[T] + (U ? L.blk[T][0].n_slots : 0) * Y.cntp[T] + gi * CL_RG + rr;
+                    dpitch = Y.cntp[T];
+                } else {
+                    dst = Pp + ((warp * 2 + (piece ? 1 : 0)) * Y.nsm) * CL_RG + rr;
+                    dpitch = CL_RG;
                 }
-            }
-            {
-                const int s0 = max(t0, stp[T][0]) - stp[T][0], s1 = tend - stp[T][0];
-                if (s0 < s1) {
-                    if (gres_on[T][1])
-                        cl_stream_ns<true>(ns1, gsrc[T][1], gpitch[T][1], i, z + Y.zoff[1], Y.ldz[1],
-                                           L.blk[T][1].slot_col, Y.nkp[1], kk, s0, s1, a1);
-                    else
-                        cl_stream_ns<false>(ns1, gsrc[T][1], gpitch[T][1], i, z + Y.zoff[1], Y.ldz[1],
-                                            L.blk[T][1].slot_col, Y.nkp[1], kk, s0, s1, a1);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < STB_MAXC; ++s) {
-                if (s < ns0) {
-                    a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], 8);
-                    a0[s] += __shfl_xor_sync(0xffffffffu, a0[s], 16);
-                }
-                if (s < ns1) {
-                    a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], 8);
-                    a1[s] += __shfl_xor_sync(0xffffffffu, a1[s], 16);
-                }
-            }
-            const bool full = t0 == 0 && tend == ST[T];
-            double* dst;
-            int pitch;
-            if (full) {
-                dst = F + Y.foff[T] + gi * CL_RG + rr;
-                pitch = Y.cntp[T];
-            } else {
-                dst = Pp + ((warp * 2 + (g != my_ga ? 1 : 0)) * Y.nfm) * CL_RG + rr;
-                pitch = CL_RG;
-            }
-            if (kk == 0) {
-#pragma unroll
-                for (int s = 0; s < STB_MAXC; ++s) {
-                    if (s < ns0) dst[s * pitch] = a0[s] * mult;
-                    if (s < ns1) dst[(ns0 + s) * pitch] = a1[s] * mult;
-                }
+                if (gres_on[T][U])
+                    cl_piece_ns<true>(ns, dyn, K.goff[T][U], nullptr, gpitch[T][U], i, zb + Y.zoff[U],
+                                      Y.ldz[U], L.blk[T][U].slot_col, Y.nkp[U], kk, s0, s1, mult, dst, dpitch);
+                else
+                    cl_piece_ns<false>(ns, dyn, 0, gsrc[T][U], gpitch[T][U], i, zb + Y.zoff[U],
+                                       Y.ldz[U], L.blk[T][U].slot_col, Y.nkp[U], kk, s0, s1, mult, dst, dpitch);
+                ++piece;
             }
             ++g;
             t0 = 0;
@@ -602,26 +644,19 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         CLPROF(0)
         __syncthreads();
         CLPROF(1)
-        // row groups shared by several warps: sum the partial fields in warp order
-        const int np = S.n_part;
-        for (int idx = tid; idx < np * Y.nfm * CL_RG; idx += STB_NT) {
-            const int g2 = S.part_rg[idx / (Y.nfm * CL_RG)];
-            const int s = (idx / CL_RG) % Y.nfm, r = idx % CL_RG;
-            const int T = g2 >= nrg[0];
-            if (s >= L.nf[T]) continue;
-            double acc = 0.0;
-            for (int w = S.rg_w0[g2]; w <= S.rg_w1[g2]; ++w) {
-                // empty share of warp w in this row group?
-                const int ag = S.wb_g[w], at = S.wb_t[w], bg = S.wb_g[w + 1], bt = S.wb_t[w + 1];
-                const int lo = ag < g2 ? 0 : at;
-                const int hi = bg > g2 ? ST[T] : bt;
-                if (hi <= lo) continue;
-                acc += Pp[((w * 2 + (g2 != ag ? 1 : 0)) * Y.nfm + s) * CL_RG + r];
+        // segments shared by several warps: sum the pieces in warp order
+        const int nc = S.n_comb;
+        if (nc > 0) {
+            for (int idx = tid; idx < nc; idx += STB_NT) {
+                const unsigned e = S.comb[idx];
+                const int w0 = (e >> 16) & 15, w1 = (e >> 20) & 15, sl0 = (e >> 24) & 1;
+                const int q = (int)((e >> 25) & 7) * CL_RG + (int)(e >> 28);
+                double acc = Pp[((w0 * 2 + sl0) * Y.nsm) * CL_RG + q];
+                for (int w = w0 + 1; w <= w1; ++w) acc += Pp[(w * 2 * Y.nsm) * CL_RG + q];
+                F[e & 0xffffu] = acc;
             }
-            const int gi = T ? g2 - nrg[0] : g2;
-            F[Y.foff[T] + s * Y.cntp[T] + gi * CL_RG + r] = acc;
+            __syncthreads();
         }
-        __syncthreads();
         CLPROF(2)
     };
 
@@ -657,8 +692,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     };
 
     // f = rhs(z) for the own elements (odesolver.py:33-43, 65-71); fields stay in F
-    auto rhs_pass = [&](const double* z, double* fout) {
-        fields_pass(z, 1.0);
+    auto rhs_pass = [&](const double* z, int zb, double* fout) {
+        fields_pass(zb, 1.0);
         for (int k = tid; k < n_own; k += STB_NT) {
             const int inf = own_inf[k];
             const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
@@ -666,63 +701,68 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         }
     };
 
-    // block-Jacobi: Minv = (I - c (Lin_T + sum_t C_t F[slot_t] (e_b - e_a) e_a^T))^-1 per own ion,
-    // W = pow2 >= s lanes per ion, Gauss-Jordan without pivoting (column-diagonally-dominant
-    // M-matrix), rows in registers, pivot rows by shuffle (as coop_block_inverse).
-    const int inv0 = (cnt[0] * Wt[0] + 31) & ~31;          // thread span of type 0, warp aligned
-    const int inv_tot = inv0 + ((cnt[1] * Wt[1] + 31) & ~31);
+    // block-Jacobi: Minv = (I - c (Lin_T + sum_t C_t F[slot_t] (e_b - e_a) e_a^T))^-1 per own ion.
+    // 1. every thread builds its own row of M in place (thread per state, as the epilogues);
+    // 2. the blocks are inverted in place: closed form for 2-state ions (thread per ion), else
+    //    Gauss-Jordan with W = pow2 >= s lanes per ion, one row per lane.
+    int inv_span[2];
+    inv_span[0] = L.s[0] == 2 ? ((cnt[0] + 31) & ~31) : ((cnt[0] * Wt[0] + 31) & ~31);
+    inv_span[1] = L.s[1] == 2 ? ((cnt[1] + 31) & ~31) : ((cnt[1] * Wt[1] + 31) & ~31);
+    const int inv0 = inv_span[0], inv_tot = inv_span[0] + inv_span[1];
     auto block_inverses = [&](double c) {
+        for (int k = tid; k < n_own; k += STB_NT) {
+            const int inf = own_inf[k];
+            const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+            const int s = L.s[T], cm = Y.cntm[T];
+            double* Mp = Minv + Y.moff[T] + (a * s) * cm + i;
+            const double* lr = P.lin[T] + a * s;
+            for (int b = 0; b < s; ++b) Mp[b * cm] = (b == a ? 1.0 : 0.0) - c * lr[b];
+            const TermTable& tt = L.terms[T];
+            const double* Fq = F + Y.foff[T] + i;
+            for (int n = S.tl_ptr[T][a]; n < S.tl_ptr[T][a + 1]; ++n) {
+                const int e = S.tl_ent[T][n];
+                const int t = e & 0x3fff;
+                const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
+                Mp[tt.a[t] * cm] += (e & 0x4000) ? -kq : kq;     // row b_t: -, row a_t: +
+            }
+        }
+        __syncthreads();
         for (int base = 0; base < inv_tot; base += STB_NT) {
             const int m = base + tid;
             if (m - lane >= inv_tot) break;                  // warp-uniform
             const int T = m >= inv0;
-            const int W = Wt[T], s = L.s[T];
+            const int s = L.s[T], cm = Y.cntm[T];
             const int mm = T ? m - inv0 : m;
+            if (s == 2) {
+                if (mm < cnt[T]) {
+                    double* Mp = Minv + Y.moff[T] + mm;
+                    const double m00 = Mp[0], m01 = Mp[cm], m10 = Mp[2 * cm], m11 = Mp[3 * cm];
+                    const double det = m00 * m11 - m01 * m10;
+                    const double id = det != 0.0 ? 1.0 / det : 0.0;
+                    Mp[0] = m11 * id;
+                    Mp[cm] = -m01 * id;
+                    Mp[2 * cm] = -m10 * id;
+                    Mp[3 * cm] = m00 * id;
+                }
+                continue;
+            }
+            const int W = Wt[T];
             const int ion = mm / W, gl = mm & (W - 1);
-            const bool valid = ion < cnt[T] && s > 0;
-            const int i = valid ? ion : 0;
-            const double* lin = P.lin[T];
-            const TermTable& tt = L.terms[T];
-            const int row = gl < s ? gl : 0;
-            double a[STB_MAXS], ai[STB_MAXS];
+            const bool valid = ion < cnt[T] && gl < s;
+            double a[STB_MAXS];
+            {
+                const double* Mp = Minv + Y.moff[T] + (gl * s) * cm + ion;
 #pragma unroll
-            for (int k = 0; k < STB_MAXS; ++k) {
-                a[k] = (k < s && cnt[T] > 0) ? -c * lin[row * s + k] : 0.0;
-                ai[k] = k == gl ? 1.0 : 0.0;
-                if (k == gl) a[k] += 1.0;
+                for (int k = 0; k < STB_MAXS; ++k) a[k] = (valid && k < s) ? Mp[k * cm] : (k == gl ? 1.0 : 0.0);
             }
-            if (cnt[T] > 0) {
-                for (int t = 0; t < tt.n_terms; ++t) {
-                    const double kq = c * P.C[tt.proc[t]] * F[Y.foff[T] + tt.fslot[t] * Y.cntp[T] + i];
-                    const int ta = tt.a[t], tb = tt.b[t];
+            if (s <= 4) cl_gj_inplace<4>(a, s, W, gl);
+            else if (s <= 8) cl_gj_inplace<8>(a, s, W, gl);
+            else cl_gj_inplace<STB_MAXS>(a, s, W, gl);
+            if (valid) {
+                double* Mp = Minv + Y.moff[T] + (gl * s) * cm + ion;
 #pragma unroll
-                    for (int k = 0; k < STB_MAXS; ++k)
-                        if (k == ta) a[k] += (gl == ta ? kq : 0.0) - (gl == tb ? kq : 0.0);
-                }
-            }
-            for (int col = 0; col < s; ++col) {
-                double acol = 0.0;
-#pragma unroll
-                for (int k = 0; k < STB_MAXS; ++k) acol = k == col ? a[k] : acol;
-                const double piv = __shfl_sync(0xffffffffu, acol, col, W);
-                const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
-                const bool mine = gl == col;
-                const double mlt = mine ? 0.0 : acol;
-#pragma unroll
-                for (int k = 0; k < STB_MAXS; ++k) {
-                    if (k < s) {
-                        const double pa = __shfl_sync(0xffffffffu, a[k], col, W) * inv;
-                        const double pi = __shfl_sync(0xffffffffu, ai[k], col, W) * inv;
-                        a[k] = mine ? pa : fma(-mlt, pa, a[k]);
-                        ai[k] = mine ? pi : fma(-mlt, pi, ai[k]);
-                    }
-                }
-            }
-            if (valid && gl < s) {
-                double* Mp = Minv + Y.moff[T] + (gl * s) * Y.cntm[T] + i;
-#pragma unroll
-                for (int b = 0; b < STB_MAXS; ++b)
-                    if (b < s) Mp[b * Y.cntm[T]] = ai[b];
+                for (int k = 0; k < STB_MAXS; ++k)
+                    if (k < s) Mp[k * cm] = a[k];
             }
         }
     };
@@ -788,7 +828,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             push(rb_zy, zy, own_ez[k], v);
         }
         sync_all();
-        rhs_pass(zy, fv);
+        rhs_pass(zy, Y.zy, fv);
         // ---- initial step (Hairer-Wanner, as scipy select_initial_step) -----------------------
         {
             double v3[3] = {0.0, 0.0, 0.0};
@@ -809,7 +849,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             for (int k = tid; k < n_own; k += STB_NT)
                 push(rb_zv, zv, own_ez[k], zy[own_ez[k]] + h0 * fv[k]);
             sync_all();
-            rhs_pass(zv, tw);
+            rhs_pass(zv, Y.zv, tw);
             double v1[1] = {0.0};
             for (int k = tid; k < n_own; k += STB_NT) {
                 const double a = (tw[k] - fv[k]) / scl[k];
@@ -876,7 +916,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 CLPROF(15)
                 sync_all();      // y_k complete in every CTA
                 CLPROF(3)
-                rhs_pass(zy, fv);
+                rhs_pass(zy, Y.zy, fv);
                 __syncthreads();
                 CLPROF(4)
                 block_inverses(c);
@@ -909,110 +949,143 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                     if (S.rv[1] != 0.0 || !isfinite(C.beta)) C.flag = 2;
                     S.gg[0] = C.beta;
                     C.inrm = C.beta > 0.0 ? 1.0 / C.beta : 0.0;
+                    if (C.flag != 2 && !(C.beta > C.tol_lin)) {
+                        // residual already below the linear tolerance: dy = 0
+                        int fl = newton_decide(C, 0.0);
+                        if (fl == 0 && C.newton_it >= STB_NEWTON_MAXIT) fl = 2;
+                        C.flag = fl;
+                    }
                 }
                 __syncthreads();
-                if (C.flag == 2) break;
                 // ---- GMRES: V_0 = tw / beta; zv holds the direction, scaled by `zmul` ----------
-                bool lin_done = !(C.beta > C.tol_lin);
+                // (C.flag: 0 while the solve runs; the thread that closes the solve leaves the Newton
+                // decision there: 1 converged, 2 failed, 0 iterate again)
+                bool lin_done = !(C.beta > C.tol_lin) || C.flag == 2;
                 int j = 0;
                 double zmul = C.inrm;
-                if (!lin_done)
-                    for (int k = tid; k < n_own; k += STB_NT) V[k] = tw[k] * zmul;
+                if (!lin_done) {
+                    double* V0 = Vrow(0);
+                    for (int k = tid; k < n_own; k += STB_NT) V0[k] = tw[k] * zmul;
+                }
                 while (!lin_done) {
                     // w = Minv (I - cJ) v / scale = V_j - c Minv k(v) / scale, k = inter-ion coupling
                     CLPROF(15)
-                    fields_pass(zv, zmul);
+                    fields_pass(Y.zv, zmul);
                     for (int k = tid; k < n_own; k += STB_NT) {
                         const int inf = own_inf[k];
                         const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
                         kv[k] = term_sum(T, a, i, zy);
                     }
                     __syncthreads();
-                    for (int k = tid; k < n_own; k += STB_NT) {
-                        const int inf = own_inf[k];
-                        const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
-                        tw[k] = V[j * PO + k] - c * minv_apply(T, a, i, kv) / scl[k];
+                    {
+                        const double* Vj = Vrow(j);
+                        for (int k = tid; k < n_own; k += STB_NT) {
+                            const int inf = own_inf[k];
+                            const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
+                            tw[k] = Vj[k] - c * minv_apply(T, a, i, kv) / scl[k];
+                        }
                     }
                     __syncthreads();
                     CLPROF(8)
                     // h_i = <w, V_i> (i <= j), ww = <w, w>: warp i takes dot i
                     const int K = j + 2;
-                    for (int i = warp; i < K; i += STB_NW) {
-                        const double* Vi = i <= j ? V + i * PO : tw;
-                        double acc = 0.0;
-                        for (int k = lane; k < n_own; k += 32) acc = fma(tw[k], Vi[k], acc);
-                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                        if (lane == 0) S.rv[i] = acc;
-                    }
-                    __syncthreads();
-                    CLPROF(9)
-                    reduce_post(K, tid < K ? S.rv[tid] : 0.0);
-                    CLPROF(10)
-                    const double ww = S.rv[j + 1];
-                    double hn2 = ww;
-                    for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
-                    if (tid <= j) S.H[tid * STB_KRYLOV + j] = S.rv[tid];
-                    // orthogonalise the own elements
-                    for (int k = tid; k < n_own; k += STB_NT) {
-                        double acc = tw[k];
-                        for (int i = 0; i <= j; ++i) acc = fma(-S.rv[i], V[i * PO + k], acc);
-                        tw[k] = acc;
-                    }
-                    if (!(hn2 > 0.01 * ww)) {
-                        // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
-                        __syncthreads();
+                    auto dots = [&]() {
                         for (int i = warp; i < K; i += STB_NW) {
-                            const double* Vi = i <= j ? V + i * PO : tw;
+                            const double* Vi = i <= j ? Vrow(i) : tw;
                             double acc = 0.0;
                             for (int k = lane; k < n_own; k += 32) acc = fma(tw[k], Vi[k], acc);
                             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
                             if (lane == 0) S.rv[i] = acc;
                         }
                         __syncthreads();
+                    };
+                    auto orth = [&]() {
+                        for (int k = tid; k < n_own; k += STB_NT) {
+                            double acc = tw[k];
+                            for (int i = 0; i <= j; ++i) acc = fma(-S.rv[i], Vrow(i)[k], acc);
+                            tw[k] = acc;
+                        }
+                    };
+                    dots();
+                    CLPROF(9)
+                    reduce_post(K, tid < K ? S.rv[tid] : 0.0);
+                    CLPROF(10)
+                    const double ww = S.rv[j + 1];
+                    double hn2 = ww;
+                    for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
+                    orth();
+                    const bool reorth = !(hn2 > 0.01 * ww);
+                    if (reorth) {
+                        // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
+                        if (tid <= j) S.H[tid * STB_KRYLOV + j] = S.rv[tid];
+                        __syncthreads();
+                        dots();
                         reduce_post(K, tid < K ? S.rv[tid] : 0.0);
                         const double w2 = S.rv[j + 1];
                         hn2 = w2;
                         for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
                         if (tid <= j) S.H[tid * STB_KRYLOV + j] += S.rv[tid];
-                        for (int k = tid; k < n_own; k += STB_NT) {
-                            double acc = tw[k];
-                            for (int i = 0; i <= j; ++i) acc = fma(-S.rv[i], V[i * PO + k], acc);
-                            tw[k] = acc;
-                        }
+                        orth();
                         if (!(hn2 > 0.01 * w2)) {
                             double v1[1] = {0.0};
                             for (int k = tid; k < n_own; k += STB_NT) v1[0] = fma(tw[k], tw[k], v1[0]);
                             reduce_vals(1, v1);
                             hn2 = S.rv[0];
                         }
+                        __syncthreads();     // H column complete
                     }
                     const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
                     const double ihn = hn > 0.0 ? 1.0 / hn : 0.0;
-                    __syncthreads();     // H column complete, S.rv free
-                    if (tid == 0) {
+                    // Givens update of column j, residual estimate and (when the solve closes) the
+                    // triangular solve + Newton decision: one thread of the least loaded warp, off
+                    // the path of the threads that orthogonalise and exchange the next direction
+                    if (tid == STB_NT - 32) {
                         C.st.n_jv += 1;
                         double* Hc = S.H + j;   // column j, stride STB_KRYLOV
+                        double prev = reorth ? Hc[0] : S.rv[0];
                         for (int i = 0; i < j; ++i) {
-                            const double a = Hc[i * STB_KRYLOV], b = Hc[(i + 1) * STB_KRYLOV];
-                            Hc[i * STB_KRYLOV] = S.cs[i] * a + S.sn[i] * b;
-                            Hc[(i + 1) * STB_KRYLOV] = -S.sn[i] * a + S.cs[i] * b;
+                            const double b = reorth ? Hc[(i + 1) * STB_KRYLOV] : S.rv[i + 1];
+                            Hc[i * STB_KRYLOV] = S.cs[i] * prev + S.sn[i] * b;
+                            prev = -S.sn[i] * prev + S.cs[i] * b;
                         }
-                        const double a = Hc[j * STB_KRYLOV];
-                        const double dnm = hypot(a, hn);
-                        if (dnm == 0.0) { S.cs[j] = 1.0; S.sn[j] = 0.0; }
-                        else { S.cs[j] = a / dnm; S.sn[j] = hn / dnm; }
+                        const double a = prev;
+                        const double dnm = sqrt(fma(a, a, hn * hn));
+                        const double idn = dnm > 0.0 ? 1.0 / dnm : 0.0;
+                        const double csj = dnm > 0.0 ? a * idn : 1.0, snj = hn * idn;
+                        S.cs[j] = csj;
+                        S.sn[j] = snj;
                         Hc[j * STB_KRYLOV] = dnm;
-                        S.gg[j + 1] = -S.sn[j] * S.gg[j];
-                        S.gg[j] = S.cs[j] * S.gg[j];
+                        S.rd[j] = idn;
+                        S.gg[j + 1] = -snj * S.gg[j];
+                        S.gg[j] = csj * S.gg[j];
                         C.kk = j + 1;
-                        C.beta = fabs(S.gg[j + 1]);
-                        if (!(hn > 0.0) || !isfinite(hn)) C.beta = 0.0;
+                        double beta = fabs(S.gg[j + 1]);
+                        if (!(hn > 0.0) || !isfinite(hn)) beta = 0.0;
+                        C.beta = beta;
+                        if (!(beta > C.tol_lin) || j + 1 >= STB_KRYLOV) {
+                            // x = V y with R y = g; ||x|| = ||y|| (orthonormal basis)
+                            const int nk = j + 1;
+                            double y2 = 0.0;
+                            for (int i = nk - 1; i >= 0; --i) {
+                                double acc = S.gg[i];
+                                for (int k = i + 1; k < nk; ++k) acc -= S.H[i * STB_KRYLOV + k] * S.yk_s[k];
+                                const double yi = acc * S.rd[i];
+                                S.yk_s[i] = yi;
+                                y2 = fma(yi, yi, y2);
+                            }
+                            int fl = newton_decide(C, sqrt(y2 / N));
+                            if (fl == 0 && C.newton_it >= STB_NEWTON_MAXIT) fl = 2;
+                            C.flag = fl;     // 2: do not apply the update
+                        }
                     }
                     // V_{j+1} = w / ||w||; its unscaled form is the next direction
-                    for (int k = tid; k < n_own; k += STB_NT) {
-                        const double v = tw[k] * ihn;
-                        V[(j + 1) * PO + k] = v;
-                        push(rb_zv, zv, own_ez[k], v * scl[k]);
+                    {
+                        double* Vn = Vrow(j + 1);
+                        for (int k = tid; k < n_own; k += STB_NT) {
+                            const double v = tw[k] * ihn;
+                            Vn[k] = v;
+                            push(rb_zv, zv, own_ez[k], v * scl[k]);
+                        }
                     }
                     zmul = 1.0;
                     CLPROF(11)
@@ -1021,28 +1094,13 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                     ++j;
                     lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
                 }
-                // ---- x = V y; dy = x * scale; ||x|| = ||y|| (orthonormal basis) --------------------
                 const int nk = C.kk;
-                if (tid == 0) {
-                    double y2 = 0.0;
-                    for (int i = nk - 1; i >= 0; --i) {
-                        double acc = S.gg[i];
-                        for (int k = i + 1; k < nk; ++k) acc -= S.H[i * STB_KRYLOV + k] * S.yk_s[k];
-                        const double hd = S.H[i * STB_KRYLOV + i];
-                        S.yk_s[i] = hd != 0.0 ? acc / hd : 0.0;
-                        y2 = fma(S.yk_s[i], S.yk_s[i], y2);
-                    }
-                    int flag = newton_decide(C, sqrt(y2 / N));
-                    if (flag == 0 && C.newton_it >= STB_NEWTON_MAXIT) flag = 2;
-                    C.flag = flag;     // 2: do not apply the update
-                }
-                __syncthreads();
                 const int flag = C.flag;
                 // a failed iteration (diverging, or out of iterations) is discarded with the step
                 if (flag != 2) {
                     for (int k = tid; k < n_own; k += STB_NT) {
                         double x = 0.0;
-                        for (int i = 0; i < nk; ++i) x = fma(S.yk_s[i], V[i * PO + k], x);
+                        for (int i = 0; i < nk; ++i) x = fma(S.yk_s[i], Vrow(i)[k], x);
                         const double dy = x * scl[k];
                         const double yn = zy[own_ez[k]] + dy;
                         dd[k] += dy;
