@@ -967,9 +967,9 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     if (own_yout) WSC(WS_YOUT, d_yout, out_bytes);
     WSC(WS_NEXT, d_next, sizeof(int));
     WSC(WS_STATS, d_stats, sizeof(stb_stats) * n);
-    WSC(WS_PROF, d_prof, sizeof(long long) * 16);
+    WSC(WS_PROF, d_prof, sizeof(long long) * 24);
     CKC(ws_events(S));
-    CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 16, S->stream));
+    CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 24, S->stream));
     CKC(cudaMemsetAsync(d_next, 0, sizeof(int), S->stream));
     CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     double* yout_p = own_yout ? d_yout : y_out;
@@ -1042,16 +1042,25 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     CKC(cudaStreamSynchronize(S->stream));
     CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
     if (getenv("STB_VERBOSE")) {
-        long long pr[16];
+        long long pr[24];
         CKC(cudaMemcpy(pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
         static const char* names[16] = {"stream", "stream_sync", "combine", "yk_barrier", "rhs_epilogue",
                                         "block_inv", "residual", "beta_reduce", "arnoldi_epi", "dots",
                                         "dots_reduce", "orth_push", "v_barrier", "newton_tail", "step_ctl",
                                         "loop_head"};
+        // unit of each phase: p = per pair pass, n = per Newton iteration, k = per Krylov iteration,
+        // s = per step
+        static const char unit[16] = {'p', 'p', 'p', 'n', 'n', 'n', 'n', 'n', 'k', 'k', 'k', 'k', 'k', 'n', 's', 's'};
         double tot = 0;
         for (int k = 0; k < 16; ++k) tot += (double)pr[k];
-        fprintf(stderr, "[stb] %.3f ms; last system of cluster 0, kcycles:", S->last_ms);
-        for (int k = 0; k < 16; ++k) fprintf(stderr, " %s=%.0f(%.0f%%)", names[k], pr[k] / 1e3, 100.0 * pr[k] / std::max(tot, 1.0));
+        const double steps = std::max<double>(1, pr[17]), nrhs = std::max<double>(1, pr[18]), njv = std::max<double>(1, pr[19]);
+        fprintf(stderr, "[stb] %.3f ms; cluster 0: %lld system(s), %.0f steps, %.0f rhs, %.0f jv, %.1f kcycles/step; "
+                "cycles per unit (p = pass, n = Newton it, k = Krylov it, s = step):", S->last_ms, pr[16],
+                steps, nrhs, njv, tot / steps / 1e3);
+        for (int k = 0; k < 16; ++k) {
+            const double den = unit[k] == 'p' ? nrhs + njv : unit[k] == 'n' ? nrhs : unit[k] == 'k' ? njv : steps;
+            fprintf(stderr, " %s=%.0f/%c(%.0f%%)", names[k], pr[k] / den, unit[k], 100.0 * pr[k] / std::max(tot, 1.0));
+        }
         fprintf(stderr, "\n");
     }
     return STB_OK;

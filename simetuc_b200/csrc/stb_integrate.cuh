@@ -58,7 +58,7 @@ struct Ctl {
     double beta, inrm, dy_norm, dy_norm_old, err_norm, safety, crate;
     double RU[(STB_MAXORD + 1) * (STB_MAXORD + 1)];
     double p[STB_MAXORD + 1];
-    int order, n_equal, status, kk, flag, newton_it, n_iter, since_verify;
+    int order, n_equal, status, kk, flag, flag2, newton_it, n_iter, since_verify;
     int64_t k_out, steps_since_out;
     stb_stats st;
     long long prof[8];

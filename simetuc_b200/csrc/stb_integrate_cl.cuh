@@ -89,7 +89,7 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
             if (L.blk[T][U].n_slots > Y.nsm) Y.nsm = L.blk[T][U].n_slots;
     Y.Pp = take(STB_NW * 2 * Y.nsm * CL_RG);
     Y.part = take(2 * G * STB_KRED);
-    Y.info = take(Y.PO);                       // two int tables of PO entries
+    Y.info = take(Y.PO + Y.PO / 2);            // three int tables of PO entries
     Y.V = v_smem > 0 ? take(v_smem * Y.PO) : -1;       // the first v_smem basis vectors
     Y.D = d_smem ? take(8 * Y.PO) : -1;
     Y.gres = o;
@@ -122,7 +122,7 @@ struct ClArgs {
     double* work;              // [n_clusters][G][work_stride]: spilled V / D
     int64_t work_stride;
     int* next_sys;             // work counter (dynamic assignment of systems to clusters)
-    long long* prof;           // [16] clock64 cycles per phase (cluster 0, rank 0, thread 0); may be null
+    long long* prof;           // [24] clock64 cycles per phase (cluster 0, rank 0, thread 0) + counters; may be null
 };
 
 __device__ __forceinline__ uint32_t cl_smem_u32(const void* p) {
@@ -161,16 +161,21 @@ __device__ __forceinline__ double2 cl_ld_nc2(const double* p) {
 //   RES: pair rows resident in shared memory, layout [pair][own row][2], addressed as offsets
 //        into the dynamic shared array (the compiler then emits LDS.128, not generic loads);
 //   else: global dense block, row-major, pitch ld (even), read through the non-allocating path.
+// Shared memory is addressed as offsets into the dynamic shared array so that LDS / STS are
+// emitted.  (Measured: a non-inlined version - one copy per (NS, RES) instead of one per call
+// site - is slower: the call ABI costs more than the smaller instruction footprint saves.)
 template <int NS, bool RES>
-__device__ __forceinline__ void cl_piece(const double* dynb, int g_off, const double* gb,
-                                         int64_t pitch, int row, int z_off, int ldz,
-                                         const int* slot_col, int nkp, int kk, int s0, int s1,
-                                         double mult, double* dst, int dpitch) {
-    double acc[NS];
+__device__ __forceinline__ void cl_piece(int g_off, const double* gb, int64_t pitch, int row, int z_off,
+                                      int ldz, const int* slot_col, int nkp, int kk, int s0, int s1,
+                                      double mult, int dst_off, int dpitch) {
+    extern __shared__ __align__(16) double dynb[];
+    double* dst = dynb + dst_off;
+    double acc[NS], acc2[NS];       // two chains per slot: the FP64 FMA latency, not its rate, binds
     int zo[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         acc[s] = 0.0;
+        acc2[s] = 0.0;
         zo[s] = z_off + slot_col[s] * ldz;
     }
     if (RES) {
@@ -185,7 +190,7 @@ __device__ __forceinline__ void cl_piece(const double* dynb, int g_off, const do
             for (int s = 0; s < NS; ++s) {
                 const double2 z = *reinterpret_cast<const double2*>(dynb + zo[s] + zk);
                 acc[s] = fma(g.x, z.x, acc[s]);
-                acc[s] = fma(g.y, z.y, acc[s]);
+                acc2[s] = fma(g.y, z.y, acc2[s]);
             }
             go += gstep;
             zk += 8;
@@ -202,12 +207,13 @@ __device__ __forceinline__ void cl_piece(const double* dynb, int g_off, const do
             for (int s = 0; s < NS; ++s) {
                 const double2 z = *reinterpret_cast<const double2*>(dynb + zo[s] + zk);
                 acc[s] = fma(g.x, z.x, acc[s]);
-                acc[s] = fma(g.y, z.y, acc[s]);
+                acc2[s] = fma(g.y, z.y, acc2[s]);
             }
         }
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
+        acc[s] += acc2[s];
         acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 8);
         acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], 16);
     }
@@ -218,11 +224,10 @@ __device__ __forceinline__ void cl_piece(const double* dynb, int g_off, const do
 }
 
 template <bool RES>
-__device__ __forceinline__ void cl_piece_ns(int ns, const double* dynb, int g_off, const double* gb,
-                                            int64_t pitch, int row, int z_off, int ldz,
-                                            const int* slot_col, int nkp, int kk, int s0, int s1,
-                                            double mult, double* dst, int dpitch) {
-#define CL_PIECE(NS_) cl_piece<NS_, RES>(dynb, g_off, gb, pitch, row, z_off, ldz, slot_col, nkp, kk, s0, s1, mult, dst, dpitch)
+__device__ __forceinline__ void cl_piece_ns(int ns, int g_off, const double* gb, int64_t pitch, int row,
+                                            int z_off, int ldz, const int* slot_col, int nkp, int kk,
+                                            int s0, int s1, double mult, int dst_off, int dpitch) {
+#define CL_PIECE(NS_) cl_piece<NS_, RES>(g_off, gb, pitch, row, z_off, ldz, slot_col, nkp, kk, s0, s1, mult, dst_off, dpitch)
     switch (ns) {
         case 1: CL_PIECE(1); break;
         case 2: CL_PIECE(2); break;
@@ -235,30 +240,6 @@ __device__ __forceinline__ void cl_piece_ns(int ns, const double* dynb, int g_of
 }
 
 #define CL_MAXCOMB ((STB_NW - 1) * STB_MAXC * CL_RG)   // a warp boundary splits at most one segment
-
-// In-place Gauss-Jordan inverse of an s x s block (s <= SM) held one row per lane, W lanes per
-// block; no pivoting (I - c J_qq is a column-diagonally-dominant M-matrix).  Entries k >= s of a
-// row must be 0.  Pivot-row elements travel by shuffle; nothing is indexed dynamically.
-template <int SM>
-__device__ __forceinline__ void cl_gj_inplace(double (&a)[STB_MAXS], int s, int W, int gl) {
-#pragma unroll
-    for (int col = 0; col < SM; ++col) {
-        if (col < s) {
-            const double piv = __shfl_sync(0xffffffffu, a[col], col, W);
-            const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
-            const bool mine = gl == col;
-            const double f = a[col];
-#pragma unroll
-            for (int k = 0; k < SM; ++k) {
-                if (k != col) {
-                    const double pr = __shfl_sync(0xffffffffu, a[k], col, W) * inv;
-                    a[k] = mine ? pr : fma(-f, pr, a[k]);
-                }
-            }
-            a[col] = mine ? inv : -f * inv;
-        }
-    }
-}
 
 struct ClConst {           // per-CTA constants that are indexed dynamically: shared, not local memory
     int r_lo[2], cnt[2], ob[2], nrg[2];
@@ -285,6 +266,38 @@ __device__ __forceinline__ void cl_compute_RU(int order, double factor, double* 
         }
 }
 
+// The same product computed by one warp: lane j builds column j of R(order, factor), lane 8 + j
+// column j of R(order, 1) (no divisions: 1/i from a table), then 36 lanes-worth of 6-term dots.
+__device__ __forceinline__ void cl_compute_RU_warp(int order, double factor, double* RU, double* R,
+                                                   double* U, int lane) {
+    const double RCP[6] = {0.0, 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2};
+    const int n = order + 1;
+    if ((lane & 7) < n && lane < 16) {
+        const int j = lane & 7;
+        const double f = lane < 8 ? factor : 1.0;
+        double* M = lane < 8 ? R : U;
+        double v = 1.0;
+        M[j] = 1.0;
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+            if (i < n) {
+                v = j == 0 ? 0.0 : v * ((i - 1 - f * j) * RCP[i]);
+                M[i * 6 + j] = v;
+            }
+        }
+    }
+    __syncwarp();
+    for (int e = lane; e < 36; e += 32) {
+        const int i = e / 6, j = e % 6;
+        if (i < n && j < n) {
+            double acc = 0.0;
+            for (int k = 0; k < n; ++k) acc += R[i * 6 + k] * U[k * 6 + j];
+            RU[i * 6 + j] = acc;
+        }
+    }
+    __syncwarp();
+}
+
 struct ClShared {
     DevLattice L;
     ClConst K;
@@ -304,7 +317,7 @@ struct ClShared {
     short tl_ptr[2][STB_MAXS + 1];               // rate terms touching state a of type T
     short tl_ent[2][2 * STB_MAXT];               // term index | sign bit (0x4000: +, i.e. b == a)
     int cur_sys;
-    long long prof[16];
+    long long prof[24];
 };
 
 __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     const int N = L.N;
 
     long long tick = clock64();
-    if (tid == 0) for (int k = 0; k < 16; ++k) S.prof[k] = 0;
+    if (tid == 0) for (int k = 0; k < 24; ++k) S.prof[k] = 0;
 #define CLPROF(k)                                            \
     if (tid == 0) {                                          \
         const long long now_ = clock64();                    \
@@ -403,6 +416,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     double* part = dyn + Y.part;
     int* own_ez = (int*)(dyn + Y.info);         // index into the gathered (padded plane) vector
     int* own_inf = own_ez + Y.PO;               // T << 30 | a << 24 | own row i
+    int* own_ref = own_inf + Y.PO;              // index in the reference (ion-major) layout
     double* wk = A.work + ((int64_t)cid * G + rank) * A.work_stride;
     const int PO = Y.PO;
     // Krylov basis [KRYLOV+1][PO]: the first nvs vectors in shared memory (a linear solve rarely
@@ -421,6 +435,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         const int a = kk_ / cnt[T], i = kk_ % cnt[T];
         own_ez[k] = Y.zoff[T] + a * Y.ldz[T] + r_lo[T] + i;
         own_inf[k] = (T << 30) | (a << 24) | i;
+        own_ref[k] = L.ref_of_plane[L.off[T] + a * L.n[T] + r_lo[T] + i];
     }
 
     // ---- rate terms by state -----------------------------------------------------------------
@@ -621,20 +636,19 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 const int s0 = max(t0, lo) - lo, s1 = min(tend, lo + stp[T][U]) - lo;
                 if (s0 >= s1) continue;
                 const int ns = L.blk[T][U].n_slots;
-                double* dst;
-                int dpitch;
+                int dst, dpitch;                 // offsets into the dynamic shared array
                 if (s0 == 0 && s1 == stp[T][U]) {
-                    dst = F + Y.foff[T] + (U ? L.blk[T][0].n_slots : 0) * Y.cntp[T] + gi * CL_RG + rr;
+                    dst = Y.F + Y.foff[T] + (U ? L.blk[T][0].n_slots : 0) * Y.cntp[T] + gi * CL_RG + rr;
                     dpitch = Y.cntp[T];
                 } else {
-                    dst = Pp + ((warp * 2 + (piece ? 1 : 0)) * Y.nsm) * CL_RG + rr;
+                    dst = Y.Pp + ((warp * 2 + (piece ? 1 : 0)) * Y.nsm) * CL_RG + rr;
                     dpitch = CL_RG;
                 }
                 if (gres_on[T][U])
-                    cl_piece_ns<true>(ns, dyn, K.goff[T][U], nullptr, gpitch[T][U], i, zb + Y.zoff[U],
+                    cl_piece_ns<true>(ns, K.goff[T][U], nullptr, gpitch[T][U], i, zb + Y.zoff[U],
                                       Y.ldz[U], L.blk[T][U].slot_col, Y.nkp[U], kk, s0, s1, mult, dst, dpitch);
                 else
-                    cl_piece_ns<false>(ns, dyn, 0, gsrc[T][U], gpitch[T][U], i, zb + Y.zoff[U],
+                    cl_piece_ns<false>(ns, 0, gsrc[T][U], gpitch[T][U], i, zb + Y.zoff[U],
                                        Y.ldz[U], L.blk[T][U].slot_col, Y.nkp[U], kk, s0, s1, mult, dst, dpitch);
                 ++piece;
             }
@@ -705,38 +719,29 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     // 1. every thread builds its own row of M in place (thread per state, as the epilogues);
     // 2. the blocks are inverted in place: closed form for 2-state ions (thread per ion), else
     //    Gauss-Jordan with W = pow2 >= s lanes per ion, one row per lane.
-    int inv_span[2];
-    inv_span[0] = L.s[0] == 2 ? ((cnt[0] + 31) & ~31) : ((cnt[0] * Wt[0] + 31) & ~31);
-    inv_span[1] = L.s[1] == 2 ? ((cnt[1] + 31) & ~31) : ((cnt[1] * Wt[1] + 31) & ~31);
-    const int inv0 = inv_span[0], inv_tot = inv_span[0] + inv_span[1];
     auto block_inverses = [&](double c) {
+        // 1. rows of M = I - c J_qq: closed-form inverse for 1- and 2-state ions (thread per ion),
+        //    else every thread builds the row of its own state in place
         for (int k = tid; k < n_own; k += STB_NT) {
             const int inf = own_inf[k];
             const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
             const int s = L.s[T], cm = Y.cntm[T];
-            double* Mp = Minv + Y.moff[T] + (a * s) * cm + i;
-            const double* lr = P.lin[T] + a * s;
-            for (int b = 0; b < s; ++b) Mp[b * cm] = (b == a ? 1.0 : 0.0) - c * lr[b];
             const TermTable& tt = L.terms[T];
+            const double* lin = P.lin[T];
             const double* Fq = F + Y.foff[T] + i;
-            for (int n = S.tl_ptr[T][a]; n < S.tl_ptr[T][a + 1]; ++n) {
-                const int e = S.tl_ent[T][n];
-                const int t = e & 0x3fff;
-                const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
-                Mp[tt.a[t] * cm] += (e & 0x4000) ? -kq : kq;     // row b_t: -, row a_t: +
-            }
-        }
-        __syncthreads();
-        for (int base = 0; base < inv_tot; base += STB_NT) {
-            const int m = base + tid;
-            if (m - lane >= inv_tot) break;                  // warp-uniform
-            const int T = m >= inv0;
-            const int s = L.s[T], cm = Y.cntm[T];
-            const int mm = T ? m - inv0 : m;
-            if (s == 2) {
-                if (mm < cnt[T]) {
-                    double* Mp = Minv + Y.moff[T] + mm;
-                    const double m00 = Mp[0], m01 = Mp[cm], m10 = Mp[2 * cm], m11 = Mp[3 * cm];
+            if (s <= 2) {
+                if (a != 0) continue;
+                double m00 = 1.0 - c * lin[0], m01 = 0.0, m10 = 0.0, m11 = 1.0;
+                if (s == 2) { m01 = -c * lin[1]; m10 = -c * lin[2]; m11 = 1.0 - c * lin[3]; }
+                for (int t = 0; t < tt.n_terms; ++t) {
+                    const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
+                    if (tt.a[t] == 0) { m00 += kq; m10 -= kq; }       // column a_t: row a_t +, row b_t -
+                    else { m11 += kq; m01 -= kq; }
+                }
+                double* Mp = Minv + Y.moff[T] + i;
+                if (s == 1) {
+                    Mp[0] = m00 != 0.0 ? 1.0 / m00 : 0.0;
+                } else {
                     const double det = m00 * m11 - m01 * m10;
                     const double id = det != 0.0 ? 1.0 / det : 0.0;
                     Mp[0] = m11 * id;
@@ -746,23 +751,59 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 }
                 continue;
             }
-            const int W = Wt[T];
-            const int ion = mm / W, gl = mm & (W - 1);
-            const bool valid = ion < cnt[T] && gl < s;
-            double a[STB_MAXS];
-            {
-                const double* Mp = Minv + Y.moff[T] + (gl * s) * cm + ion;
-#pragma unroll
-                for (int k = 0; k < STB_MAXS; ++k) a[k] = (valid && k < s) ? Mp[k * cm] : (k == gl ? 1.0 : 0.0);
+            double* Mp = Minv + Y.moff[T] + (a * s) * cm + i;
+            const double* lr = lin + a * s;
+            for (int b = 0; b < s; ++b) Mp[b * cm] = (b == a ? 1.0 : 0.0) - c * lr[b];
+            for (int n = S.tl_ptr[T][a]; n < S.tl_ptr[T][a + 1]; ++n) {
+                const int e = S.tl_ent[T][n];
+                const int t = e & 0x3fff;
+                const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
+                Mp[tt.a[t] * cm] += (e & 0x4000) ? -kq : kq;     // row b_t: -, row a_t: +
             }
-            if (s <= 4) cl_gj_inplace<4>(a, s, W, gl);
-            else if (s <= 8) cl_gj_inplace<8>(a, s, W, gl);
-            else cl_gj_inplace<STB_MAXS>(a, s, W, gl);
-            if (valid) {
-                double* Mp = Minv + Y.moff[T] + (gl * s) * cm + ion;
+        }
+        __syncthreads();
+        // 2. in-place Gauss-Jordan of the larger blocks, 64 threads per ion (<= 3 entries each), no
+        //    pivoting (column-diagonally-dominant M-matrix); compact rolled code: a lane-per-row
+        //    shuffle version costs 4-10k cycles per call (tools/ubench.cu), mostly instruction fetch
+        for (int T = 0; T < 2; ++T) {
+            const int s = L.s[T], cm = Y.cntm[T];
+            if (s <= 2 || cnt[T] <= 0) continue;
+            const int ss = s * s, tl = tid & 63;
+            int ei[3], ej[3];
 #pragma unroll
-                for (int k = 0; k < STB_MAXS; ++k)
-                    if (k < s) Mp[k * cm] = a[k];
+            for (int u = 0; u < 3; ++u) {
+                const int e = tl + 64 * u;
+                ei[u] = e / s;
+                ej[u] = e - ei[u] * s;
+            }
+            for (int ion0 = 0; ion0 < cnt[T]; ion0 += STB_NT / 64) {
+                const int ion = ion0 + (tid >> 6);
+                const bool act = ion < cnt[T];
+                double* Mq = Minv + Y.moff[T] + (act ? ion : 0);
+                for (int p = 0; p < s; ++p) {
+                    double nv[3];
+                    if (act) {
+                        const double piv = Mq[(p * s + p) * cm];
+                        const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int e = tl + 64 * u;
+                            if (e < ss) {
+                                const int i = ei[u], j = ej[u];
+                                const double aip = Mq[(i * s + p) * cm] * inv, apj = Mq[(p * s + j) * cm];
+                                nv[u] = i == p ? (j == p ? inv : apj * inv)
+                                               : (j == p ? -aip : fma(-aip, apj, Mq[e * cm]));
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    if (act) {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u)
+                            if (tl + 64 * u < ss) Mq[(tl + 64 * u) * cm] = nv[u];
+                    }
+                    __syncthreads();
+                }
             }
         }
     };
@@ -816,6 +857,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             C.since_verify = 0;
             memset(&C.st, 0, sizeof(stb_stats));
         }
+        int64_t k_out_l = 1;                                   // output cursor, uniform over the cluster
+        double tq_l = A.n_t > 1 ? A.t[1] : INFINITY;
         // D0 = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
         for (int k = tid; k < n_own; k += STB_NT) {
             const int inf = own_inf[k];
@@ -824,7 +867,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             const double v = y0[e];
             D[k] = v;
             for (int j = 1; j < 8; ++j) D[j * PO + k] = 0.0;
-            y_out[L.ref_of_plane[e]] = v;
+            y_out[own_ref[k]] = v;
             push(rb_zy, zy, own_ez[k], v);
         }
         sync_all();
@@ -874,7 +917,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
         while (true) {
             __syncthreads();
             CLPROF(14)
-            if (C.status != 0 || C.k_out >= A.n_t) break;
+            if (C.status != 0 || k_out_l >= A.n_t) break;
             if (tid == 0) {
                 C.flag = 0;
                 const double t_new = C.t + C.h;
@@ -1014,7 +1057,11 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                     double hn2 = ww;
                     for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
                     orth();
-                    const bool reorth = !(hn2 > 0.01 * ww);
+                    // Pythagorean norm of the orthogonalised vector: with ||w_orth|| > 1e-4 ||w|| the
+                    // cancellation costs at most 8 of 16 digits of hn2 and the basis stays orthogonal
+                    // to ~1e-12, far inside the linear tolerance; below that (a preconditioned operator
+                    // this close to the identity ends the solve anyway) re-orthogonalise explicitly
+                    const bool reorth = !(hn2 > 1e-8 * ww);
                     if (reorth) {
                         // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
                         if (tid <= j) S.H[tid * STB_KRYLOV + j] = S.rv[tid];
@@ -1026,7 +1073,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                         for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
                         if (tid <= j) S.H[tid * STB_KRYLOV + j] += S.rv[tid];
                         orth();
-                        if (!(hn2 > 0.01 * w2)) {
+                        if (!(hn2 > 1e-8 * w2)) {
                             double v1[1] = {0.0};
                             for (int k = tid; k < n_own; k += STB_NT) v1[0] = fma(tw[k], tw[k], v1[0]);
                             reduce_vals(1, v1);
@@ -1034,8 +1081,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                         }
                         __syncthreads();     // H column complete
                     }
-                    const double hn = hn2 > 0.0 ? sqrt(hn2) : 0.0;
-                    const double ihn = hn > 0.0 ? 1.0 / hn : 0.0;
+                    const double ihn = hn2 > 0.0 ? rsqrt(hn2) : 0.0;
+                    const double hn = hn2 * ihn;
                     // Givens update of column j, residual estimate and (when the solve closes) the
                     // triangular solve + Newton decision: one thread of the least loaded warp, off
                     // the path of the threads that orthogonalise and exchange the next direction
@@ -1125,21 +1172,23 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 continue;
             }
             CLPROF(13)
+            const double h = C.h, t_new = C.t + C.h;     // read before the control warp may change them
             // ---- error test and order selection share one reduction -------------------------------
             {
                 double v3[3] = {0.0, 0.0, 0.0};
                 for (int k = tid; k < n_own; k += STB_NT) {
                     const double sc = atol + rtol * fabs(zy[own_ez[k]]);
                     scl[k] = sc;
+                    const double rsc = 1.0 / sc;
                     const double dv = dd[k];
-                    const double er = ERRC[order] * dv / sc;
+                    const double er = ERRC[order] * dv * rsc;
                     v3[0] = fma(er, er, v3[0]);
                     if (order > 1) {
-                        const double em = ERRC[order - 1] * (D[order * PO + k] + dv) / sc;
+                        const double em = ERRC[order - 1] * (D[order * PO + k] + dv) * rsc;
                         v3[1] = fma(em, em, v3[1]);
                     }
                     if (order < STB_MAXORD) {
-                        const double ep = ERRC[order + 1] * (dv - D[(order + 1) * PO + k]) / sc;
+                        const double ep = ERRC[order + 1] * (dv - D[(order + 1) * PO + k]) * rsc;
                         v3[2] = fma(ep, ep, v3[2]);
                     }
                 }
@@ -1168,7 +1217,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             }
             const double err_m2 = S.rv[1], err_p2 = S.rv[2];
             // ---- accepted: update differences, dense output, order / step selection -------------
-            const double h = C.h, t_new = C.t + C.h;
+            // Every thread updates and interpolates its own elements with no barrier in between
+            // (the output cursor k_out_l / tq_l is kept identically by all threads); the scalar
+            // control work runs meanwhile on the last, least loaded warp.
             for (int k = tid; k < n_own; k += STB_NT) {
                 const double dv = dd[k];
                 const double dp1 = D[(order + 1) * PO + k];
@@ -1180,77 +1231,90 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                     D[i * PO + k] = run;
                 }
             }
-            while (true) {     // dense output for every requested time in (t, t_new]
-                __syncthreads();
-                if (tid == 0) {
-                    C.flag = 0;
-                    if (C.k_out < A.n_t) {
-                        const double tq = A.t[C.k_out];
-                        if (tq <= t_new * (1.0 + 1e-15) || tq <= t_new) {
-                            C.flag = tq >= t_new ? 2 : 1;
-                            double pr = 1.0;
-                            for (int jj = 0; jj < order; ++jj) {
-                                pr *= (tq - (t_new - h * jj)) / (h * (1 + jj));
-                                C.p[jj + 1] = pr;
-                            }
-                        }
+            bool wrote = false;
+            if (k_out_l < A.n_t && (tq_l <= t_new * (1.0 + 1e-15) || tq_l <= t_new)) {
+                const double ih = 1.0 / h;
+                const double RCPJ[5] = {1.0, 0.5, 1.0 / 3.0, 0.25, 0.2};
+                do {     // dense output for every requested time in (t, t_new]
+                    const bool exact = tq_l >= t_new;
+                    double pj[STB_MAXORD];
+                    double pr = 1.0;
+#pragma unroll
+                    for (int jj = 0; jj < STB_MAXORD; ++jj) {
+                        pr *= (tq_l - (t_new - h * jj)) * (ih * RCPJ[jj]);
+                        pj[jj] = jj < order ? pr : 0.0;
                     }
-                }
-                __syncthreads();
-                if (C.flag == 0) break;
-                double* row = y_out + C.k_out * (int64_t)N;
-                const bool exact = C.flag == 2;
-                for (int k = tid; k < n_own; k += STB_NT) {
-                    const int inf = own_inf[k];
-                    const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
-                    double acc = D[k];
-                    if (!exact)
-                        for (int jj = 1; jj <= order; ++jj) acc = fma(C.p[jj], D[jj * PO + k], acc);
-                    row[L.ref_of_plane[L.off[T] + a * L.n[T] + r_lo[T] + i]] = acc;
-                }
-                __syncthreads();
-                if (tid == 0) { C.k_out += 1; C.st.n_out = C.k_out; C.steps_since_out = 0; }
+                    double* row = y_out + k_out_l * (int64_t)N;
+                    for (int k = tid; k < n_own; k += STB_NT) {
+                        double acc = D[k];
+                        if (!exact) {
+#pragma unroll
+                            for (int jj = 0; jj < STB_MAXORD; ++jj)
+                                if (jj < order) acc = fma(pj[jj], D[(jj + 1) * PO + k], acc);
+                        }
+                        row[own_ref[k]] = acc;
+                    }
+                    wrote = true;
+                    ++k_out_l;
+                    tq_l = k_out_l < A.n_t ? A.t[k_out_l] : INFINITY;
+                } while (k_out_l < A.n_t && (tq_l <= t_new * (1.0 + 1e-15) || tq_l <= t_new));
             }
-            if (tid == 0) {
+            if (warp == STB_NW - 1) {
                 const bool need_order = (C.n_equal + 1) >= order + 1;
-                C.st.n_steps += 1;
-                C.steps_since_out += 1;
-                C.n_equal += 1;
-                C.t = t_new;
-                C.flag = 0;
+                int new_order = order;
+                double factor = 1.0;
                 if (need_order) {
-                    const double err_m = order > 1 ? sqrt(err_m2 / N) : INFINITY;
-                    const double err_p = order < STB_MAXORD ? sqrt(err_p2 / N) : INFINITY;
-                    double fm = err_m > 0.0 ? pow(err_m, -1.0 / order) : INFINITY;
-                    const double f0 = C.err_norm > 0.0 ? pow(C.err_norm, -1.0 / (order + 1)) : INFINITY;
-                    double fp = err_p > 0.0 ? pow(err_p, -1.0 / (order + 2)) : INFINITY;
-                    if (order == 1) fm = 0.0;
-                    if (order == STB_MAXORD) fp = 0.0;
-                    if (isinf(err_m)) fm = 0.0;
-                    if (isinf(err_p)) fp = 0.0;
+                    double f = 0.0;
+                    if (lane < 3) {
+                        // candidate orders order-1, order, order+1 on lanes 0, 1, 2
+                        const bool avail = lane == 1 || (lane == 0 ? order > 1 : order < STB_MAXORD);
+                        const double en = lane == 1 ? C.err_norm : sqrt((lane == 0 ? err_m2 : err_p2) / N);
+                        f = !avail ? 0.0 : (en > 0.0 ? pow(en, -1.0 / (order + lane)) : INFINITY);
+                    }
+                    const double fm = __shfl_sync(0xffffffffu, f, 0);
+                    const double f0 = __shfl_sync(0xffffffffu, f, 1);
+                    const double fp = __shfl_sync(0xffffffffu, f, 2);
                     int delta;
                     double best;
                     // numpy argmax picks the first maximum: order-1 wins ties, then same order
                     if (fm >= f0 && fm >= fp) { best = fm; delta = -1; }
                     else if (f0 >= fp) { best = f0; delta = 0; }
                     else { best = fp; delta = 1; }
-                    C.order = order + delta;
-                    const double factor = fmin(STB_MAX_FACTOR, C.safety * best);
-                    cl_compute_RU(C.order, factor, C.RU, K.Rs, K.Us);
-                    C.h *= factor;
-                    C.n_equal = 0;
-                    C.flag = 1;
+                    new_order = order + delta;
+                    factor = fmin(STB_MAX_FACTOR, C.safety * best);
+                    cl_compute_RU_warp(new_order, factor, C.RU, K.Rs, K.Us, lane);
                 }
-                C.st.last_order = C.order;
-                C.st.last_h = C.h;
+                if (lane == 0) {
+                    C.st.n_steps += 1;
+                    C.steps_since_out = wrote ? 1 : C.steps_since_out + 1;
+                    C.k_out = k_out_l;
+                    C.st.n_out = k_out_l;
+                    C.t = t_new;
+                    C.flag2 = 0;      // (not C.flag: slow threads may still be reading the rejection test)
+                    if (need_order) {
+                        C.order = new_order;
+                        C.h = h * factor;
+                        C.n_equal = 0;
+                        C.flag2 = 1;
+                    } else {
+                        C.n_equal += 1;
+                    }
+                    C.st.last_order = C.order;
+                    C.st.last_h = C.h;
+                }
             }
             __syncthreads();
-            if (C.flag == 1) apply_change_D(C.order);
+            if (C.flag2 == 1) apply_change_D(C.order);
         }
         __syncthreads();
         CLPROF(14)
-        if (tid == 0 && rank == 0 && cid == 0 && A.prof)
-            for (int k = 0; k < 16; ++k) A.prof[k] = S.prof[k];
+        if (tid == 0 && rank == 0 && cid == 0 && A.prof) {
+            S.prof[16] += 1;                 // systems this cluster solved; counters of all of them
+            S.prof[17] += C.st.n_steps;
+            S.prof[18] += C.st.n_rhs;
+            S.prof[19] += C.st.n_jv;
+            for (int k = 0; k < 24; ++k) A.prof[k] = S.prof[k];
+        }
         if (tid == 0 && rank == 0) {
             C.st.status = C.status;
             C.st.t_reached = C.t;
