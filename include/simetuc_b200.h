@@ -174,6 +174,12 @@ int stb_integrate_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, 
  * record their own events on it; and the number of kernels launched by the library so far. */
 void* stb_stream(const stb_system* sys);
 int64_t stb_launch_count(void);
+
+/* Device buffers of destroyed handles are parked (per device, up to 8 GB) and reused by the next
+ * handle instead of going through cudaFree / cudaMalloc: a sweep such as
+ * `simulate_power_dependence` (simulations.py:1277-1316) builds one system per call.  This returns
+ * the parked memory to the driver; the result is the number of bytes released. */
+int64_t stb_release_cached_memory(void);
 /* Device time (ms, CUDA events) of the last stb_integrate call's kernels, and the number of
  * kernel launches it made. */
 int stb_last_timing(const stb_system* sys, float* ms, int64_t* launches);

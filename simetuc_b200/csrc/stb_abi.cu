@@ -16,6 +16,102 @@
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};   // kernels launched by this library (all handles)
 
+// ---- device memory pool ----------------------------------------------------------------------
+// cudaMalloc / cudaFree synchronise the device and, on this platform, stall for tens to hundreds
+// of milliseconds every few calls.  A sweep creates and destroys one system per call, always with
+// the same buffer sizes, so freed blocks are parked per device and handed out again by size;
+// at most STB_POOL_CAP bytes stay parked (stb_release_cached_memory returns them to the driver).
+#include <mutex>
+#include <unordered_map>
+#define STB_POOL_CAP (8ull << 30)
+struct PoolBlock { void* p; size_t bytes; int dev; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBlock> g_pool_parked;
+static std::unordered_map<void*, PoolBlock> g_pool_live;
+static size_t g_pool_parked_bytes = 0;
+
+static cudaError_t pool_malloc(void** out, size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        int best = -1;
+        for (int k = 0; k < (int)g_pool_parked.size(); ++k) {
+            const PoolBlock& b = g_pool_parked[k];
+            if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 4 + 4096) continue;
+            if (best < 0 || b.bytes < g_pool_parked[best].bytes) best = k;
+        }
+        if (best >= 0) {
+            PoolBlock b = g_pool_parked[best];
+            g_pool_parked.erase(g_pool_parked.begin() + best);
+            g_pool_parked_bytes -= b.bytes;
+            g_pool_live[b.p] = b;
+            *out = b.p;
+            return cudaSuccess;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        // give parked memory back and retry once
+        cudaGetLastError();
+        std::vector<PoolBlock> drop;
+        {
+            std::lock_guard<std::mutex> lk(g_pool_mu);
+            drop.swap(g_pool_parked);
+            g_pool_parked_bytes = 0;
+        }
+        for (auto& b : drop) cudaFree(b.p);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    g_pool_live[p] = PoolBlock{p, bytes, dev};
+    *out = p;
+    return cudaSuccess;
+}
+template <class T>
+static cudaError_t pool_malloc(T** out, size_t bytes) { return pool_malloc((void**)out, bytes); }
+
+// The caller guarantees that no kernel still uses the block (handles synchronise their stream
+// before they release anything).
+static void pool_free(void* p) {
+    if (!p) return;
+    PoolBlock b{nullptr, 0, 0};
+    std::vector<PoolBlock> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        auto it = g_pool_live.find(p);
+        if (it == g_pool_live.end()) { b.p = p; }       // not ours: plain cudaFree below
+        else {
+            PoolBlock blk = it->second;
+            g_pool_live.erase(it);
+            g_pool_parked.push_back(blk);
+            g_pool_parked_bytes += blk.bytes;
+            while (g_pool_parked_bytes > STB_POOL_CAP && !g_pool_parked.empty()) {
+                drop.push_back(g_pool_parked.front());
+                g_pool_parked_bytes -= g_pool_parked.front().bytes;
+                g_pool_parked.erase(g_pool_parked.begin());
+            }
+        }
+    }
+    if (b.p) cudaFree(b.p);
+    for (auto& d : drop) cudaFree(d.p);
+}
+
+extern "C" int64_t stb_release_cached_memory(void) {
+    std::vector<PoolBlock> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        drop.swap(g_pool_parked);
+        g_pool_parked_bytes = 0;
+    }
+    int64_t bytes = 0;
+    for (auto& b : drop) { cudaFree(b.p); bytes += (int64_t)b.bytes; }
+    return bytes;
+}
+
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -87,10 +183,10 @@ struct stb_system {
 static cudaError_t ws_get(stb_system* S, int slot, size_t bytes, void** out) {
     bytes = std::max<size_t>(bytes, 16);
     if (bytes > S->ws_cap[slot]) {
-        if (S->ws_ptr[slot]) cudaFree(S->ws_ptr[slot]);
+        if (S->ws_ptr[slot]) pool_free(S->ws_ptr[slot]);
         S->ws_ptr[slot] = nullptr;
         S->ws_cap[slot] = 0;
-        cudaError_t e = cudaMalloc(&S->ws_ptr[slot], bytes);
+        cudaError_t e = pool_malloc(&S->ws_ptr[slot], bytes);
         if (e != cudaSuccess) return e;
         S->ws_cap[slot] = bytes;
     }
@@ -124,7 +220,7 @@ extern "C" int stb_describe(char* buf, int64_t buf_len) {
 template <class T>
 static cudaError_t upload(T** dst, const std::vector<T>& v) {
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
-    cudaError_t e = cudaMalloc((void**)dst, bytes);
+    cudaError_t e = pool_malloc((void**)dst, bytes);
     if (e != cudaSuccess) return e;
     if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
@@ -150,29 +246,30 @@ static bool invert3(const double* m, double* inv) {
 extern "C" void stb_system_destroy(stb_system* S) {
     if (!S) return;
     cudaSetDevice(S->device);
-    cudaFree(S->dL);
-    cudaFree(S->d_type);
-    cudaFree(S->d_local_idx);
-    cudaFree(S->d_gs_ref);
-    cudaFree(S->d_plane_of_ref);
-    cudaFree(S->d_ref_of_plane);
-    cudaFree(S->d_len);
+    if (S->stream) cudaStreamSynchronize(S->stream);      // nothing may still use the pooled blocks
+    pool_free(S->dL);
+    pool_free(S->d_type);
+    pool_free(S->d_local_idx);
+    pool_free(S->d_gs_ref);
+    pool_free(S->d_plane_of_ref);
+    pool_free(S->d_ref_of_plane);
+    pool_free(S->d_len);
     for (int T = 0; T < 2; ++T) {
-        cudaFree(S->d_gs_of_local[T]);
+        pool_free(S->d_gs_of_local[T]);
         for (int U = 0; U < 2; ++U) {
-            cudaFree(S->d_col[T][U]);
-            cudaFree(S->d_line_ptr[T][U]);
-            for (int m = 0; m < STB_MAXM; ++m) cudaFree(S->d_g[T][U][m]);
+            pool_free(S->d_col[T][U]);
+            pool_free(S->d_line_ptr[T][U]);
+            for (int m = 0; m < STB_MAXM; ++m) pool_free(S->d_g[T][U][m]);
         }
     }
-    cudaFree(S->d_blocks);
-    cudaFree(S->d_strengths);
-    cudaFree(S->d_y);
-    cudaFree(S->d_v);
-    cudaFree(S->d_out);
-    cudaFree(S->d_F);
-    cudaFree(S->d_tmp);
-    for (int k = 0; k < stb_system::WS_COUNT; ++k) cudaFree(S->ws_ptr[k]);
+    pool_free(S->d_blocks);
+    pool_free(S->d_strengths);
+    pool_free(S->d_y);
+    pool_free(S->d_v);
+    pool_free(S->d_out);
+    pool_free(S->d_F);
+    pool_free(S->d_tmp);
+    for (int k = 0; k < stb_system::WS_COUNT; ++k) pool_free(S->ws_ptr[k]);
     if (S->ev0) cudaEventDestroy(S->ev0);
     if (S->ev1) cudaEventDestroy(S->ev1);
     if (S->stream) cudaStreamDestroy(S->stream);
@@ -339,21 +436,21 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     G.d_max = d_max;
     double* d_geo = nullptr;
     if (dist_array) {
-        CKP(cudaMalloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
+        CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
         CKP(cudaMemcpy(d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
         G.dist = d_geo;
     } else {
-        CKP(cudaMalloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
+        CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
         CKP(cudaMemcpy(d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
         G.pos = d_geo;
         if (cell) {
             G.periodic = 1;
             memcpy(G.cell, cell, sizeof(double) * 9);
-            if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); cudaFree(d_geo); delete S; return nullptr; }
+            if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); pool_free(d_geo); delete S; return nullptr; }
         }
     }
     // ---- pass 1: row lengths ---------------------------------------------------------------------
-    CKP(cudaMalloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
+    CKP(pool_malloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
     g_launches++;
     k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
@@ -393,7 +490,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
                 if (L.blk[T][U].n_slots == 0 || S->n[T] == 0 || S->n[U] == 0) continue;
                 const size_t cells = (size_t)S->n[T] * L.ld[U];
                 for (int m = 0; m < L.n_mult; ++m) {
-                    CKP(cudaMalloc((void**)&S->d_g[T][U][m], cells * sizeof(double)));
+                    CKP(pool_malloc((void**)&S->d_g[T][U][m], cells * sizeof(double)));
                     CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, cells * sizeof(double), S->stream));
                     L.blk[T][U].g[m] = S->d_g[T][U][m];
                     FD.g[T][U][m] = S->d_g[T][U][m];
@@ -434,10 +531,10 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             S->h_line_ptr[T][U] = lp;
             CKP(upload(&S->d_line_ptr[T][U], lp));
             size_t slots = std::max<int64_t>(lines * 32, 1);
-            CKP(cudaMalloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
+            CKP(pool_malloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
             CKP(cudaMemsetAsync(S->d_col[T][U], 0, slots * sizeof(uint32_t), S->stream));
             for (int m = 0; m < L.n_mult; ++m) {
-                CKP(cudaMalloc((void**)&S->d_g[T][U][m], slots * sizeof(double)));
+                CKP(pool_malloc((void**)&S->d_g[T][U][m], slots * sizeof(double)));
                 CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, slots * sizeof(double), S->stream));
             }
             S->slots += lines * 32;
@@ -473,9 +570,9 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     CKP(cudaGetLastError());
     CKP(cudaStreamSynchronize(S->stream));
     }
-    cudaFree(d_geo);
+    pool_free(d_geo);
     L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
-    CKP(cudaMalloc((void**)&S->dL, sizeof(DevLattice)));
+    CKP(pool_malloc((void**)&S->dL, sizeof(DevLattice)));
     CKP(cudaMemcpy(S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
     if (stb_set_batch(S, 1) != STB_OK) { stb_system_destroy(S); return nullptr; }
     return S;
@@ -517,11 +614,11 @@ extern "C" int stb_set_batch(stb_system* S, int32_t n_sys) {
     S->h_strengths.resize((size_t)n_sys * std::max(S->n_proc, 1));
     for (int b = 0; b < n_sys; ++b)
         for (int p = 0; p < S->n_proc; ++p) S->h_strengths[(size_t)b * S->n_proc + p] = S->procs[p].strength;
-    cudaFree(S->d_blocks);
-    cudaFree(S->d_strengths);
+    pool_free(S->d_blocks);
+    pool_free(S->d_strengths);
     S->d_blocks = S->d_strengths = nullptr;
-    CK(cudaMalloc((void**)&S->d_blocks, sizeof(double) * S->h_blocks.size()));
-    CK(cudaMalloc((void**)&S->d_strengths, sizeof(double) * S->h_strengths.size()));
+    CK(pool_malloc((void**)&S->d_blocks, sizeof(double) * S->h_blocks.size()));
+    CK(pool_malloc((void**)&S->d_strengths, sizeof(double) * S->h_strengths.size()));
     S->params_dirty = true;
     return STB_OK;
 }
@@ -623,10 +720,10 @@ extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint
     EA.procs = d_pr;
     EA.n_proc = S->n_proc;
     EA.n = n;
-    if (N_indices) CK(cudaMalloc((void**)&EA.N_indices, sizeof(uint32_t) * 2 * M));
-    if (et_rows) CK(cudaMalloc((void**)&EA.et_rows, sizeof(int32_t) * 4 * M));
-    if (et_w) CK(cudaMalloc((void**)&EA.et_w, sizeof(double) * M));
-    if (jac_indices) CK(cudaMalloc((void**)&EA.jac, sizeof(uint32_t) * 6 * M));
+    if (N_indices) CK(pool_malloc((void**)&EA.N_indices, sizeof(uint32_t) * 2 * M));
+    if (et_rows) CK(pool_malloc((void**)&EA.et_rows, sizeof(int32_t) * 4 * M));
+    if (et_w) CK(pool_malloc((void**)&EA.et_w, sizeof(double) * M));
+    if (jac_indices) CK(pool_malloc((void**)&EA.jac, sizeof(uint32_t) * 6 * M));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
     g_launches++;
     k_export<<<blocks, 256, 0, S->stream>>>(EA);
@@ -636,26 +733,26 @@ extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint
     if (et_w) CK(cudaMemcpyAsync(et_w, EA.et_w, sizeof(double) * M, cudaMemcpyDeviceToHost, S->stream));
     if (jac_indices) CK(cudaMemcpyAsync(jac_indices, EA.jac, sizeof(uint32_t) * 6 * M, cudaMemcpyDeviceToHost, S->stream));
     CK(cudaStreamSynchronize(S->stream));
-    cudaFree(EA.N_indices);
-    cudaFree(EA.et_rows);
-    cudaFree(EA.et_w);
-    cudaFree(EA.jac);
-    cudaFree(d_off);
-    cudaFree(d_pr);
+    pool_free(EA.N_indices);
+    pool_free(EA.et_rows);
+    pool_free(EA.et_w);
+    pool_free(EA.jac);
+    pool_free(d_off);
+    pool_free(d_pr);
     return STB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 static int ensure_scratch(stb_system* S, int n) {
     if (S->scratch_n >= n) return STB_OK;
-    cudaFree(S->d_y); cudaFree(S->d_v); cudaFree(S->d_out); cudaFree(S->d_F); cudaFree(S->d_tmp);
+    pool_free(S->d_y); pool_free(S->d_v); pool_free(S->d_out); pool_free(S->d_F); pool_free(S->d_tmp);
     S->d_y = S->d_v = S->d_out = S->d_F = S->d_tmp = nullptr;
     size_t bytes = sizeof(double) * (size_t)n * S->N;
-    CK(cudaMalloc((void**)&S->d_y, bytes));
-    CK(cudaMalloc((void**)&S->d_v, bytes));
-    CK(cudaMalloc((void**)&S->d_out, bytes));
-    CK(cudaMalloc((void**)&S->d_tmp, bytes));
-    CK(cudaMalloc((void**)&S->d_F, sizeof(double) * (size_t)n * std::max(S->hL.NF, 1)));
+    CK(pool_malloc((void**)&S->d_y, bytes));
+    CK(pool_malloc((void**)&S->d_v, bytes));
+    CK(pool_malloc((void**)&S->d_out, bytes));
+    CK(pool_malloc((void**)&S->d_tmp, bytes));
+    CK(pool_malloc((void**)&S->d_F, sizeof(double) * (size_t)n * std::max(S->hL.NF, 1)));
     S->scratch_n = n;
     return STB_OK;
 }
@@ -677,14 +774,14 @@ extern "C" int stb_to_planes(const stb_system* S, int32_t n, const double* y_hos
     CK(cudaSetDevice(S->device));
     double* tmp = nullptr;
     size_t bytes = sizeof(double) * (size_t)n * S->N;
-    CK(cudaMalloc((void**)&tmp, bytes));
+    CK(pool_malloc((void**)&tmp, bytes));
     CK(cudaMemcpyAsync(tmp, y_host, bytes, cudaMemcpyHostToDevice, S->stream));
     int64_t tot = (int64_t)n * S->N;
     g_launches++;
     k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, tmp, y_planes_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(S->stream));
-    cudaFree(tmp);
+    pool_free(tmp);
     return STB_OK;
 }
 
@@ -693,14 +790,14 @@ extern "C" int stb_from_planes(const stb_system* S, int32_t n, const double* y_p
     CK(cudaSetDevice(S->device));
     double* tmp = nullptr;
     size_t bytes = sizeof(double) * (size_t)n * S->N;
-    CK(cudaMalloc((void**)&tmp, bytes));
+    CK(pool_malloc((void**)&tmp, bytes));
     int64_t tot = (int64_t)n * S->N;
     g_launches++;
     k_planes_to_ref<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, S->N, n, y_planes_dev, tmp);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(y_host, tmp, bytes, cudaMemcpyDeviceToHost, S->stream));
     CK(cudaStreamSynchronize(S->stream));
-    cudaFree(tmp);
+    pool_free(tmp);
     return STB_OK;
 }
 

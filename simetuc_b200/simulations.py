@@ -56,10 +56,12 @@ class Solution:
     '''Base class for solutions of rate equation problems (`simulations.py:41-286`).'''
 
     def __init__(self, t_sol: np.array, y_sol: np.array, index_S_i: List[int],
-                 index_A_j: List[int], cte, average: bool = False) -> None:
+                 index_A_j: List[int], cte, average: bool = False, own_cte: bool = False) -> None:
         self.t_sol = t_sol
         self.y_sol = y_sol
-        self.cte = copy.deepcopy(cte)
+        # the reference copies the settings (`simulations.py:64`); `own_cte=True`: the caller
+        # hands over a private copy it made for this solution (the sweeps do)
+        self.cte = cte if own_cte else copy.deepcopy(cte)
         self.index_S_i = list(index_S_i)
         self.index_A_j = list(index_A_j)
         self.average = average
@@ -565,11 +567,11 @@ class Simulations:
                 # under the device-computed emission curves gives the same steady state without
                 # moving the [n_t, N] trajectory to the host
                 avg_steady = cumulative_trapezoid(avg, t_sol)
-                sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte)
+                sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, own_cte=True)
                 sol.set_avg_data(avg_steady)
             else:
                 sol = SteadyStateSolution(t_sol, y_sol if y_sol is not None else avg,
-                                          index_S_i, index_A_j, cte)
+                                          index_S_i, index_A_j, cte, own_cte=True)
                 sol.set_avg_data(avg)
             sol.solver_stats = st
             solutions.append(sol)
