@@ -13,6 +13,7 @@ index_S_i, index_A_j, cte, list_avg_data, steady_state_populations, power_dens,
 concentration, errors`); plotting and HDF5 persistence are outside this path (results are
 saved as `.npz`).
 """
+import concurrent.futures
 import copy
 import csv
 import logging
@@ -367,9 +368,12 @@ class Simulations:
 
     `devices`: CUDA device ordinals to spread independent systems over (default: device 0).'''
 
-    def __init__(self, cte, full_path: str = None, devices: Optional[Sequence[int]] = None) -> None:
+    def __init__(self, cte, full_path: str = None, devices: Optional[Sequence[int]] = None,
+                 streams_per_device: int = 8) -> None:
         self.cte = cte
         self.full_path = full_path
+        #: independent lattices (concentration points) solved concurrently on one device
+        self.streams_per_device = max(1, int(streams_per_device))
         self.devices = list(devices) if devices else [0]
 
     def __bool__(self) -> bool:
@@ -546,16 +550,28 @@ class Simulations:
         logger = logging.getLogger(__name__ + '.pow_dep')
         start_time = time.time()
         power_dens_list = [float(elem) for elem in list(power_dens_list)]
-        ctes = []
+        pulsed = self._is_pulsed()
+        # The device only needs the absorption block of every power: the batch is launched from
+        # light settings (shared sections, private excitations) and the full per-solution copies
+        # the reference makes (`simulations.py:1290`) are built while the GPU integrates.
+        light = []
         for power_dens in power_dens_list:
-            cte = copy.deepcopy(self.cte)
+            cte = copy.copy(self.cte)
+            cte['excitations'] = copy.deepcopy(self.cte['excitations'])
             for exc_list in cte['excitations'].values():
                 for exc in exc_list:
                     exc.power_dens = power_dens
-            ctes.append(cte)
-        pulsed = self._is_pulsed()
-        sols, index_S_i, index_A_j, lat, stats = self._sweep_same_lattice(ctes, dynamics=pulsed,
-                                                                         keep_y=keep_y)
+            light.append(cte)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+            pending = pool.submit(self._sweep_same_lattice, light, dynamics=pulsed, keep_y=keep_y)
+            ctes = []
+            for power_dens in power_dens_list:
+                cte = copy.deepcopy(self.cte)
+                for exc_list in cte['excitations'].values():
+                    for exc in exc_list:
+                        exc.power_dens = power_dens
+                ctes.append(cte)
+            sols, index_S_i, index_A_j, lat, stats = pending.result()
         solutions = []
         for cte, (t_sol, y_sol, avg), st in zip(ctes, sols, stats):
             cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
@@ -622,11 +638,14 @@ class Simulations:
                 sol.set_avg_data(avg)
             return sol
 
+        # every point is its own lattice, i.e. its own handle and stream: several points are in
+        # flight per device (a system of this size occupies one cluster of <= 8 SMs out of 148)
         n_dev = min(len(self.devices), len(concentrations))
+        per_dev = max(1, min(self.streams_per_device, -(-len(concentrations) // n_dev)))
         jobs = [(lambda k=k: solve_point(k, self.devices[k % n_dev]))
                 for k in range(len(concentrations))]
         with disable_loggers([__name__ + '.dynamics', __name__ + '.steady_state']):
-            solutions = _run_on_devices(jobs, n_dev)
+            solutions = _run_on_devices(jobs, n_dev * per_dev)
         self.cte['lattice']['N_uc'] = N_uc_list[-1]
         self.cte['lattice']['S_conc'], self.cte['lattice']['A_conc'] = concentrations[-1]
         conc_dep_solution = ConcentrationDependenceSolution(dynamics=dynamics)
