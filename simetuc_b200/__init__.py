@@ -12,3 +12,11 @@ compute call does (there is no CPU fallback).
 VERSION = '0.1.0'
 from .settings import Settings            # noqa: E402,F401
 from .simulations import Simulations      # noqa: E402,F401
+
+import os as _os
+
+# Every handle of the library owns a CUDA stream, and sweeps keep several handles in flight per
+# device.  With the default of 8 hardware work queues, streams share queues and a short kernel of
+# one handle (pair build, layout conversion) waits behind the persistent integrator kernel of
+# another one; 32 is the maximum.  Only effective before the CUDA context of the process exists.
+_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')

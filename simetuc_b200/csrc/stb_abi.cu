@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,6 +15,8 @@
 #include "stb_kernels.cuh"
 
 static thread_local std::string g_err;
+// see simetuc_b200/__init__.py: one hardware work queue per stream in flight, if nobody chose otherwise
+static const int g_env_once = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 static std::atomic<long long> g_launches{0};   // kernels launched by this library (all handles)
 
 // ---- device memory pool ----------------------------------------------------------------------
@@ -922,6 +925,26 @@ extern "C" int stb_jv_dev(stb_system* S, int32_t first, int32_t n, int32_t pulse
 
 // ---------------------------------------------------------------------------------------------
 // Cluster integrator (small lattices): launch plan and driver.
+// Opt both integrators into the full dynamic shared memory of an SM once per device: the attribute
+// belongs to the function, not to a launch, and handles on several host threads launch concurrently.
+template <class K>
+static cudaError_t allow_max_smem(K kernel) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;      // (function, device) already set
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& d : done)
+        if (d.first == (const void*)kernel && d.second == dev) return cudaSuccess;
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             232448 - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) done.emplace_back((const void*)kernel, dev);
+    return e;
+}
+
 struct ClPlan {
     int G = 0, n_clusters = 0, resmask = 0, v_smem = 0, d_smem = 0;
     size_t dyn_bytes = 0;
@@ -929,8 +952,7 @@ struct ClPlan {
 };
 
 static cudaError_t cl_max_clusters(int G, size_t dyn_bytes, int sm_count, int* out) {
-    cudaError_t e = cudaFuncSetAttribute(k_integrate_cl, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)dyn_bytes);
+    cudaError_t e = allow_max_smem(k_integrate_cl);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1114,7 +1136,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         g_launches++;
-        CKC(cudaFuncSetAttribute(k_integrate_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dyn_bytes));
+        CKC(allow_max_smem(k_integrate_cl));
         CKC(cudaLaunchKernelEx(&cfg, k_integrate_cl, A));
     }
     CKC(cudaEventRecord(e1, S->stream));
@@ -1232,7 +1254,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64;
     int n_groups = std::max(1, std::min(max_ctas / G, n));
     const int grid = n_groups * G;
-    CK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_bytes));
+    CK(allow_max_smem(k_integrate));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate, STB_NT, dyn_bytes));
     if (occ < 1) return fail(STB_ECUDA, "integrator kernel does not fit on an SM");

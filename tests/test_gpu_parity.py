@@ -269,3 +269,39 @@ def test_dense_and_indexed_formats_agree(monkeypatch):
     assert np.all(np.abs(ja - jb) <= 1e-13 * np.abs(jb).max())
     a.close()
     b.close()
+
+
+def test_c2_full_size_vs_golden():
+    """The bench workload at FULL size (BASELINE.json configs[1]: N_uc=15, 5 % Yb, 0.5 % Tm, the
+    lattice bench.py solves): three powers of the 32-point sweep as one batch, pulse + 1000-point
+    relaxation at rtol 1e-8, against the oracle's committed trajectories
+    (`oracle/make_golden_c2.py`; LSODA needs minutes per system)."""
+    import bench
+    with np.load(os.path.join(GOLDEN, 'c2_power_sweep.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    powers = bench.powers_list()
+    idx = [int(k) for k in gold['power_idx']]
+    assert np.allclose([powers[k] for k in idx], gold['powers'], rtol=1e-15)
+    cte = bench.make_cte()
+    lat = lattice.generate(cte, seed=2000)
+    assert np.array_equal(lat.ion_type, gold['ion_type'])           # the same lattice realisation
+    system = precalculate.build_system(cte, lat, n_sys=len(idx))
+    for slot, k in enumerate(idx):
+        for exc in cte['excitations']['NIR_980']:
+            exc.power_dens = powers[k]
+        system.set_abs_blocks(*precalculate.absorption_blocks(cte), system=slot)
+    _, _, pop = system.ground_states()
+    t_pulse, t_sol = bench.t_grids(cte)
+    assert np.array_equal(t_sol, gold['t_sol'])
+    y0 = np.tile(pop.astype(float), (len(idx), 1))
+    y_p, _, st_p = system.integrate(t_pulse, y0, pulse=True, rtol=1e-8, atol=1e-15)
+    y, avg, st = system.integrate(t_sol, y_p[:, -1], pulse=False, rtol=1e-8, atol=1e-15, want_avg=True)
+    system.close()
+    assert all(s['status'] == 0 for s in st_p + st)
+    rows = gold['rows']
+    for slot in range(len(idx)):
+        assert parity_metric(y_p[slot, -1], gold['y_pulse_end'][slot]) <= 1.0
+        assert parity_metric(y[slot][rows], gold['y_rows'][slot]) <= 1.0
+        ref = gold['avg'][slot]
+        big = ref > 1e-9
+        assert np.all(np.abs(avg[slot] - ref)[big] <= 1e-4 * ref[big])

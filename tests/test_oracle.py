@@ -141,3 +141,27 @@ def test_results_helpers():
     cs = onp.cumulative_steady_state(t, y)
     from scipy.integrate import cumulative_trapezoid
     assert np.allclose(cs, cumulative_trapezoid(y, x=t, axis=0, initial=0))
+
+
+def test_c2_golden_is_self_consistent():
+    """The full-size golden trajectories of the bench workload (`oracle/make_golden_c2.py`): ion
+    populations are conserved (every operator's columns sum to zero), and the stored emission
+    curves are the ion averages of the stored state vectors (`simulations.py:100-128`)."""
+    import os
+    from tests.helpers import GOLDEN
+    with np.load(os.path.join(GOLDEN, 'c2_power_sweep.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    ion_type = gold['ion_type']
+    iS, iA, pop = onp.ground_states(ion_type, 2, 9)
+    assert gold['y_rows'].shape == (3, len(gold['rows']), len(pop))
+    for slot in range(3):
+        y = gold['y_rows'][slot]
+        for gs_list, n in ((iS, 2), (iA, 9)):
+            for gs in np.asarray(gs_list).ravel():
+                if gs != -1:
+                    assert np.allclose(y[:, gs:gs + n].sum(axis=1), 1.0, atol=1e-9)
+        avg = onp.avg_populations(y, iS, iA, 2, 9).T
+        assert np.allclose(avg, gold['avg'][slot][gold['rows']], rtol=1e-12, atol=1e-300)
+    # more power, more excitation: the Yb excited-state population right after the pulse grows
+    exc = [gold['y_pulse_end'][s][np.asarray(iS).ravel()[np.asarray(iS).ravel() != -1] + 1].mean() for s in range(3)]
+    assert exc[0] < exc[1] < exc[2]
