@@ -338,10 +338,15 @@ def run_gpu(args):
         'roofline': {'bound': 'hbm', 'kernel': 'k_integrate_cl (cluster BDF/Newton-Krylov integrator; its '
                      'inner loop is the pair-stream pass, pair rows resident in shared memory)',
                      'achieved': achieved, 'peak': peaks['hbm_gbs'],
-                     'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': None,
+                     'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': 2.2e6,
+                     'traffic_source': 'profiles/r01_ncu_integrate_cl.txt: dram read+write of one '
+                                       'launch of this batch with 40 output times (pair rows, state '
+                                       'and Krylov vectors live in shared memory; the full run adds '
+                                       'its trajectory output, 181 MB per launch)',
                      'peak_source': peak_src,
                      'algorithmic_bytes_per_launch': n_rhs * b_rhs + n_jv * b_jv,
-                     'note': 'latency-bound regime: 89,700-pair lattice (1.1 MB) is L2-resident; '
+                     'note': 'latency-bound regime: the 89,700-pair lattice (0.7 MB) is resident in the '
+                             'shared memory of its cluster, algorithmic bytes are a unit of account; '
                              'the HBM-bound numbers are in roofline_kernels'},
     }
     if not args.no_large:

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -20,21 +21,135 @@ static const int g_env_once = setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 static std::atomic<long long> g_launches{0};   // kernels launched by this library (all handles)
 
 // ---- device memory pool ----------------------------------------------------------------------
-// cudaMalloc / cudaFree synchronise the device and, on this platform, stall for tens to hundreds
-// of milliseconds every few calls.  A sweep creates and destroys one system per call, always with
-// the same buffer sizes, so freed blocks are parked per device and handed out again by size;
-// at most STB_POOL_CAP bytes stay parked (stb_release_cached_memory returns them to the driver).
+// cudaMalloc and cudaFree wait for every kernel running on the device (measured: a 256-byte
+// cudaMalloc takes 320-450 ms while an integrator kernel of another handle runs), so they have no
+// place on a path where several handles are in flight.  Two layers:
+//   * freed blocks are parked per device and size class and handed out again (a sweep creates and
+//     destroys one system per call with the same or similar buffer sizes); at most STB_POOL_CAP
+//     bytes stay parked (stb_release_cached_memory returns them to the driver);
+//   * a miss is served from an arena reserved once per device before the first kernel of the
+//     library runs (STB_ARENA_MB, default 1024 MB, at most 1/8 of the free memory): a first-fit
+//     free list with coalescing, no driver call at all;
+//   * what does not fit there goes to the stream-ordered allocator (cudaMallocAsync on a private
+//     stream, release threshold "never"; measured 1-150 ms while kernels run), else cudaMalloc.
 #include <mutex>
 #include <unordered_map>
 #define STB_POOL_CAP (8ull << 30)
-struct PoolBlock { void* p; size_t bytes; int dev; };
+#include <map>
+struct PoolBlock { void* p; size_t bytes; int dev; bool async; bool arena; };
+struct Arena {
+    char* base = nullptr;
+    size_t size = 0;
+    bool tried = false;
+    std::map<size_t, size_t> free_at;       // offset -> length of every free range
+};
 static std::mutex g_pool_mu;
 static std::vector<PoolBlock> g_pool_parked;
 static std::unordered_map<void*, PoolBlock> g_pool_live;
 static size_t g_pool_parked_bytes = 0;
+#define STB_MAX_DEV 64
+static Arena g_arena[STB_MAX_DEV];
+
+// (g_pool_mu held)  Reserve the arena of `dev` on first use.
+static void arena_init(int dev) {
+    Arena& A = g_arena[dev];
+    if (A.tried) return;
+    A.tried = true;
+    size_t want = 1024;
+    if (const char* env = getenv("STB_ARENA_MB")) want = (size_t)std::max(0, atoi(env));
+    want <<= 20;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) want = std::min(want, free_b / 8);
+    if (want < (1u << 20)) return;
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return; }
+    A.base = (char*)p;
+    A.size = want;
+    A.free_at[0] = want;
+}
+
+// (g_pool_mu held)  First fit; bytes is a multiple of 256.
+static void* arena_alloc(int dev, size_t bytes) {
+    Arena& A = g_arena[dev];
+    for (auto it = A.free_at.begin(); it != A.free_at.end(); ++it) {
+        if (it->second < bytes) continue;
+        const size_t off = it->first, len = it->second;
+        A.free_at.erase(it);
+        if (len > bytes) A.free_at[off + bytes] = len - bytes;
+        return A.base + off;
+    }
+    return nullptr;
+}
+
+// (g_pool_mu held)
+static void arena_free(int dev, void* p, size_t bytes) {
+    Arena& A = g_arena[dev];
+    size_t off = (size_t)((char*)p - A.base), len = bytes;
+    auto nxt = A.free_at.lower_bound(off);
+    if (nxt != A.free_at.begin()) {
+        auto prv = std::prev(nxt);
+        if (prv->first + prv->second == off) { off = prv->first; len += prv->second; A.free_at.erase(prv); }
+    }
+    if (nxt != A.free_at.end() && off + len == nxt->first) { len += nxt->second; A.free_at.erase(nxt); }
+    A.free_at[off] = len;
+}
+static cudaStream_t g_alloc_stream[STB_MAX_DEV] = {};
+static int g_alloc_state[STB_MAX_DEV] = {};      // 0: not probed, 1: stream-ordered allocator, -1: cudaMalloc only
+
+// stream of the stream-ordered allocator on `dev`, or null when the device / driver has none
+static cudaStream_t alloc_stream(int dev) {
+    if (dev < 0 || dev >= STB_MAX_DEV) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_alloc_state[dev] == 0) {
+        g_alloc_state[dev] = -1;
+        int ok = 0;
+        cudaMemPool_t mp;
+        if (!getenv("STB_NO_MALLOC_ASYNC") &&
+            cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess && ok &&
+            cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+            unsigned long long never = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &never);
+            if (cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking) == cudaSuccess)
+                g_alloc_state[dev] = 1;
+        }
+        cudaGetLastError();
+    }
+    return g_alloc_state[dev] == 1 ? g_alloc_stream[dev] : nullptr;
+}
+
+static cudaError_t raw_malloc(void** p, size_t bytes, int dev, bool* async) {
+    cudaStream_t st = alloc_stream(dev);
+    if (st) {
+        cudaError_t e = cudaMallocAsync(p, bytes, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) { *async = true; return e; }
+        cudaGetLastError();
+    }
+    *async = false;
+    return cudaMalloc(p, bytes);
+}
+
+static void raw_free(const PoolBlock& b) {
+    cudaStream_t st = b.async ? alloc_stream(b.dev) : nullptr;
+    if (st) {
+        cudaFreeAsync(b.p, st);
+        cudaStreamSynchronize(st);
+    } else {
+        cudaFree(b.p);
+    }
+}
 
 static cudaError_t pool_malloc(void** out, size_t bytes) {
-    bytes = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+    // size classes, 8 per octave (<= 12.5 % over-allocation): lattices of similar size - the points
+    // of a concentration sweep - then reuse each other's blocks instead of reaching cudaMalloc,
+    // which waits for the kernels of every other handle
+    bytes = std::max<size_t>(bytes, 256);
+    {
+        size_t p2 = 256;
+        while (p2 < bytes) p2 <<= 1;
+        const size_t step = std::max<size_t>(p2 >> 4, 256);      // p2/2 .. p2 in 8 steps
+        bytes = (bytes + step - 1) / step * step;
+    }
     int dev = 0;
     cudaGetDevice(&dev);
     {
@@ -42,7 +157,7 @@ static cudaError_t pool_malloc(void** out, size_t bytes) {
         int best = -1;
         for (int k = 0; k < (int)g_pool_parked.size(); ++k) {
             const PoolBlock& b = g_pool_parked[k];
-            if (b.dev != dev || b.bytes < bytes || b.bytes > bytes + bytes / 4 + 4096) continue;
+            if (b.dev != dev || b.bytes != bytes) continue;
             if (best < 0 || b.bytes < g_pool_parked[best].bytes) best = k;
         }
         if (best >= 0) {
@@ -53,9 +168,26 @@ static cudaError_t pool_malloc(void** out, size_t bytes) {
             *out = b.p;
             return cudaSuccess;
         }
+        if (dev >= 0 && dev < STB_MAX_DEV) {
+            arena_init(dev);
+            if (void* q = arena_alloc(dev, bytes)) {
+                g_pool_live[q] = PoolBlock{q, bytes, dev, false, true};
+                *out = q;
+                return cudaSuccess;
+            }
+        }
     }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, bytes);
+    static const bool verbose = getenv("STB_VERBOSE_POOL") != nullptr;
+    timespec ts0, ts1;
+    if (verbose) clock_gettime(CLOCK_MONOTONIC, &ts0);
+    bool async = false;
+    cudaError_t e = raw_malloc(&p, bytes, dev, &async);
+    if (verbose) {
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        fprintf(stderr, "[stb] pool miss: %s(%zu) took %.2f ms\n", async ? "cudaMallocAsync" : "cudaMalloc", bytes,
+                (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+    }
     if (e == cudaErrorMemoryAllocation) {
         // give parked memory back and retry once
         cudaGetLastError();
@@ -65,12 +197,12 @@ static cudaError_t pool_malloc(void** out, size_t bytes) {
             drop.swap(g_pool_parked);
             g_pool_parked_bytes = 0;
         }
-        for (auto& b : drop) cudaFree(b.p);
-        e = cudaMalloc(&p, bytes);
+        for (auto& b : drop) raw_free(b);
+        e = raw_malloc(&p, bytes, dev, &async);
     }
     if (e != cudaSuccess) return e;
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    g_pool_live[p] = PoolBlock{p, bytes, dev};
+    g_pool_live[p] = PoolBlock{p, bytes, dev, async, false};
     *out = p;
     return cudaSuccess;
 }
@@ -81,7 +213,7 @@ static cudaError_t pool_malloc(T** out, size_t bytes) { return pool_malloc((void
 // before they release anything).
 static void pool_free(void* p) {
     if (!p) return;
-    PoolBlock b{nullptr, 0, 0};
+    PoolBlock b{nullptr, 0, 0, false, false};
     std::vector<PoolBlock> drop;
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
@@ -90,6 +222,10 @@ static void pool_free(void* p) {
         else {
             PoolBlock blk = it->second;
             g_pool_live.erase(it);
+            if (blk.arena) {
+                arena_free(blk.dev, blk.p, blk.bytes);
+                return;
+            }
             g_pool_parked.push_back(blk);
             g_pool_parked_bytes += blk.bytes;
             while (g_pool_parked_bytes > STB_POOL_CAP && !g_pool_parked.empty()) {
@@ -100,7 +236,7 @@ static void pool_free(void* p) {
         }
     }
     if (b.p) cudaFree(b.p);
-    for (auto& d : drop) cudaFree(d.p);
+    for (auto& d : drop) raw_free(d);
 }
 
 extern "C" int64_t stb_release_cached_memory(void) {
@@ -111,7 +247,7 @@ extern "C" int64_t stb_release_cached_memory(void) {
         g_pool_parked_bytes = 0;
     }
     int64_t bytes = 0;
-    for (auto& b : drop) { cudaFree(b.p); bytes += (int64_t)b.bytes; }
+    for (auto& b : drop) { raw_free(b); bytes += (int64_t)b.bytes; }
     return bytes;
 }
 
@@ -220,12 +356,20 @@ extern "C" int stb_describe(char* buf, int64_t buf_len) {
     return STB_OK;
 }
 
+// Blocking copy ordered on the handle's own stream.  (cudaMemcpy uses the legacy default stream and
+// waited behind the integrator kernels of other handles.)
+static cudaError_t copy_on(cudaStream_t st, void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, st);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(st);
+}
+
 template <class T>
-static cudaError_t upload(T** dst, const std::vector<T>& v) {
+static cudaError_t upload(cudaStream_t st, T** dst, const std::vector<T>& v) {
     size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
     cudaError_t e = pool_malloc((void**)dst, bytes);
     if (e != cudaSuccess) return e;
-    if (!v.empty()) e = cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (!v.empty()) e = copy_on(st, *dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return e;
 }
 
@@ -423,12 +567,12 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     }
     if (build_tables(S, L) != STB_OK) { delete S; return nullptr; }
 
-    CKP(upload(&S->d_type, S->type));
-    CKP(upload(&S->d_local_idx, S->local_idx));
-    CKP(upload(&S->d_gs_ref, S->gs_ref));
-    CKP(upload(&S->d_plane_of_ref, S->plane_of_ref));
-    CKP(upload(&S->d_ref_of_plane, S->ref_of_plane));
-    for (int T = 0; T < 2; ++T) CKP(upload(&S->d_gs_of_local[T], S->gs_of_local[T]));
+    CKP(upload(S->stream, &S->d_type, S->type));
+    CKP(upload(S->stream, &S->d_local_idx, S->local_idx));
+    CKP(upload(S->stream, &S->d_gs_ref, S->gs_ref));
+    CKP(upload(S->stream, &S->d_plane_of_ref, S->plane_of_ref));
+    CKP(upload(S->stream, &S->d_ref_of_plane, S->ref_of_plane));
+    for (int T = 0; T < 2; ++T) CKP(upload(S->stream, &S->d_gs_of_local[T], S->gs_of_local[T]));
     L.plane_of_ref = S->d_plane_of_ref;
     L.ref_of_plane = S->d_ref_of_plane;
 
@@ -440,11 +584,11 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     double* d_geo = nullptr;
     if (dist_array) {
         CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
-        CKP(cudaMemcpy(d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+        CKP(copy_on(S->stream, d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
         G.dist = d_geo;
     } else {
         CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
-        CKP(cudaMemcpy(d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
+        CKP(copy_on(S->stream, d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
         G.pos = d_geo;
         if (cell) {
             G.periodic = 1;
@@ -532,7 +676,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             }
             int64_t lines = lp.back();
             S->h_line_ptr[T][U] = lp;
-            CKP(upload(&S->d_line_ptr[T][U], lp));
+            CKP(upload(S->stream, &S->d_line_ptr[T][U], lp));
             size_t slots = std::max<int64_t>(lines * 32, 1);
             CKP(pool_malloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
             CKP(cudaMemsetAsync(S->d_col[T][U], 0, slots * sizeof(uint32_t), S->stream));
@@ -576,7 +720,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     pool_free(d_geo);
     L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
     CKP(pool_malloc((void**)&S->dL, sizeof(DevLattice)));
-    CKP(cudaMemcpy(S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
+    CKP(copy_on(S->stream, S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
     if (stb_set_batch(S, 1) != STB_OK) { stb_system_destroy(S); return nullptr; }
     return S;
 }
@@ -710,8 +854,8 @@ extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint
     memset(&EA, 0, sizeof(EA));
     int64_t* d_off = nullptr;
     stb_process* d_pr = nullptr;
-    CK(upload(&d_off, off));
-    CK(upload(&d_pr, pr));
+    CK(upload(S->stream, &d_off, off));
+    CK(upload(S->stream, &d_pr, pr));
     EA.L = S->dL;
     EA.type = S->d_type;
     EA.local_idx = S->d_local_idx;
@@ -1141,8 +1285,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     }
     CKC(cudaEventRecord(e1, S->stream));
     S->last_launches = dev ? 1 : 2;
+    double* avg_p = avg_out;
     if (avg_out) {
-        double* avg_p = avg_out;
         if (!dev) {
             WSC(WS_AVG, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]));
             avg_p = d_avg;
@@ -1151,6 +1295,12 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
         CKC(cudaGetLastError());
         S->last_launches += 1;
+    }
+    // Wait for the kernels HERE: a device-to-host copy into pageable memory issued behind a running
+    // kernel blocks inside the driver with the context lock held, and the launches of every other
+    // handle (other host threads) then wait for this solve to finish.
+    CKC(cudaStreamSynchronize(S->stream));
+    if (avg_out) {
         if (!dev)
             CKC(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
                                 cudaMemcpyDeviceToHost, S->stream));
@@ -1162,7 +1312,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
     if (getenv("STB_VERBOSE")) {
         long long pr[24];
-        CKC(cudaMemcpy(pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
+        CKC(copy_on(S->stream, pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
         static const char* names[16] = {"stream", "stream_sync", "combine", "yk_barrier", "rhs_epilogue",
                                         "block_inv", "residual", "beta_reduce", "arnoldi_epi", "dots",
                                         "dots_reduce", "orth_push", "v_barrier", "newton_tail", "step_ctl",
@@ -1323,8 +1473,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     CKI(cudaLaunchCooperativeKernel((void*)k_integrate, dim3(grid), dim3(STB_NT), kargs, dyn_bytes, S->stream));
     CKI(cudaEventRecord(e1, S->stream));
     S->last_launches = dev ? 1 : 2;
+    double* avg_p = avg_out;
     if (avg_out) {
-        double* avg_p = avg_out;
         if (!dev) {
             WSI(WS_AVG, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]));
             avg_p = d_avg;
@@ -1333,6 +1483,9 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
         CKI(cudaGetLastError());
         S->last_launches += 1;
+    }
+    CKI(cudaStreamSynchronize(S->stream));     // before any pageable device-to-host copy, see integrate_cluster
+    if (avg_out) {
         if (!dev)
             CKI(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
                                 cudaMemcpyDeviceToHost, S->stream));

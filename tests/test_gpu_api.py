@@ -174,3 +174,47 @@ def test_objective_batch_equals_sequential_objective(tmp_path, monkeypatch):
     for cand, err in zip(cands, errors):
         seq = optimize.optim_fun(sim.simulate_dynamics, cand, sim)
         assert np.allclose(seq, err, rtol=1e-9, atol=1e-12)
+
+
+def test_concurrent_handles_match_sequential():
+    """Independent lattices solved from several host threads at once (what
+    `simulate_concentration_dependence` does with `streams_per_device`) give bit-identical
+    results to solving them one after the other: handles share nothing but the memory pool."""
+    import threading
+    from simetuc_b200.engine import RateSystem
+
+    cte = configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=2.0, power_dens=1e8, t_pulse=1e-8)
+    t = np.logspace(-8, -4, 30)
+
+    def solve(seed):
+        lat = lattice.generate(cte, seed=seed)
+        system = RateSystem(lat, cte['energy_transfer'], device=0)
+        try:
+            system.set_batch(1)
+            system.set_decay_blocks(*precalculate.decay_blocks(cte))
+            system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+            system.set_strengths([p.strength for p in cte['energy_transfer'].values() if len(p.type) == 2])
+            _, _, pop = system.ground_states()
+            y, _, st = system.integrate(t, pop.astype(float)[None, :], pulse=True, rtol=1e-8, atol=1e-15)
+            assert st[0]['status'] == 0
+            return y[0]
+        finally:
+            system.close()
+
+    seeds = list(range(7000, 7006))
+    sequential = [solve(s) for s in seeds]
+    parallel = [None] * len(seeds)
+    errors = []
+
+    def worker(k):
+        try:
+            parallel[k] = solve(seeds[k])
+        except BaseException as err:      # pylint: disable=broad-except
+            errors.append(err)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(len(seeds))]
+    [th.start() for th in threads]
+    [th.join() for th in threads]
+    assert not errors, errors
+    for a, b in zip(sequential, parallel):
+        assert np.array_equal(a, b)

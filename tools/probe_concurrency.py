@@ -55,14 +55,22 @@ def build_and_solve(k, out):
     sysk.set_abs_blocks(*precalculate.absorption_blocks(cte))
     sysk.set_strengths([p.strength for p in cte['energy_transfer'].values() if len(p.type) == 2])
     t1 = time.perf_counter()
+    if BARRIER is not None:
+        BARRIER.wait()
+    t1b = time.perf_counter()
     tmp = [None] * n
     solve(sysk, tmp, k)
     t2 = time.perf_counter()
+    if BARRIER is not None:
+        BARRIER.wait()
+    t2b = time.perf_counter()
     sysk.close()
-    out[k] = (round(1e3 * (t1 - t0)), round(1e3 * (t2 - t1)), round(1e3 * (time.perf_counter() - t2)))
+    out[k] = (round(1e3 * (t1 - t0)), round(1e3 * (t2 - t1b)), round(tmp[k][1]), round(1e3 * (time.perf_counter() - t2b)))
 
 
-for label, par in (('sequential', False), ('threads', True)):
+BARRIER = None
+for label, par in (('sequential', False), ('threads', True), ('threads, phases separated by barriers', True)):
+    BARRIER = threading.Barrier(n) if 'barriers' in label else None
     t0 = time.perf_counter()
     if par:
         ths = [threading.Thread(target=build_and_solve, args=(k, out)) for k in range(n)]
@@ -71,4 +79,4 @@ for label, par in (('sequential', False), ('threads', True)):
     else:
         for k in range(n):
             build_and_solve(k, out)
-    print('build+solve+close %s: %.3f s total; (build, solve, close) ms: %s' % (label, time.perf_counter() - t0, out))
+    print('build+solve+close %s: %.3f s total; (build, solve wall, relax kernel, close) ms: %s' % (label, time.perf_counter() - t0, out))
