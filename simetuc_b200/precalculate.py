@@ -9,6 +9,7 @@ The per-ion-type absorption and decay blocks (`precalculate.py:79-230`) are tiny
 returns are materialised from the device export for API compatibility and carry a reference to
 the device-resident `RateSystem`, which `odesolver.solve_pulse / solve_relax` use directly.
 """
+import copy
 import logging
 import os
 import time
@@ -145,27 +146,97 @@ def build_system(cte, lat: Lattice, device: int = 0, d_max: Optional[float] = No
     return system
 
 
+def jac_indices_of(N_indices) -> np.ndarray:
+    """`[2M,3]` rows `(r, N_i[r], N_j[r])`, `(r, N_j[r], N_i[r])` interleaved
+    (`precalculate.py:603-623`)."""
+    N_indices = np.asarray(N_indices, dtype=np.uint32).reshape(-1, 2)
+    M = N_indices.shape[0]
+    out = np.empty((2 * M, 3), dtype=np.uint32)
+    out[:, 0] = np.repeat(np.arange(M, dtype=np.uint32), 2)
+    out[0::2, 1], out[0::2, 2] = N_indices[:, 0], N_indices[:, 1]
+    out[1::2, 1], out[1::2, 2] = N_indices[:, 1], N_indices[:, 0]
+    return out
+
+
+def average_lattice(cte) -> Lattice:
+    """Lattice of the AVERAGE rate equations (`precalculate.py:911-977`): one sensitizer and/or one
+    activator ion with every distance, the ion's distance to itself included, equal to 1 A - so an
+    ion also "interacts with itself", which is how the average equations express A-A and S-S
+    processes.  Same checks and errors as the reference (`:930-958`)."""
+    lat = cte['lattice']
+    S_conc, A_conc = float(lat['S_conc']), float(lat['A_conc'])
+    n_S, n_A = int(S_conc != 0), int(A_conc != 0)
+    if n_S + n_A == 0:
+        raise LatticeError('No ions generated, the concentrations are too small!')
+    if lat['N_uc'] <= 0:
+        raise LatticeError('Wrong number of unit cells: {}. It must be a positive integer.'.format(lat['N_uc']))
+    if not ((0.0 <= S_conc <= 100.0) and (0.0 <= A_conc <= 100.0) and (0 <= S_conc + A_conc <= 100.0)):
+        raise LatticeError('Wrong ion concentrations: {:.2f}% Sensitizer, {:.2f}% Activator. '
+                           'Their sum must be between 0% and 100%.'.format(S_conc, A_conc))
+    sS, sA = cte['states']['sensitizer_states'], cte['states']['activator_states']
+    if (S_conc != 0 and sS == 0) or (A_conc != 0 and sA == 0):
+        raise LatticeError('The number of states of each ion cannot be zero.')
+    ion_type = [0] * n_S + [1] * n_A
+    n = len(ion_type)
+    return Lattice.from_arrays(ion_type, np.ones((n, n)), sS, sA)
+
+
+def average_processes(cte):
+    """Energy-transfer processes with `strength = strength_avg` where one is given
+    (`precalculate.py:999-1003`); the caller's processes are left untouched (the reference
+    overwrites them in place through a shallow dict copy)."""
+    out = type(cte['energy_transfer'])()
+    for name, p in cte['energy_transfer'].items():
+        q = copy.copy(p)
+        q.strength = p.strength_avg
+        out[name] = q
+    return out
+
+
+def average_view(cte):
+    """Shallow copy of `cte` whose pair processes carry their average strengths."""
+    view = copy.copy(cte)
+    view['energy_transfer'] = average_processes(cte)
+    return view
+
+
+def setup_average_eqs(cte, gen_lattice: bool = False, full_path: Optional[str] = None,
+                      device: int = 0):
+    """Average rate equations (`precalculate.py:884-1051`): the same 12-tuple as
+    `setup_microscopic_eqs` for the two-ion average lattice; interaction columns that cancel
+    identically (energy migration of an ion with itself) are removed from the exported operands
+    as the reference does (`:1013-1021`)."""
+    lat = average_lattice(cte)
+    out = _setup_eqs(cte, lat, device, average_processes(cte), drop_empty=True)
+    logging.getLogger(__name__).info('Number of interactions: %d.', out[7].shape[0])
+    return out
+
+
 def setup_microscopic_eqs(cte, gen_lattice: bool = False, full_path: Optional[str] = None,
                           device: int = 0):
     """Same contract as the reference (`precalculate.py:713-878`): returns
     `(cte, initial_population, index_S_i, index_A_j, total_abs_matrix, decay_matrix, ET_matrix,
     N_indices, jac_indices, coop_ET_matrix, coop_N_indices, coop_jac_indices)`.
     The matrices carry `.stb = (RateSystem, system_index)`."""
+    lat = get_lattice(cte, gen_lattice=gen_lattice, full_path=full_path)
+    return _setup_eqs(cte, lat, device, cte['energy_transfer'], drop_empty=False)
+
+
+def _setup_eqs(cte, lat, device, processes, drop_empty):
     logger = logging.getLogger(__name__)
     start = time.time()
-    lat = get_lattice(cte, gen_lattice=gen_lattice, full_path=full_path)
     cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
     cte['states']['energy_states'] = lat.n_states
-    for name, p in cte['energy_transfer'].items():
+    for name, p in processes.items():
         if len(p.type) == 3 and not np.isclose(p.strength, 0.0):
             raise NotImplementedError('cooperative (three-ion) energy transfer process %s: '
                                       'not yet on the device path' % name)
-    key = (id(lat), tuple((n, p.indices, p.mult) for n, p in cte['energy_transfer'].items()
-                          if len(p.type) == 2), device)
+    key = (id(lat), tuple((n, p.indices, p.mult, bool(np.isclose(p.strength, 0.0)))
+                          for n, p in processes.items() if len(p.type) == 2), device)
     system = _SYSTEM_CACHE.get(key)
     if system is None or system.handle is None:
         check_process_states(cte)
-        system = RateSystem(lat, cte['energy_transfer'], device=device)
+        system = RateSystem(lat, processes, device=device)
         _SYSTEM_CACHE.clear()          # one resident lattice per process is enough here
         _SYSTEM_CACHE[key] = system
     check_process_states(cte)
@@ -174,12 +245,19 @@ def setup_microscopic_eqs(cte, gen_lattice: bool = False, full_path: Optional[st
     aS, aA = absorption_blocks(cte)
     system.set_decay_blocks(dS, dA)
     system.set_abs_blocks(aS, aA)
-    system.set_strengths([p.strength for n, p in cte['energy_transfer'].items() if len(p.type) == 2]
+    system.set_strengths([p.strength for n, p in processes.items() if len(p.type) == 2]
                          or np.zeros(0))
     index_S_i, index_A_j, initial_population = system.ground_states()
     total_abs_matrix = _block_diag(aS, aA, index_S_i, index_A_j)
     decay_matrix = _block_diag(dS, dA, index_S_i, index_A_j)
     ET_matrix, N_indices, jac_indices = system.ET_matrix(0)
+    if drop_empty and N_indices.shape[0]:
+        dense = ET_matrix.toarray()
+        keep = np.array([not np.allclose(dense[:, k], 0) for k in range(dense.shape[1])])
+        if not keep.all():
+            ET_matrix = sp.csr_matrix(dense[:, keep])
+            N_indices = N_indices[keep]
+            jac_indices = jac_indices_of(N_indices)
     N = system.N
     coop_ET_matrix = sp.csr_matrix((N, 0), dtype=np.float64)
     coop_N_indices = np.zeros((0, 3), dtype=np.uint32)

@@ -369,7 +369,7 @@ class Simulations:
     `devices`: CUDA device ordinals to spread independent systems over (default: device 0).'''
 
     def __init__(self, cte, full_path: str = None, devices: Optional[Sequence[int]] = None,
-                 streams_per_device: int = 8) -> None:
+                 streams_per_device: int = 16) -> None:
         self.cte = cte
         self.full_path = full_path
         #: independent lattices (concentration points) solved concurrently on one device
@@ -410,15 +410,15 @@ class Simulations:
 
     # ------------------------------------------------------------------ single systems
     def simulate_dynamics(self, average: bool = False) -> DynamicsSolution:
-        '''Pulse then relaxation on 1000 log-spaced points (`simulations.py:1096-1176`).'''
-        if average:
-            raise NotImplementedError('average rate equations are outside the device path')
+        '''Pulse then relaxation on 1000 log-spaced points (`simulations.py:1096-1176`);
+        `average=True`: the average rate equations (`:1114-1119`).'''
         logger = logging.getLogger(__name__ + '.dynamics')
         start_time = time.time()
         gen_lattice = self.cte.get('gen_lattice', False)
+        setup_func = precalculate.setup_average_eqs if average else precalculate.setup_microscopic_eqs
         (cte_updated, initial_population, index_S_i, index_A_j, total_abs_matrix, decay_matrix,
          ET_matrix, N_indices, jac_indices, coop_ET_matrix, coop_N_indices,
-         coop_jac_indices) = precalculate.setup_microscopic_eqs(
+         coop_jac_indices) = setup_func(
              self.cte, full_path=self.full_path, gen_lattice=gen_lattice, device=self.devices[0])
         self.cte = cte_updated
         tf = self._get_t_simulation()
@@ -451,12 +451,11 @@ class Simulations:
 
     def simulate_CW_steady_state(self, average: bool = False) -> SteadyStateSolution:
         '''`linspace(0, 15 tau_max, N_steps)` under constant excitation (`simulations.py:1195-1257`).'''
-        if average:
-            raise NotImplementedError('average rate equations are outside the device path')
         start_time = time.time()
+        setup_func = precalculate.setup_average_eqs if average else precalculate.setup_microscopic_eqs
         (cte_updated, initial_population, index_S_i, index_A_j, total_abs_matrix, decay_matrix,
          ET_matrix, N_indices, jac_indices, coop_ET_matrix, coop_N_indices,
-         coop_jac_indices) = precalculate.setup_microscopic_eqs(
+         coop_jac_indices) = setup_func(
              self.cte, full_path=self.full_path, device=self.devices[0])
         self.cte = cte_updated
         tf = self._get_t_simulation()
@@ -480,10 +479,13 @@ class Simulations:
 
     # ------------------------------------------------------------------ batched sweeps
     def _solve_batch(self, lat, ctes: List[Any], device: int, dynamics: bool,
-                     strengths: Optional[np.ndarray] = None, keep_y: bool = True):
+                     strengths: Optional[np.ndarray] = None, keep_y: bool = True,
+                     average: bool = False):
         """Integrate `len(ctes)` systems that share `lat` in one batch on `device`.
         Each cte supplies its own absorption / decay blocks (and optionally ET strengths).
         Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics."""
+        if average:       # same systems, processes at their average strengths (`precalculate.py:999-1003`)
+            ctes = [precalculate.average_view(cte) for cte in ctes]
         cte0 = ctes[0]
         n = len(ctes)
         system = precalculate.build_system(cte0, lat, device=device, n_sys=n)
@@ -521,14 +523,17 @@ class Simulations:
             system.close()
 
     def _sweep_same_lattice(self, ctes: List[Any], dynamics: bool, keep_y: bool = True,
-                            strengths: Optional[np.ndarray] = None):
+                            strengths: Optional[np.ndarray] = None, average: bool = False):
         """Systems sharing one lattice, dealt round-robin over `self.devices`."""
         gen_lattice = self.cte.get('gen_lattice', False)
-        lat = precalculate.get_lattice(self.cte, gen_lattice=gen_lattice, full_path=self.full_path)
+        if average:
+            lat = precalculate.average_lattice(self.cte)
+        else:
+            lat = precalculate.get_lattice(self.cte, gen_lattice=gen_lattice, full_path=self.full_path)
         n_dev = min(len(self.devices), len(ctes))
         shards = [list(range(d, len(ctes), n_dev)) for d in range(n_dev)]
         jobs = [(lambda d=d, ids=ids: self._solve_batch(
-            lat, [ctes[i] for i in ids], self.devices[d], dynamics, keep_y=keep_y,
+            lat, [ctes[i] for i in ids], self.devices[d], dynamics, keep_y=keep_y, average=average,
             strengths=None if strengths is None else strengths[ids])) for d, ids in enumerate(shards)]
         results = _run_on_devices(jobs, n_dev)
         out = [None] * len(ctes)
@@ -545,8 +550,6 @@ class Simulations:
         '''Steady state at every power density (`simulations.py:1277-1316`).  All powers share
         the lattice, the decay blocks and the pair stream; only the absorption block differs
         (`precalculate.py:99,112,120`), so they are integrated as one batch per device.'''
-        if average:
-            raise NotImplementedError('average rate equations are outside the device path')
         logger = logging.getLogger(__name__ + '.pow_dep')
         start_time = time.time()
         power_dens_list = [float(elem) for elem in list(power_dens_list)]
@@ -563,7 +566,8 @@ class Simulations:
                     exc.power_dens = power_dens
             light.append(cte)
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-            pending = pool.submit(self._sweep_same_lattice, light, dynamics=pulsed, keep_y=keep_y)
+            pending = pool.submit(self._sweep_same_lattice, light, dynamics=pulsed, keep_y=keep_y,
+                                  average=average)
             ctes = []
             for power_dens in power_dens_list:
                 cte = copy.deepcopy(self.cte)
@@ -577,17 +581,19 @@ class Simulations:
             cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
             cte['states']['energy_states'] = lat.n_states
             if pulsed and y_sol is not None:
-                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte).calculate_steady_state()
+                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
+                                       average=average).calculate_steady_state()
             elif pulsed:
                 # keep_y=False: the ion average commutes with the time integral, so the area
                 # under the device-computed emission curves gives the same steady state without
                 # moving the [n_t, N] trajectory to the host
                 avg_steady = cumulative_trapezoid(avg, t_sol)
-                sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, own_cte=True)
+                sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, average=average,
+                                          own_cte=True)
                 sol.set_avg_data(avg_steady)
             else:
                 sol = SteadyStateSolution(t_sol, y_sol if y_sol is not None else avg,
-                                          index_S_i, index_A_j, cte, own_cte=True)
+                                          index_S_i, index_A_j, cte, average=average, own_cte=True)
                 sol.set_avg_data(avg)
             sol.solver_stats = st
             solutions.append(sol)
@@ -606,8 +612,6 @@ class Simulations:
                                           average: bool = False) -> ConcentrationDependenceSolution:
         '''One lattice per (S_conc, A_conc) point (`simulations.py:1318-1385`); the points are
         independent and are dealt round-robin over the devices.'''
-        if average:
-            raise NotImplementedError('average rate equations are outside the device path')
         start_time = time.time()
         concentrations = [(float(a), float(b)) for a, b in list(concentrations)]
         if N_uc_list is None:
@@ -622,19 +626,23 @@ class Simulations:
             cte['lattice']['N_uc'] = N_uc_list[k]
             cte['lattice']['S_conc'], cte['lattice']['A_conc'] = concentrations[k]
             sim = Simulations(cte, devices=[device])
-            lat = precalculate.get_lattice(cte, gen_lattice=cte.get('gen_lattice', False))
+            if average:
+                lat = precalculate.average_lattice(cte)
+            else:
+                lat = precalculate.get_lattice(cte, gen_lattice=cte.get('gen_lattice', False))
             sols, index_S_i, index_A_j, st = sim._solve_batch(lat, [cte], device,
-                                                              dynamics or pulsed)
+                                                              dynamics or pulsed, average=average)
             cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
             cte['states']['energy_states'] = lat.n_states
             t_sol, y_sol, avg = sols[0]
             if dynamics:
-                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte)
+                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte, average=average)
                 sol.set_avg_data(avg)
             elif pulsed:
-                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte).calculate_steady_state()
+                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
+                                       average=average).calculate_steady_state()
             else:
-                sol = SteadyStateSolution(t_sol, y_sol, index_S_i, index_A_j, cte)
+                sol = SteadyStateSolution(t_sol, y_sol, index_S_i, index_A_j, cte, average=average)
                 sol.set_avg_data(avg)
             return sol
 

@@ -218,3 +218,51 @@ def test_concurrent_handles_match_sequential():
     assert not errors, errors
     for a, b in zip(sequential, parallel):
         assert np.array_equal(a, b)
+
+
+def _oracle_average(cte):
+    """Oracle operands of the average equations: the two-ion all-ones lattice with the processes at
+    their average strengths, interaction columns that cancel identically removed
+    (`precalculate.py:971-1021`)."""
+    avg_cte = precalculate.average_view(cte)
+    n_S, n_A = int(float(cte['lattice']['S_conc']) != 0), int(float(cte['lattice']['A_conc']) != 0)
+    ion_type = np.array([0] * n_S + [1] * n_A)
+    g = {'ion_type': ion_type, 'dist_array': np.ones((len(ion_type),) * 2),
+         'info': np.array([cte['states']['sensitizer_states'], cte['states']['activator_states']])}
+    op = oracle_operands(g, avg_cte)
+    dense = op['ET'].toarray()
+    keep = np.array([not np.allclose(dense[:, k], 0) for k in range(dense.shape[1])], dtype=bool)
+    return op, dense[:, keep], op['N_indices'][keep]
+
+
+def test_average_rate_equations_match_oracle():
+    """`average=True` (`simulations.py:1114-1119`, `precalculate.py:884-1051`): operands equal to
+    the oracle's, dynamics within the trajectory tolerance of scipy LSODA on the same equations."""
+    cte = configs.yb_tm_cte(N_uc=8, S_conc=10.0, A_conc=1.0, power_dens=1e8, t_pulse=1e-8,
+                            rtol=1e-8, atol=1e-15, N_steps=300)
+    for k, p in enumerate(cte['energy_transfer'].values()):
+        p._strength_avg = p.strength * (0.5 + 0.1 * k) * 1e-3      # average strengths differ from microscopic ones
+    op, ET_ref, N_ref = _oracle_average(cte)
+    out = precalculate.setup_average_eqs(cte)
+    (_, pop, iS, iA, abs_m, dec_m, ET, N_idx, jac_idx, cM, cN, cJ) = out
+    assert np.array_equal(pop, op['initial_population']) and list(iS) == list(np.ravel(op['index_S_i']))
+    assert np.array_equal(N_idx, N_ref) and np.array_equal(jac_idx, onp.jac_indices(N_ref))
+    assert np.allclose(ET.toarray(), ET_ref, rtol=1e-14, atol=0)
+    assert np.allclose(abs_m.toarray(), op['abs'].toarray(), rtol=1e-15, atol=0)
+    assert np.allclose(dec_m.toarray(), op['decay'].toarray(), rtol=1e-15, atol=0)
+    assert cM.shape == (11, 0) and cN.shape == (0, 3) and cJ.shape == (0, 4)
+
+    sim = Simulations(cte)
+    sol = sim.simulate_dynamics(average=True)
+    assert sol.average and sol.y_sol.shape == (300, 11)
+    t_pulse, t_sol = onp.time_grids(1e-8, onp.t_simulation(cte['decay']), 300)
+    kw = dict(rtol=1e-8, atol=1e-15, nsteps=100000)
+    yp = onp.solve_pulse(t_pulse, op['initial_population'].astype(float), op['abs'], op['decay'],
+                         op['ET'], op['N_indices'], op['jac_indices'], **kw)
+    y_ref = onp.solve_relax(t_sol, yp[-1], op['decay'], op['ET'], op['N_indices'], op['jac_indices'], **kw)
+    err = np.abs(sol.y_sol - y_ref) / (1e-4 * np.abs(y_ref) + 1e-12)
+    assert err.max() <= 1.0
+    # sweeps accept the flag too and agree with single runs
+    pd = sim.simulate_power_dependence([1e6, 1e8], average=True)
+    single = Simulations(cte).simulate_steady_state(average=True)
+    assert np.allclose(pd[1].steady_state_populations, single.steady_state_populations, rtol=1e-9)

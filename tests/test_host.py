@@ -178,3 +178,36 @@ def test_two_process_gather_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert 'GATHER_OK' in res.stdout
+
+
+def test_average_lattice_and_processes():
+    """Average rate equations (`precalculate.py:884-1051`): a two-ion lattice whose distances,
+    self-distances included, are all 1; processes at `strength_avg` without touching the caller's."""
+    from simetuc_b200 import precalculate
+    from simetuc_b200.util import LatticeError
+    cte = configs.yb_tm_cte(N_uc=8, S_conc=10.0, A_conc=1.0)
+    lat = precalculate.average_lattice(cte)
+    assert (lat.n_ions, lat.n_S, lat.n_A, lat.n_states) == (2, 1, 1, 11)
+    assert np.array_equal(lat.dist_array, np.ones((2, 2)))
+    cte['lattice']['S_conc'] = 0.0
+    lat = precalculate.average_lattice(cte)
+    assert (lat.n_ions, lat.n_S, lat.n_A) == (1, 0, 1)
+    cte['lattice']['A_conc'] = 0.0
+    with pytest.raises(LatticeError):
+        precalculate.average_lattice(cte)
+    cte['lattice']['A_conc'] = 120.0
+    with pytest.raises(LatticeError):
+        precalculate.average_lattice(cte)
+    cte = configs.yb_tm_cte(N_uc=8, S_conc=10.0, A_conc=1.0)
+    first = next(iter(cte['energy_transfer'].values()))
+    strength = first.strength
+    first._strength_avg = 42.0
+    avg = precalculate.average_processes(cte)
+    assert next(iter(avg.values())).strength == 42.0
+    assert first.strength == strength and list(avg) == list(cte['energy_transfer'])
+    # the oracle's interaction lists on the all-ones distance matrix contain the ion itself
+    iS, iA, pop = onp.ground_states(np.array([0, 1]), 2, 9)
+    lists = onp.interaction_lists(np.array([0, 1]), np.ones((2, 2)), iS, iA, 2, 9)
+    assert [list(r) for r in lists[0]] == [[0]] and [list(r) for r in lists[3]] == [[2]]
+    assert np.array_equal(precalculate.jac_indices_of(np.array([[1, 5], [3, 7]], np.uint32)),
+                          onp.jac_indices(np.array([[1, 5], [3, 7]], np.uint32)))

@@ -16,7 +16,7 @@ for seed in range(n_seeds):
             concs.append((S, A))
             n_uc.append(nuc)
 out = {'points': len(concs)}
-for streams in (1, 8):
+for streams in (1, 8, 16):
     cte = configs.yb_tm_cte(N_uc=15, S_conc=25.0, A_conc=0.3, power_dens=1e7, t_pulse=1e-8,
                             rtol=1e-8, atol=1e-15, N_steps=1000)
     cte['lattice_seed'] = 3000
