@@ -25,6 +25,9 @@
 #define CL_RG 8            // rows per row group
 #define CL_MAXRG 256       // row groups per CTA
 #define CL_MAXG 8
+#ifndef CL_PIECE_FIX
+#define CL_PIECE_FIX 6     // fixed cost of a pair-pass piece, in steps
+#endif
 
 struct ClLayout {          // offsets in doubles into dynamic shared memory
     int NZ;                // gathered vector, padded planes
@@ -387,7 +390,11 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 gres_on[T][U] = Y.gres_off[T][U] >= 0 && used && cnt[T] > 0;
             }
             ST[T] = stp[T][0] + stp[T][1];
-            WT[T] = stp[T][0] * cst[T][0] + stp[T][1] * cst[T][1];
+            // every piece also pays a fixed price (addresses, cross-lane reduction, store): CL_PIECE_FIX
+            // pseudo-steps in front of each segment keep warps with three short pieces from
+            // finishing long after warps with one long piece
+            WT[T] = (stp[T][0] ? (stp[T][0] + CL_PIECE_FIX) * cst[T][0] : 0) +
+                    (stp[T][1] ? (stp[T][1] + CL_PIECE_FIX) * cst[T][1] : 0);
             Wt[T] = cl_pow2ceil(max(L.s[T], 1));
         }
         const double KAPPA[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
@@ -473,8 +480,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 x -= (int64_t)gi * WT[1];
                 g = nrg[0] + gi;
             }
-            const int64_t c0 = (int64_t)stp[T][0] * cst[T][0];
-            t = x < c0 ? (int)(x / cst[T][0]) : stp[T][0] + (int)((x - c0) / cst[T][1]);
+            const int64_t c0 = stp[T][0] ? (int64_t)(stp[T][0] + CL_PIECE_FIX) * cst[T][0] : 0;
+            if (x < c0) t = max(0, (int)(x / cst[T][0]) - CL_PIECE_FIX);
+            else t = stp[T][0] + (stp[T][1] ? min(stp[T][1], max(0, (int)((x - c0) / cst[T][1]) - CL_PIECE_FIX)) : 0);
         }
         S.wb_g[tid] = g;
         S.wb_t[tid] = t;

@@ -140,6 +140,71 @@ __global__ void __cluster_dims__(4, 1, 1) k_cluster(long long* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
 }
 
+// L2 -> SM streaming: 8 CTAs of 512 threads read a 13 MB dense block, (a) as the cluster integrator
+// does (a warp = 8 rows x 4 lanes x 16 B, rows `pitch` apart), (b) fully coalesced (512 B per warp
+// request); DEPTH independent loads per lane are issued before the first use.
+__device__ __forceinline__ double2 ld_nc2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+template <int DEPTH, bool ROWS>
+__global__ void k_stream(const double* g, int n_rows, int pitch, double* sink, long long* cyc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows_per_cta = n_rows / gridDim.x;
+    double acc = 0.0;
+    long long t0 = clock64();
+    if (ROWS) {
+        const int rr = lane & 7, kk = lane >> 3;
+        const int nst = pitch / 8;                       // steps of 8 doubles along a row
+        // (row group, step) work split evenly over the warps like the integrator does
+        const int n_groups = rows_per_cta / 8;
+        const long long total = (long long)n_groups * nst;
+        long long w0 = total * warp / 16, w1 = total * (warp + 1) / 16;
+        while (w0 < w1) {
+            const int grp = (int)(w0 / nst), s0 = (int)(w0 % nst);
+            const int s1 = (int)min((long long)nst, s0 + (w1 - w0));
+            const double* gr = g + ((size_t)(blockIdx.x * rows_per_cta + grp * 8 + rr)) * pitch + 2 * kk;
+            int st = s0;
+            for (; st + DEPTH <= s1; st += DEPTH) {
+                double2 v[DEPTH];
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) v[u] = ld_nc2(gr + 8 * (st + u));
+#pragma unroll
+                for (int u = 0; u < DEPTH; ++u) acc += v[u].x + v[u].y;
+            }
+            for (; st < s1; ++st) { double2 v = ld_nc2(gr + 8 * st); acc += v.x + v.y; }
+            w0 += s1 - s0;
+        }
+    } else {
+        const size_t per_cta = (size_t)rows_per_cta * pitch;
+        const double* base = g + blockIdx.x * per_cta;
+        const size_t per_warp = per_cta / 16;
+        const double* p = base + warp * per_warp + 2 * lane;
+        const size_t n_it = per_warp / 64;               // 64 doubles = 512 B per warp request
+        size_t it = 0;
+        for (; it + DEPTH <= n_it; it += DEPTH) {
+            double2 v[DEPTH];
+#pragma unroll
+            for (int u = 0; u < DEPTH; ++u) v[u] = ld_nc2(p + 64 * (it + u));
+#pragma unroll
+            for (int u = 0; u < DEPTH; ++u) acc += v[u].x + v[u].y;
+        }
+    }
+    long long t1 = clock64();
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
+}
+
+template <int DEPTH, bool ROWS>
+static void run_stream(const double* g, int n_rows, int pitch, double* sink, long long* d_out, const char* name) {
+    for (int rep = 0; rep < 3; ++rep) k_stream<DEPTH, ROWS><<<8, 512>>>(g, n_rows, pitch, sink, d_out);
+    long long c;
+    cudaMemcpy(&c, d_out, sizeof(c), cudaMemcpyDeviceToHost);
+    const double bytes = (double)n_rows * pitch * 8 / 8;       // per CTA
+    printf("L2 stream %-34s depth %2d: %8.0f cycles per pass, %5.1f B/clk/SM\n", name, DEPTH, (double)c, bytes / c);
+}
+
 int main() {
     long long* d_out;
     double* d_sink;
@@ -159,6 +224,20 @@ int main() {
         printf("--- %d threads per CTA\n", threads);
         for (int k = 0; k < 11; ++k) printf("%-45s %8.1f cycles\n", names[k], h[k] / div[k]);
         printf("Gauss-Jordan 9x9 IEEE, calls 1..3: %lld %lld %lld cycles\n", h[11], h[12], h[13]);
+    }
+    {
+        const int n_rows = 1280, pitch = 1280;          // 13.1 MB of doubles: L2-resident
+        double* g;
+        double* sink2;
+        cudaMalloc(&g, sizeof(double) * (size_t)n_rows * pitch);
+        cudaMalloc(&sink2, sizeof(double) * 8 * 512);
+        cudaMemset(g, 0, sizeof(double) * (size_t)n_rows * pitch);
+        run_stream<1, true>(g, n_rows, pitch, sink2, d_out, "8 rows x 64 B per warp request");
+        run_stream<4, true>(g, n_rows, pitch, sink2, d_out, "8 rows x 64 B per warp request");
+        run_stream<16, true>(g, n_rows, pitch, sink2, d_out, "8 rows x 64 B per warp request");
+        run_stream<1, false>(g, n_rows, pitch, sink2, d_out, "512 B contiguous per warp request");
+        run_stream<4, false>(g, n_rows, pitch, sink2, d_out, "512 B contiguous per warp request");
+        run_stream<16, false>(g, n_rows, pitch, sink2, d_out, "512 B contiguous per warp request");
     }
     k_cluster<<<4, 512>>>(d_out);
     long long h0;
