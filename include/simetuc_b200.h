@@ -173,6 +173,23 @@ int stb_integrate_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, 
 /* The CUDA stream (cudaStream_t) every kernel of this system is launched on, so that callers can
  * record their own events on it; and the number of kernels launched by the library so far. */
 void* stb_stream(const stb_system* sys);
+/* Cooperative (three-ion, S-S-A) energy transfer: precalculate._create_coop_ET_matrices
+ * (precalculate.py:427-599) and _calculate_coop_jac_matrices (:626-699), the third term of
+ * odesolver._rate_eq (:40-41) and of _jac_rate_eq (:56-60).
+ * Geometry as in stb_system_create (the same lattice); idx6 = (ii, ki, li, if, kf, lf), the initial
+ * states of the three transitions then the final ones (util.py:247-248); d_max_coop <= 0 or inf: no
+ * cutoff (precalculate.py:477).  Triples are enumerated in the reference's order; rate of a triple
+ * = strength * (1/(d_li d_lk)^mult + 1/(d_li d_ik)^mult + 1/(d_ik d_lk)^mult) (:499-506, 585).
+ * A strength of 0 removes the process.  Call before stb_set_batch.  Systems with a cooperative
+ * process are integrated by the cluster integrator (lattices whose state fits on 8 SMs); larger
+ * ones are rejected with STB_EINVAL. */
+int stb_set_coop(stb_system* S, const double* dist_array, const double* positions, const double* cell,
+                 const int32_t* idx6, int32_t mult, double strength, double d_max_coop);
+int64_t stb_coop_count(const stb_system* S);
+/* coop_N_indices [Mc][3] (u32), rows of the 6 entries of every column (i32: -w at rows 0, 2, 4,
+ * +w at rows 1, 3, 5), coop_w [Mc]; any pointer may be NULL. */
+int stb_export_coop(const stb_system* S, uint32_t* coop_N_indices, int32_t* coop_rows, double* coop_w);
+
 int64_t stb_launch_count(void);
 
 /* Device buffers of destroyed handles are parked (per device, up to 8 GB) and reused by the next

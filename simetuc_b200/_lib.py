@@ -34,6 +34,7 @@ EXPORTS = ['stb_last_error', 'stb_device_count', 'stb_describe', 'stb_system_cre
            'stb_set_blocks', 'stb_set_strengths', 'stb_num_interactions',
            'stb_export_interactions', 'stb_rhs', 'stb_jv', 'stb_rhs_dev', 'stb_jv_dev',
            'stb_to_planes', 'stb_from_planes', 'stb_integrate', 'stb_integrate_dev', 'stb_stream', 'stb_launch_count', 'stb_release_cached_memory',
+           'stb_set_coop', 'stb_coop_count', 'stb_export_coop',
            'stb_last_timing', 'stb_last_profile']
 
 _lib = None
@@ -90,6 +91,10 @@ def load():
     lib.stb_stream.restype = C.c_void_p
     lib.stb_launch_count.restype = C.c_int64
     lib.stb_release_cached_memory.restype = C.c_int64
+    lib.stb_set_coop.argtypes = [P, P, P, P, P, C.c_int32, C.c_double, C.c_double]
+    lib.stb_coop_count.argtypes = [P]
+    lib.stb_coop_count.restype = C.c_int64
+    lib.stb_export_coop.argtypes = [P, P, P, P]
     lib.stb_last_timing.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
     lib.stb_last_profile.argtypes = [P, C.POINTER(C.c_double)]
     _lib = lib

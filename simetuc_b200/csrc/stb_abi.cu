@@ -316,6 +316,13 @@ struct stb_system {
     void* ws_ptr[WS_COUNT] = {};
     size_t ws_cap[WS_COUNT] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // cooperative (three-ion) process: reference-ordered triples on the host (export), ion-owned
+    // lists on the device
+    std::vector<uint32_t> h_coop_N;      // [Mc][3]
+    std::vector<int32_t> h_coop_rows;    // [Mc][6]
+    std::vector<double> h_coop_w;        // [Mc] strength * geometry
+    void* d_coop[3][4] = {};             // per role: row_ptr, p1, p2, w
+    int n_terms_pair[2] = {0, 0}, nf_pair[2] = {0, 0};
 };
 
 // grow-only workspace slot of the handle
@@ -417,6 +424,8 @@ extern "C" void stb_system_destroy(stb_system* S) {
     pool_free(S->d_F);
     pool_free(S->d_tmp);
     for (int k = 0; k < stb_system::WS_COUNT; ++k) pool_free(S->ws_ptr[k]);
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 4; ++k) pool_free(S->d_coop[r][k]);
     if (S->ev0) cudaEventDestroy(S->ev0);
     if (S->ev1) cudaEventDestroy(S->ev1);
     if (S->stream) cudaStreamDestroy(S->stream);
@@ -955,6 +964,12 @@ static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* 
     g_launches++;
     k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     CK(cudaGetLastError());
+    if (S->hL.n_coop) {
+        g_launches++;
+        k_coop_add<<<dim3((unsigned)std::min<int64_t>((S->n_ions + 7) / 8, S->sm_count * 8), n), 256, 0, S->stream>>>(
+            S->dL, y, nullptr, out);
+        CK(cudaGetLastError());
+    }
     return STB_OK;
 }
 
@@ -966,6 +981,12 @@ static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y
     g_launches++;
     k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     CK(cudaGetLastError());
+    if (S->hL.n_coop) {
+        g_launches++;
+        k_coop_add<<<dim3((unsigned)std::min<int64_t>((S->n_ions + 7) / 8, S->sm_count * 8), n), 256, 0, S->stream>>>(
+            S->dL, y, v, out);
+        CK(cudaGetLastError());
+    }
     return STB_OK;
 }
 
@@ -1359,6 +1380,10 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
             return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
                                      avg_out, stats, dev);
     }
+    if (S->hL.n_coop)
+        return fail(STB_EINVAL, "cooperative energy transfer is integrated by the cluster integrator only, "
+                                "and this lattice does not fit it (all-to-all pairs, one multipolarity, "
+                                "state vector within the shared memory of 8 SMs)");
     // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
     const int max_ctas = S->sm_count;   // one CTA per SM
     const int total_slices = L.n_slices[0] + L.n_slices[1];
@@ -1514,6 +1539,147 @@ extern "C" int stb_integrate_dev(stb_system* S, int32_t first, int32_t n, int32_
 }
 
 extern "C" void* stb_stream(const stb_system* S) { return S ? (void*)S->stream : nullptr; }
+
+
+// ---- cooperative (three-ion) process --------------------------------------------------------
+extern "C" int stb_set_coop(stb_system* S, const double* dist_array, const double* positions,
+                            const double* cell, const int32_t* idx6, int32_t mult, double strength,
+                            double d_max_coop) {
+    if (!S || !idx6 || (!dist_array && !positions)) return fail(STB_EINVAL, "bad arguments");
+    CK(cudaSetDevice(S->device));
+    CK(cudaStreamSynchronize(S->stream));
+    DevLattice& L = S->hL;
+    // drop a previous cooperative process: lists, field slots and terms
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 4; ++k) { pool_free(S->d_coop[r][k]); S->d_coop[r][k] = nullptr; }
+    S->h_coop_N.clear(); S->h_coop_rows.clear(); S->h_coop_w.clear();
+    if (L.n_coop == 0) {
+        for (int T = 0; T < 2; ++T) { S->n_terms_pair[T] = L.terms[T].n_terms; S->nf_pair[T] = L.nf[T]; }
+    }
+    for (int T = 0; T < 2; ++T) { L.terms[T].n_terms = S->n_terms_pair[T]; L.nf[T] = S->nf_pair[T]; }
+    L.n_coop = 0;
+    const int n = (int)S->n_ions;
+    const int ii = idx6[0], ki = idx6[1], li = idx6[2], if_ = idx6[3], kf = idx6[4], lf = idx6[5];
+    const bool active = stb_active_strength(strength) && S->N > 5 && S->n[0] >= 2 && S->n[1] >= 1;
+    if (active) {
+        if (ii >= S->s[0] || if_ >= S->s[0] || ki >= S->s[0] || kf >= S->s[0] || li >= S->s[1] || lf >= S->s[1] ||
+            ii < 0 || if_ < 0 || ki < 0 || kf < 0 || li < 0 || lf < 0)
+            return fail(STB_EINVAL, "The number of A or S states is lower than required by a process.");
+        if (L.n_proc >= STB_MAX_PROC) return fail(STB_EINVAL, "too many processes");
+        if (L.nf[0] + 2 > 2 * STB_MAXC || L.nf[1] + 1 > 2 * STB_MAXC ||
+            L.terms[0].n_terms + 2 > STB_MAXT || L.terms[1].n_terms + 1 > STB_MAXT)
+            return fail(STB_EINVAL, "too many distinct field slots");
+        Geo G;
+        memset(&G, 0, sizeof(G));
+        G.n = n;
+        G.dist = dist_array;
+        G.pos = dist_array ? nullptr : positions;
+        if (!dist_array && cell) {
+            G.periodic = 1;
+            memcpy(G.cell, cell, sizeof(double) * 9);
+            if (!invert3(G.cell, G.inv)) return fail(STB_EINVAL, "singular cell");
+        }
+        // reference order (precalculate.py:471-480): acceptors in lattice order, pairs (i < k) of
+        // their sensitizer partners in combination order, both closer than d_max_coop
+        std::vector<int> s_ions;
+        for (int q = 0; q < n; ++q) if (S->type[q] == 0) s_ions.push_back(q);
+        const bool cut = d_max_coop > 0.0 && std::isfinite(d_max_coop);
+        std::vector<int64_t> cnt[3];
+        cnt[0].assign((size_t)S->n[0] + 1, 0); cnt[1].assign((size_t)S->n[0] + 1, 0); cnt[2].assign((size_t)S->n[1] + 1, 0);
+        struct Tri { int i, k, l; double w; };
+        std::vector<Tri> tri;
+        std::vector<double> dl(s_ions.size());
+        std::vector<int> keep;
+        for (int l = 0; l < n; ++l) {
+            if (S->type[l] != 1) continue;
+            keep.clear();
+            for (size_t a = 0; a < s_ions.size(); ++a) {
+                dl[a] = geo_dist(G, l, s_ions[a]);
+                if (dl[a] != 0.0) keep.push_back((int)a);       // np.nonzero(dist), lattice.py:335
+            }
+            for (size_t x = 0; x < keep.size(); ++x)
+                for (size_t y = x + 1; y < keep.size(); ++y) {
+                    const int a = keep[x], b = keep[y];
+                    const double dli = dl[a], dlk = dl[b];
+                    if (cut && !(std::max(dli, dlk) < d_max_coop)) continue;
+                    const double dik = geo_dist(G, s_ions[a], s_ions[b]);
+                    const double w = 1.0 / std::pow(dli * dlk, (double)mult) + 1.0 / std::pow(dli * dik, (double)mult) +
+                                     1.0 / std::pow(dik * dlk, (double)mult);
+                    tri.push_back({s_ions[a], s_ions[b], l, strength * w});
+                }
+        }
+        const size_t Mc = tri.size();
+        S->h_coop_N.resize(Mc * 3); S->h_coop_rows.resize(Mc * 6); S->h_coop_w.resize(Mc);
+        for (size_t r = 0; r < Mc; ++r) {
+            const Tri& t = tri[r];
+            const int gi = S->gs_ref[t.i], gk = S->gs_ref[t.k], gl = S->gs_ref[t.l];
+            S->h_coop_N[3 * r] = gi + ii; S->h_coop_N[3 * r + 1] = gk + ki; S->h_coop_N[3 * r + 2] = gl + li;
+            int32_t* rw = &S->h_coop_rows[6 * r];
+            rw[0] = gi + ii; rw[1] = gi + if_; rw[2] = gk + ki; rw[3] = gk + kf; rw[4] = gl + li; rw[5] = gl + lf;
+            S->h_coop_w[r] = t.w;
+            cnt[0][S->local_idx[t.i] + 1]++; cnt[1][S->local_idx[t.k] + 1]++; cnt[2][S->local_idx[t.l] + 1]++;
+        }
+        if (Mc > 0) {
+            for (int r = 0; r < 3; ++r)
+                for (size_t q = 1; q < cnt[r].size(); ++q) cnt[r][q] += cnt[r][q - 1];
+            std::vector<uint32_t> p1[3], p2[3];
+            std::vector<double> ww[3];
+            std::vector<int64_t> fill[3];
+            for (int r = 0; r < 3; ++r) { p1[r].resize(Mc); p2[r].resize(Mc); ww[r].resize(Mc); fill[r] = cnt[r]; }
+            for (size_t r = 0; r < Mc; ++r) {
+                const Tri& t = tri[r];
+                const uint32_t li_ = S->local_idx[t.i], lk_ = S->local_idx[t.k], ll_ = S->local_idx[t.l];
+                int64_t e = fill[0][li_]++; p1[0][e] = lk_; p2[0][e] = ll_; ww[0][e] = t.w;   // owner i: (k, l)
+                e = fill[1][lk_]++; p1[1][e] = li_; p2[1][e] = ll_; ww[1][e] = t.w;           // owner k: (i, l)
+                e = fill[2][ll_]++; p1[2][e] = li_; p2[2][e] = lk_; ww[2][e] = t.w;           // owner l: (i, k)
+            }
+            for (int r = 0; r < 3; ++r) {
+                CK(upload(S->stream, (int64_t**)&S->d_coop[r][0], cnt[r]));
+                CK(upload(S->stream, (uint32_t**)&S->d_coop[r][1], p1[r]));
+                CK(upload(S->stream, (uint32_t**)&S->d_coop[r][2], p2[r]));
+                CK(upload(S->stream, (double**)&S->d_coop[r][3], ww[r]));
+            }
+            // roles: 0 = first sensitizer (ii -> if; partners k [S, ki], l [A, li]),
+            //        1 = second sensitizer (ki -> kf; partners i [S, ii], l [A, li]),
+            //        2 = acceptor (li -> lf; partners i [S, ii], k [S, ki])
+            const int role_T[3] = {0, 0, 1}, role_a[3] = {ii, ki, li}, role_b[3] = {if_, kf, lf};
+            const int T1[3] = {0, 0, 0}, c1[3] = {ki, ii, ii}, T2[3] = {1, 1, 0}, c2[3] = {li, li, ki};
+            for (int r = 0; r < 3; ++r) {
+                CoopList& C = L.coop[r];
+                C.row_ptr = (const int64_t*)S->d_coop[r][0];
+                C.p1 = (const uint32_t*)S->d_coop[r][1];
+                C.p2 = (const uint32_t*)S->d_coop[r][2];
+                C.w = (const double*)S->d_coop[r][3];
+                C.T = role_T[r]; C.T1 = T1[r]; C.col1 = c1[r]; C.T2 = T2[r]; C.col2 = c2[r];
+                C.a = role_a[r]; C.b = role_b[r];
+                const int T = role_T[r];
+                C.fslot = L.nf[T]++;
+                TermTable& tt = L.terms[T];
+                const int k = tt.n_terms++;
+                tt.fslot[k] = (short)C.fslot; tt.a[k] = (short)C.a; tt.b[k] = (short)C.b;
+                tt.proc[k] = (short)L.n_proc;          // reserved strength slot, always 1 (w carries the strength)
+            }
+            L.n_coop = 3;
+        }
+    }
+    L.foff[0] = 0;
+    L.foff[1] = L.nf[0] * L.n[0];
+    L.NF = L.nf[0] * L.n[0] + L.nf[1] * L.n[1];
+    CK(copy_on(S->stream, S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
+    S->scratch_n = 0;       // the field scratch depends on NF
+    return STB_OK;
+}
+
+extern "C" int64_t stb_coop_count(const stb_system* S) { return S ? (int64_t)S->h_coop_w.size() : -1; }
+
+extern "C" int stb_export_coop(const stb_system* S, uint32_t* coop_N_indices, int32_t* coop_rows, double* coop_w) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    const size_t Mc = S->h_coop_w.size();
+    if (coop_N_indices && Mc) memcpy(coop_N_indices, S->h_coop_N.data(), sizeof(uint32_t) * 3 * Mc);
+    if (coop_rows && Mc) memcpy(coop_rows, S->h_coop_rows.data(), sizeof(int32_t) * 6 * Mc);
+    if (coop_w && Mc) memcpy(coop_w, S->h_coop_w.data(), sizeof(double) * Mc);
+    return STB_OK;
+}
 
 extern "C" int64_t stb_launch_count(void) { return (int64_t)g_launches.load(); }
 

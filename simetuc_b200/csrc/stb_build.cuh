@@ -17,7 +17,7 @@ struct Geo {
 };
 
 // minimum-image distance, same arithmetic as simetuc_b200/lattice.py:mic_distances
-__device__ __forceinline__ double geo_dist(const Geo& G, int a, int b) {
+__host__ __device__ __forceinline__ double geo_dist(const Geo& G, int a, int b) {
     if (G.dist) return G.dist[(int64_t)a * G.n + b];
     double d0 = G.pos[3 * b] - G.pos[3 * a];
     double d1 = G.pos[3 * b + 1] - G.pos[3 * a + 1];

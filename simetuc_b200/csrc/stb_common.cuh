@@ -46,6 +46,20 @@ struct TermTable {
     short a[STB_MAXT], b[STB_MAXT], proc[STB_MAXT];
 };
 
+// Cooperative (three-ion, S-S-A) energy transfer (precalculate.py:427-599), ion-owned like the pair
+// lists: every ion holds, per role it plays in a triple, the list of its two partners and the
+// rate `strength * (1/(d_li d_lk)^m + 1/(d_li d_ik)^m + 1/(d_ik d_lk)^m)`.  The sum over the list
+// of w * z[p1] * z[p2] is one more FIELD of the ion (slot `fslot` of its type), so that the rate
+// terms, the block-Jacobi preconditioner and the Jacobian-vector product treat it like a pair
+// process: rate = y_q[a] * F[fslot], moved from state a to state b.
+struct CoopList {
+    const int64_t* row_ptr;      // [n[T] + 1]
+    const uint32_t* p1;          // type-local index of the first partner (type T1, state col1)
+    const uint32_t* p2;          // ... second partner (type T2, state col2)
+    const double* w;
+    int T, T1, col1, T2, col2, fslot, a, b;
+};
+
 struct DevLattice {
     int n_ions, N, NF;
     int n[2], s[2], off[2];      // ions / states / plane offset per type
@@ -61,6 +75,8 @@ struct DevLattice {
     const int* plane_of_ref;     // [N]
     const int* ref_of_plane;     // [N]
     int blk_stride;              // doubles per system in the `blocks` array
+    int n_coop;                  // 0, or 3 roles: S as first donor, S as second donor, A as acceptor
+    CoopList coop[3];
 };
 
 // per-system parameters as the kernels see them

@@ -244,6 +244,8 @@ __device__ __forceinline__ double slice_fields_impl(const DevLattice& L, int T, 
         }
         out += ns;
     }
+    if (Fq)      // slots past the pair blocks (cooperative fields) are filled elsewhere: zero here
+        for (int k = out; k < L.nf[T]; ++k) Fq[k] = 0.0;
     return fl;
 }
 
@@ -375,4 +377,21 @@ __device__ __forceinline__ void load_sys_params(const DevLattice& L, const doubl
         double c = strengths[(int64_t)sys * L.n_proc + i];
         P.C[i] = stb_active_strength(c) ? c : 0.0;
     }
+    if (threadIdx.x == 0 && L.n_coop) P.C[L.n_proc] = 1.0;     // cooperative terms: w carries the strength
 }
+
+// cooperative field of one ion (see CoopList in stb_common.cuh)
+__device__ __forceinline__ double coop_list_field(const CoopList& C, int q, const double* y1, const double* y2,
+                                                  const double* v1, const double* v2, int lane) {
+    const int64_t e0 = C.row_ptr[q], e1 = C.row_ptr[q + 1];
+    double acc = 0.0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const uint32_t a = C.p1[e], b = C.p2[e];
+        const double w = C.w[e];
+        if (v1) acc = fma(w, fma(v1[a], y2[b], y1[a] * v2[b]), acc);
+        else acc = fma(w * y1[a], y2[b], acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+

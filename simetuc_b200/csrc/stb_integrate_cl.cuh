@@ -244,6 +244,31 @@ __device__ __forceinline__ void cl_piece_ns(int ns, int g_off, const double* gb,
 
 #define CL_MAXCOMB ((STB_NW - 1) * STB_MAXC * CL_RG)   // a warp boundary splits at most one segment
 
+// Cooperative (three-ion) fields of the own ions, one warp per ion and role: F[coop slot][row] =
+// mult * sum w z1[p1] z2[p2], or its derivative in the direction z at the vector at lin_at
+// (Krylov operator).  Not inlined: the integrator kernel is at its register limit and systems
+// without a cooperative process (every shipped configuration) must not pay for this code.
+__device__ __noinline__ void cl_coop_fields(const DevLattice& L, const ClLayout& Y, const int* r_lo,
+                                            const int* cnt, int zb, double mult, int lin_at, int warp,
+                                            int lane) {
+    extern __shared__ __align__(16) double dynb[];
+    double* F = dynb + Y.F;
+    for (int r = 0; r < L.n_coop; ++r) {
+        const CoopList& Cl = L.coop[r];
+        const int T = Cl.T;
+        const int o1 = Y.zoff[Cl.T1] + Cl.col1 * Y.ldz[Cl.T1], o2 = Y.zoff[Cl.T2] + Cl.col2 * Y.ldz[Cl.T2];
+        for (int i = warp; i < cnt[T]; i += STB_NW) {
+            double f;
+            if (lin_at >= 0)
+                f = mult * coop_list_field(Cl, r_lo[T] + i, dynb + lin_at + o1, dynb + lin_at + o2,
+                                           dynb + zb + o1, dynb + zb + o2, lane);
+            else
+                f = mult * coop_list_field(Cl, r_lo[T] + i, dynb + zb + o1, dynb + zb + o2, nullptr, nullptr, lane);
+            if (lane == 0) F[Y.foff[T] + Cl.fslot * Y.cntp[T] + i] = f;
+        }
+    }
+}
+
 struct ClConst {           // per-CTA constants that are indexed dynamically: shared, not local memory
     int r_lo[2], cnt[2], ob[2], nrg[2];
     int stp[2][2], cst[2][2], ST[2], WT[2], Wt[2];
@@ -631,7 +656,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
     // ---- pair pass: F[slot][row] = mult * sum_k g(row, k) z[col_slot][k] for the own rows --------
     const int rr = lane & 7, kk = lane >> 3;
     // zb: offset of the gathered vector (Y.zy or Y.zv) in the dynamic shared array
-    auto fields_pass = [&](int zb, double mult) {
+    // lin_at >= 0: cooperative fields are linearised at the vector at offset lin_at (Krylov operator)
+    auto fields_pass = [&](int zb, double mult, int lin_at) {
         int g = my_ga, t0 = my_ta, piece = 0;
         while (g < NRG && (g < my_gb || (g == my_gb && t0 < my_tb))) {
             const int T = g >= nrg[0];
@@ -679,6 +705,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             }
             __syncthreads();
         }
+        if (L.n_coop) {
+            cl_coop_fields(L, Y, r_lo, cnt, zb, mult, lin_at, warp, lane);
+            __syncthreads();
+        }
         CLPROF(2)
     };
 
@@ -715,7 +745,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
 
     // f = rhs(z) for the own elements (odesolver.py:33-43, 65-71); fields stay in F
     auto rhs_pass = [&](const double* z, int zb, double* fout) {
-        fields_pass(zb, 1.0);
+        fields_pass(zb, 1.0, -1);
         for (int k = tid; k < n_own; k += STB_NT) {
             const int inf = own_inf[k];
             const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
@@ -1021,7 +1051,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
                 while (!lin_done) {
                     // w = Minv (I - cJ) v / scale = V_j - c Minv k(v) / scale, k = inter-ion coupling
                     CLPROF(15)
-                    fields_pass(Y.zv, zmul);
+                    fields_pass(Y.zv, zmul, Y.zy);
                     for (int k = tid; k < n_own; k += STB_NT) {
                         const int inf = own_inf[k];
                         const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;

@@ -162,3 +162,52 @@ __global__ void k_avg_populations(const DevLattice* Lg, const double* y_out, int
         __syncthreads();
     }
 }
+
+
+// ---- cooperative (three-ion) energy transfer: odesolver.py:40-41 (RHS), :56-60 (Jacobian) --------
+// Field of ion q in role r: Fc = sum over its partner pairs of w * z1[p1] * z2[p2]; `lin`: the
+// derivative of the field in the direction v at y, sum of w * (v1 y2 + y1 v2).  One warp per ion,
+// lanes stride over the ion's list (16 B per entry, coalesced), shuffle reduction: deterministic.
+// out += cooperative contribution (RHS when v == null, J(y) v otherwise); planes layout,
+// blockIdx.y = system of the batch.  The fused pair kernels see zero in the cooperative field
+// slots, so nothing is counted twice.
+__global__ void __launch_bounds__(256) k_coop_add(const DevLattice* Lp, const double* y_all, const double* v_all,
+                                                  double* out_all) {
+    __shared__ DevLattice L;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
+        ((int*)&L)[i] = ((const int*)Lp)[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const double* y = y_all + (int64_t)b * L.N;
+    const double* v = v_all ? v_all + (int64_t)b * L.N : nullptr;
+    double* out = out_all + (int64_t)b * L.N;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int n_all = L.n[0] + L.n[1];
+    for (int idx = warp; idx < n_all; idx += nwarps) {
+        const int T = idx >= L.n[0];
+        const int q = T ? idx - L.n[0] : idx;
+        for (int r = 0; r < L.n_coop; ++r) {       // the roles of one ion in turn: no two warps
+            const CoopList& C = L.coop[r];          // touch the same state
+            if (C.T != T) continue;
+            const double* y1 = y + L.off[C.T1] + C.col1 * L.n[C.T1];
+            const double* y2 = y + L.off[C.T2] + C.col2 * L.n[C.T2];
+            const double Fy = coop_list_field(C, q, y1, y2, nullptr, nullptr, lane);
+            double rate;
+            const int ea = L.off[T] + C.a * L.n[T] + q, eb = L.off[T] + C.b * L.n[T] + q;
+            if (v) {
+                const double* v1 = v + L.off[C.T1] + C.col1 * L.n[C.T1];
+                const double* v2 = v + L.off[C.T2] + C.col2 * L.n[C.T2];
+                const double Fv = coop_list_field(C, q, y1, y2, v1, v2, lane);
+                rate = fma(v[ea], Fy, y[ea] * Fv);
+            } else {
+                rate = y[ea] * Fy;
+            }
+            if (lane == 0) {
+                out[ea] -= rate;
+                out[eb] += rate;
+            }
+            __syncwarp();
+        }
+    }
+}

@@ -21,11 +21,22 @@ def pair_processes(energy_transfer) -> list:
     return [(name, p) for name, p in energy_transfer.items() if len(p.type) == 2]
 
 
+def coop_process(energy_transfer):
+    """The first cooperative process of type (S, S, A) with non-zero strength
+    (`precalculate.py:512-520`), or None."""
+    for p in energy_transfer.values():
+        if len(p.type) == 3 and not np.isclose(p.strength, 0.0) and \
+                tuple(ion_code(t) for t in p.type) == (0, 0, 1):
+            return p
+    return None
+
+
 class RateSystem:
     """Device-resident ET coupling of one lattice + per-system linear blocks and ET strengths."""
 
     def __init__(self, lattice: Lattice, energy_transfer, device: int = 0,
-                 d_max: Optional[float] = None, geometry: str = 'auto'):
+                 d_max: Optional[float] = None, geometry: str = 'auto',
+                 d_max_coop: Optional[float] = None):
         lib = _lib.require_gpu()
         self.lib = lib
         self.lattice = lattice
@@ -67,6 +78,49 @@ class RateSystem:
         self.n_sys = 1
         #: bytes streamed per stored pair: 8 (dense all-to-all blocks) or 4 + 8 per multipolarity
         self.bytes_per_pair = self.stream_bytes // self.n_slots if self.n_slots else 0
+        self._geometry = (dist, pos, cell)
+        self.n_coop = 0
+        coop = coop_process(energy_transfer)
+        if coop is not None:
+            self.set_coop(coop, d_max_coop)
+
+    def set_coop(self, process, d_max_coop: Optional[float] = None):
+        """Install (or, with strength 0, remove) the cooperative S-S-A process
+        (`precalculate.py:427-599`); call before `set_batch`."""
+        dist, pos, cell = self._geometry
+        idx6 = np.ascontiguousarray(process.indices, dtype=np.int32)
+        if idx6.shape != (6,):
+            raise ValueError('a cooperative process has three transitions')
+        d_max = -1.0 if d_max_coop is None or not np.isfinite(d_max_coop) else float(d_max_coop)
+        rc = self.lib.stb_set_coop(self.handle, _lib.ptr(dist), _lib.ptr(pos), _lib.ptr(cell),
+                                   _lib.ptr(idx6), int(process.mult), float(process.strength), d_max)
+        if rc != 0:
+            msg = _lib.last_error()
+            if 'states' in msg or 'process' in msg:
+                raise LatticeError(msg)
+            raise _lib.StbError(rc, msg)
+        self.n_coop = int(self.lib.stb_coop_count(self.handle))
+
+    def coop_operands(self):
+        """`(coop_ET_matrix [N, Mc] CSR, coop_N_indices [Mc, 3], coop_jac_indices [3 Mc, 4])` in the
+        reference's layout (`precalculate.py:575-599, 626-699`)."""
+        Mc = self.n_coop
+        if Mc == 0:
+            return (sp.csr_matrix((self.N, 0), dtype=np.float64), np.zeros((0, 3), dtype=np.uint32),
+                    np.zeros((0, 4), dtype=np.uint32))
+        N3 = np.empty((Mc, 3), dtype=np.uint32)
+        rows = np.empty((Mc, 6), dtype=np.int32)
+        w = np.empty(Mc, dtype=np.float64)
+        _lib.check(self.lib.stb_export_coop(self.handle, _lib.ptr(N3), _lib.ptr(rows), _lib.ptr(w)))
+        vals = np.column_stack((-w, w, -w, w, -w, w)).ravel()
+        cols = np.repeat(np.arange(Mc, dtype=np.int64), 6)
+        M = sp.csr_matrix((vals, (rows.ravel().astype(np.int64), cols)), shape=(self.N, Mc), dtype=np.float64)
+        jac = np.empty((3 * Mc, 4), dtype=np.uint32)
+        jac[:, 0] = np.repeat(np.arange(Mc, dtype=np.uint32), 3)
+        jac[0::3, 1], jac[1::3, 1], jac[2::3, 1] = N3[:, 2], N3[:, 1], N3[:, 0]
+        jac[0::3, 2], jac[1::3, 2], jac[2::3, 2] = N3[:, 0], N3[:, 0], N3[:, 1]
+        jac[0::3, 3], jac[1::3, 3], jac[2::3, 3] = N3[:, 1], N3[:, 2], N3[:, 2]
+        return M, N3, jac
 
     # ------------------------------------------------------------------ lifetime
     def close(self):

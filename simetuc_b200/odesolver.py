@@ -30,23 +30,27 @@ def _system_of(*operands):
                     '(no device system attached); this path has no CPU fallback')
 
 
-def _check_coop(coop_N_indices):
-    if coop_N_indices is not None and np.shape(coop_N_indices)[0] != 0:
-        raise NotImplementedError('cooperative (three-ion) terms are not on the device path yet')
+def _check_coop(coop_N_indices, system=None):
+    """Cooperative operands are accepted when they describe the process the device system was
+    built with (they are then views exported from it); anything else has no device counterpart."""
+    n = 0 if coop_N_indices is None else np.shape(coop_N_indices)[0]
+    if system is not None and n != system.n_coop:
+        raise TypeError('cooperative operands do not match the device system (%d interactions, '
+                        'the system holds %d)' % (n, system.n_coop))
 
 
 def _rate_eq(t, y, decay_matrix, UC_matrix, N_indices, coop_ET_matrix, coop_N_indices):
     '''Calculates the rhs of the ODE for the relaxation (reference: `odesolver.py:33-43`).'''
-    _check_coop(coop_N_indices)
     system, k = _system_of(UC_matrix, decay_matrix)
+    _check_coop(coop_N_indices, system)
     return system.rhs(np.asarray(y, dtype=np.float64), pulse=False, first=k)
 
 
 def _rate_eq_pulse(t, y, abs_matrix, decay_matrix, UC_matrix, N_indices,
                    coop_ET_matrix, coop_N_indices):
     '''Calculates the rhs of the ODE for the excitation pulse (`odesolver.py:65-71`).'''
-    _check_coop(coop_N_indices)
     system, k = _system_of(UC_matrix, decay_matrix, abs_matrix)
+    _check_coop(coop_N_indices, system)
     return system.rhs(np.asarray(y, dtype=np.float64), pulse=True, first=k)
 
 
@@ -70,16 +74,16 @@ def _dense_jacobian(system, k, y, pulse):
 def _jac_rate_eq(t, y, decay_matrix, UC_matrix, jac_indices, coop_ET_matrix, coop_jac_indices):
     '''Dense Jacobian of the relaxation (`odesolver.py:46-62`), assembled from N device Jv
     products.  Kept for interface parity; the device integrator is Jacobian-free.'''
-    _check_coop(coop_jac_indices)
     system, k = _system_of(UC_matrix, decay_matrix)
+    _check_coop(None if coop_jac_indices is None else np.asarray(coop_jac_indices)[::3], system)
     return _dense_jacobian(system, k, y, pulse=False)
 
 
 def _jac_rate_eq_pulse(t, y, abs_matrix, decay_matrix, UC_matrix, jac_indices,
                        coop_ET_matrix, coop_jac_indices):
     '''Dense Jacobian of the excitation pulse (`odesolver.py:74-80`).'''
-    _check_coop(coop_jac_indices)
     system, k = _system_of(UC_matrix, decay_matrix, abs_matrix)
+    _check_coop(None if coop_jac_indices is None else np.asarray(coop_jac_indices)[::3], system)
     return _dense_jacobian(system, k, y, pulse=True)
 
 
@@ -95,7 +99,7 @@ def _solve_ode(t_arr: np.array, fun: Callable, fargs: Tuple, jfun: Callable, jar
         raise ValueError("only method='bdf' is available on the device path")
     pulse = fun is _rate_eq_pulse
     system, k = _system_of(*fargs)
-    _check_coop(fargs[-1])
+    _check_coop(fargs[-1], system)
     y0 = np.asarray(initial_population, dtype=np.float64).ravel()
     y_out, _, stats = system.integrate(np.asarray(t_arr, dtype=np.float64), y0, pulse=pulse,
                                        rtol=rtol, atol=atol, nsteps=nsteps, first=k)

@@ -139,7 +139,8 @@ def build_system(cte, lat: Lattice, device: int = 0, d_max: Optional[float] = No
     """Device-resident system for `lat` with `cte`'s processes; every system of the batch gets
     `cte`'s decay and absorption blocks."""
     check_process_states(cte)
-    system = RateSystem(lat, cte['energy_transfer'], device=device, d_max=d_max)
+    system = RateSystem(lat, cte['energy_transfer'], device=device, d_max=d_max,
+                        d_max_coop=cte['lattice'].get('d_max_coop'))
     system.set_batch(n_sys)
     system.set_decay_blocks(*decay_blocks(cte))
     system.set_abs_blocks(*absorption_blocks(cte))
@@ -227,16 +228,14 @@ def _setup_eqs(cte, lat, device, processes, drop_empty):
     start = time.time()
     cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
     cte['states']['energy_states'] = lat.n_states
-    for name, p in processes.items():
-        if len(p.type) == 3 and not np.isclose(p.strength, 0.0):
-            raise NotImplementedError('cooperative (three-ion) energy transfer process %s: '
-                                      'not yet on the device path' % name)
-    key = (id(lat), tuple((n, p.indices, p.mult, bool(np.isclose(p.strength, 0.0)))
-                          for n, p in processes.items() if len(p.type) == 2), device)
+    d_max_coop = (cte['lattice'].get('d_max_coop') if hasattr(cte['lattice'], 'get') else None)
+    key = (id(lat), tuple((n, p.indices, p.mult, bool(np.isclose(p.strength, 0.0)),
+                           p.strength if len(p.type) == 3 else None)
+                          for n, p in processes.items()), d_max_coop, device)
     system = _SYSTEM_CACHE.get(key)
     if system is None or system.handle is None:
         check_process_states(cte)
-        system = RateSystem(lat, processes, device=device)
+        system = RateSystem(lat, processes, device=device, d_max_coop=d_max_coop)
         _SYSTEM_CACHE.clear()          # one resident lattice per process is enough here
         _SYSTEM_CACHE[key] = system
     check_process_states(cte)
@@ -259,10 +258,8 @@ def _setup_eqs(cte, lat, device, processes, drop_empty):
             N_indices = N_indices[keep]
             jac_indices = jac_indices_of(N_indices)
     N = system.N
-    coop_ET_matrix = sp.csr_matrix((N, 0), dtype=np.float64)
-    coop_N_indices = np.zeros((0, 3), dtype=np.uint32)
-    coop_jac_indices = np.zeros((0, 4), dtype=np.uint32)
-    for m in (total_abs_matrix, decay_matrix, ET_matrix):
+    coop_ET_matrix, coop_N_indices, coop_jac_indices = system.coop_operands()
+    for m in (total_abs_matrix, decay_matrix, ET_matrix, coop_ET_matrix):
         m.stb = (system, 0)
     logger.info('Setup finished. Total time: %.2fs.', time.time() - start)
     return (cte, initial_population, list(index_S_i), list(index_A_j), total_abs_matrix,

@@ -305,3 +305,107 @@ def test_c2_full_size_vs_golden():
         ref = gold['avg'][slot]
         big = ref > 1e-9
         assert np.all(np.abs(avg[slot] - ref)[big] <= 1e-4 * ref[big])
+
+
+# ---------------------------------------------------------------- cooperative (three-ion) ET
+def make_coop_system(g, cte, d_max_coop=None, **kw):
+    lat = Lattice.from_arrays(g['ion_type'], g['dist_array'], int(g['info'][0]), int(g['info'][1]),
+                              positions=g.get('doped_lattice'))
+    system = RateSystem(lat, cte['energy_transfer'], d_max_coop=d_max_coop, **kw)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    return system
+
+
+@pytest.mark.parametrize('tag', ['1S_1A', '2S_0A', '2S_2A', '3S_1A', '3S_2A'])
+@pytest.mark.parametrize('d_max_coop', [None, 25.0, 9.0])
+def test_coop_operands_bit_exact(tag, d_max_coop):
+    """Cooperative operands (`precalculate.py:427-599, 626-699`) against the oracle (itself pinned
+    to the reference's known answers for 1S1A and 2S2A, `test_setup.py`): indices bit-exact,
+    rates to 1e-14 relative, the same triples kept by the `d_max_coop` cutoff."""
+    g = load_golden(tag)
+    cte = configs.test_cte()
+    cte['lattice']['d_max_coop'] = np.inf if d_max_coop is None else d_max_coop
+    op = oracle_operands(g, cte, coop=True)
+    cM, cN, cJ = op['coop']
+    system = make_coop_system(g, cte, d_max_coop=d_max_coop)
+    M, N3, J4 = system.coop_operands()
+    assert N3.shape == cN.shape and np.array_equal(N3, cN)
+    assert np.array_equal(J4, cJ)
+    assert M.shape == cM.shape
+    if cN.shape[0]:
+        a, b = M.toarray(), cM.toarray()
+        assert np.all((a == 0) == (b == 0))
+        assert np.allclose(a, b, rtol=1e-14, atol=0)
+    system.close()
+
+
+@pytest.mark.parametrize('tag', ['2S_2A', '3S_2A'])
+def test_coop_rhs_and_jv(tag):
+    """RHS and J v with the cooperative term (`odesolver.py:40-41, 56-60`) against the oracle."""
+    g = load_golden(tag)
+    cte = configs.test_cte()
+    cte['lattice']['d_max_coop'] = np.inf
+    cte['energy_transfer']['coop1'].strength = 1e18         # make the term matter next to the pair terms
+    op = oracle_operands(g, cte, coop=True)
+    cM, cN, cJ = op['coop']
+    assert cN.shape[0] > 0
+    system = make_coop_system(g, cte)
+    rng = np.random.default_rng(77)
+    for _ in range(3):
+        y = 10.0 ** rng.uniform(-3, 0, size=op['N'])
+        v = rng.standard_normal(op['N']) * y
+        for pulse in (True, False):
+            if pulse:
+                f_ref = onp.rate_eq_pulse(0.0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], cM, cN)
+                J_ref = onp.jac_rate_eq_pulse(0.0, y, op['abs'], op['decay'], op['ET'], op['jac_indices'], cM, cJ)
+            else:
+                f_ref = onp.rate_eq(0.0, y, op['decay'], op['ET'], op['N_indices'], cM, cN)
+                J_ref = onp.jac_rate_eq(0.0, y, op['decay'], op['ET'], op['jac_indices'], cM, cJ)
+            f = np.ravel(system.rhs(y, pulse=pulse))
+            jv = np.ravel(system.jv(y, v, pulse=pulse))
+            assert np.all(np.abs(f - f_ref) <= 1e-12 * np.abs(f_ref).max())
+            jv_ref = J_ref @ v
+            assert np.all(np.abs(jv - jv_ref) <= 1e-12 * np.abs(jv_ref).max())
+    # the cooperative term is really there: without it the RHS differs
+    f_pair = onp.rate_eq(0.0, y, op['decay'], op['ET'], op['N_indices'], *onp.empty_coop(op['N'])[:2])
+    assert np.abs(f_pair - f_ref).max() > 1e-6 * np.abs(f_ref).max()     # 1e6 x the tolerance above
+    system.close()
+
+
+def test_coop_trajectory_vs_lsoda():
+    """Pulse + relaxation with a strong cooperative process through the cluster integrator against
+    scipy LSODA on the oracle's operators (trajectory tolerance of the module header)."""
+    cte = configs.test_cte()
+    cte['lattice'] = dict(cte['lattice'])
+    lat_cte = configs.yb_tm_cte(N_uc=6, S_conc=10.0, A_conc=3.0)
+    lat = lattice.generate_arrays(lat_cte, seed=4242)
+    g = {'ion_type': lat['ion_type'], 'dist_array': lat['dist_array'], 'info': np.array([2, 7]),
+         'doped_lattice': lat['doped_lattice']}
+    cte['lattice']['d_max_coop'] = np.inf
+    cte['energy_transfer']['coop1'].strength = 5e11
+    for exc in cte['excitations']['Vis_473']:
+        exc.active = False
+    for exc in cte['excitations']['NIR_980']:
+        exc.active = True
+        exc.power_dens = 1e9
+    op = oracle_operands(g, cte, coop=True)
+    cM, cN, cJ = op['coop']
+    assert cN.shape[0] > 100
+    system = make_coop_system(g, cte)
+    t_pulse, t_sol = onp.time_grids(1e-8, onp.t_simulation(cte['decay']), 200)
+    y0 = op['initial_population'].astype(float)
+    y_p, _, st_p = system.integrate(t_pulse, y0, pulse=True, rtol=1e-8, atol=1e-15)
+    y, _, st = system.integrate(t_sol, y_p[0, -1], pulse=False, rtol=1e-8, atol=1e-15)
+    assert st_p[0]['status'] == 0 and st[0]['status'] == 0
+    kw = dict(rtol=1e-8, atol=1e-15, nsteps=100000)
+    yp_ref = onp.solve_pulse(t_pulse, y0, op['abs'], op['decay'], op['ET'], op['N_indices'],
+                             op['jac_indices'], coop=(cM, cN, cJ), **kw)
+    y_ref = onp.solve_relax(t_sol, yp_ref[-1], op['decay'], op['ET'], op['N_indices'],
+                            op['jac_indices'], coop=(cM, cN, cJ), **kw)
+    assert parity_metric(y_p[0, -1], yp_ref[-1]) <= 1.0
+    assert parity_metric(y[0], y_ref) <= 1.0
+    # and the cooperative channel is visible: the 1G4 state (5) of the activators is fed by it
+    y_nc = onp.solve_relax(t_sol, yp_ref[-1], op['decay'], op['ET'], op['N_indices'], op['jac_indices'], **kw)
+    assert np.abs(y_nc - y_ref).max() > 1e-3 * np.abs(y_ref).max()
+    system.close()
