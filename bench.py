@@ -335,7 +335,7 @@ def run_gpu(args):
         'solver': {'ok': bool(ok), 'rhs_passes_per_step': n_rhs, 'jv_passes_per_step': n_jv,
                    'steps_min_max': [min(s['n_steps'] for s in stats_last[1]),
                                      max(s['n_steps'] for s in stats_last[1])]},
-        'roofline': {'bound': 'hbm', 'kernel': 'k_integrate_cl (cluster BDF/Newton-Krylov integrator; its '
+        'roofline': {'bound': 'hbm', 'kernel': 'k_integrate_cl_t<false> (cluster BDF/Newton-Krylov integrator; its '
                      'inner loop is the pair-stream pass, pair rows resident in shared memory)',
                      'achieved': achieved, 'peak': peaks['hbm_gbs'],
                      'unit': 'GB/s', 'frac': achieved / peaks['hbm_gbs'], 'traffic': 2.2e6,

@@ -1110,14 +1110,20 @@ static cudaError_t allow_max_smem(K kernel) {
     return e;
 }
 
+typedef void (*ClKernel)(ClArgs);
+// the plain cluster integrator, or the instance with the cooperative field pass
+static ClKernel cl_kernel(const stb_system* S) {
+    return S->hL.n_coop ? (ClKernel)k_integrate_cl_t<true> : (ClKernel)k_integrate_cl_t<false>;
+}
+
 struct ClPlan {
     int G = 0, n_clusters = 0, resmask = 0, v_smem = 0, d_smem = 0;
     size_t dyn_bytes = 0;
     double resident_frac = 0.0;
 };
 
-static cudaError_t cl_max_clusters(int G, size_t dyn_bytes, int sm_count, int* out) {
-    cudaError_t e = allow_max_smem(k_integrate_cl);
+static cudaError_t cl_max_clusters(ClKernel kern, int G, size_t dyn_bytes, int sm_count, int* out) {
+    cudaError_t e = allow_max_smem(kern);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -1131,7 +1137,7 @@ static cudaError_t cl_max_clusters(int G, size_t dyn_bytes, int sm_count, int* o
     at.val.clusterDim.z = 1;
     cfg.attrs = &at;
     cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(out, k_integrate_cl, &cfg);
+    return cudaOccupancyMaxActiveClusters(out, kern, &cfg);
 }
 
 // Picks the cluster size and what lives in shared memory; false = use the cooperative-grid
@@ -1146,7 +1152,8 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
         if (forced != 1 && forced != 2 && forced != 4 && forced != 8) return false;
     }
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, k_integrate_cl) != cudaSuccess) { cudaGetLastError(); return false; }
+    ClKernel kern = cl_kernel(S);
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return false; }
     const size_t cap = 232448 - fa.sharedSizeBytes - 64;   // 227 KB per CTA
     int want_res = 1;
     if (const char* env = getenv("STB_RESIDENT")) want_res = atoi(env) != 0;
@@ -1195,7 +1202,7 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
         cl_layout(L, G, mask, v_smem, d_smem, Y);
         const size_t bytes = (size_t)Y.total * sizeof(double);
         int maxc = 0;
-        cudaError_t e = cl_max_clusters(G, bytes, S->sm_count, &maxc);
+        cudaError_t e = cl_max_clusters(kern, G, bytes, S->sm_count, &maxc);
         if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
         // rounds of the batch x time of one system (falls with G, less than linearly; streaming
         // the pair rows from L2 instead of shared memory roughly doubles a pass)
@@ -1301,8 +1308,9 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         g_launches++;
-        CKC(allow_max_smem(k_integrate_cl));
-        CKC(cudaLaunchKernelEx(&cfg, k_integrate_cl, A));
+        ClKernel kern = cl_kernel(S);
+        CKC(allow_max_smem(kern));
+        CKC(cudaLaunchKernelEx(&cfg, kern, A));
     }
     CKC(cudaEventRecord(e1, S->stream));
     S->last_launches = dev ? 1 : 2;

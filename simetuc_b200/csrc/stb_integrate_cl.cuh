@@ -348,7 +348,10 @@ struct ClShared {
     long long prof[24];
 };
 
-__global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
+// COOP: the instance for systems with a cooperative (three-ion) process; the plain instance
+// carries none of that code (it costs registers: +5 % on the C2 sweep when compiled in).
+template <bool COOP>
+__global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     extern __shared__ __align__(16) double dyn[];
     __shared__ ClShared S;
     DevLattice& L = S.L;
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl(ClArgs A) {
             }
             __syncthreads();
         }
-        if (L.n_coop) {
+        if (COOP) {
             cl_coop_fields(L, Y, r_lo, cnt, zb, mult, lin_at, warp, lane);
             __syncthreads();
         }
