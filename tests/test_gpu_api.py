@@ -266,3 +266,34 @@ def test_average_rate_equations_match_oracle():
     pd = sim.simulate_power_dependence([1e6, 1e8], average=True)
     single = Simulations(cte).simulate_steady_state(average=True)
     assert np.allclose(pd[1].steady_state_populations, single.steady_state_populations, rtol=1e-9)
+
+
+def test_cooperative_process_through_the_reference_api(lattice_file_2S_2A):
+    """A settings tree with a cooperative S-S-A process (`conftest.py:26-117` has `coop1`) through
+    `setup_microscopic_eqs` and the reference-named solver entry points: the cooperative operands
+    are the oracle's (`precalculate.py:427-699`), the callbacks and `solve_pulse` use them."""
+    cte = configs.test_cte()
+    cte['lattice']['d_max_coop'] = np.inf
+    cte['energy_transfer']['coop1'].strength = 1e15
+    out = precalculate.setup_microscopic_eqs(cte, full_path=lattice_file_2S_2A)
+    (_, pop, iS, iA, abs_m, dec_m, ET, N_idx, jac, cET, cN, cJ) = out
+    op = oracle_operands(load_golden('sim_2S_2A'), cte, coop=True)
+    cM_ref, cN_ref, cJ_ref = op['coop']
+    assert cN_ref.shape[0] == 2 and np.array_equal(cN, cN_ref) and np.array_equal(cJ, cJ_ref)
+    assert np.allclose(cET.toarray(), cM_ref.toarray(), rtol=1e-14, atol=0)
+    y = load_golden('sim_2S_2A')['sim_y'][0]
+    f = odesolver._rate_eq_pulse(0, y, abs_m, dec_m, ET, N_idx, cET, cN)
+    ref = onp.rate_eq_pulse(0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], cM_ref, cN_ref)
+    assert np.all(np.abs(f - ref) <= 1e-12 * np.abs(ref).max())
+    J = odesolver._jac_rate_eq_pulse(0, y, abs_m, dec_m, ET, jac, cET, cJ)
+    Jref = onp.jac_rate_eq_pulse(0, y, op['abs'], op['decay'], op['ET'], op['jac_indices'], cM_ref, cJ_ref)
+    assert np.all(np.abs(J - Jref) <= 1e-12 * np.abs(Jref).max())
+    t = np.linspace(0, 1e-4, 20)
+    kw = dict(rtol=1e-8, atol=1e-15)
+    y_dev = odesolver.solve_pulse(t, pop, abs_m, dec_m, ET, N_idx, jac, cET, cN, cJ, nsteps=100000, **kw)
+    y_ref = onp.solve_pulse(t, pop.astype(float), op['abs'], op['decay'], op['ET'], op['N_indices'],
+                            op['jac_indices'], coop=(cM_ref, cN_ref, cJ_ref), nsteps=100000, **kw)
+    assert np.all(np.abs(y_dev - y_ref) <= 1e-4 * np.abs(y_ref) + 1e-12)
+    # operands of another system are refused, not silently solved without the term
+    with pytest.raises(TypeError):
+        odesolver._rate_eq_pulse(0, y, abs_m, dec_m, ET, N_idx, cET, np.zeros((0, 3), np.uint32))
