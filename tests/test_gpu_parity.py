@@ -409,3 +409,32 @@ def test_coop_trajectory_vs_lsoda():
     y_nc = onp.solve_relax(t_sol, yp_ref[-1], op['decay'], op['ET'], op['N_indices'], op['jac_indices'], **kw)
     assert np.abs(y_nc - y_ref).max() > 1e-3 * np.abs(y_ref).max()
     system.close()
+
+
+def test_solves_are_bit_reproducible():
+    """The integrators sum in a fixed order (no atomics, fixed warp / CTA order), so a repeated
+    solve must be bit-identical - which also makes this a cheap detector for data races in the
+    kernels (compute-sanitizer is not available on the GPU pool).  Batch of 8 systems of the
+    bench lattice (cluster integrator, 4 CTAs per system), pulse then a 60-point relaxation."""
+    import bench
+    cte = bench.make_cte()
+    powers = bench.powers_list()[::4]
+    lat = lattice.generate(cte, seed=2000)
+    runs = []
+    for rep in range(3):
+        system = precalculate.build_system(cte, lat, n_sys=len(powers))
+        for k, P in enumerate(powers):
+            for exc in cte['excitations']['NIR_980']:
+                exc.power_dens = P
+            system.set_abs_blocks(*precalculate.absorption_blocks(cte), system=k)
+        _, _, pop = system.ground_states()
+        y0 = np.tile(pop.astype(float), (len(powers), 1))
+        y_p, _, st_p = system.integrate(np.array([0.0, 1e-8]), y0, pulse=True, rtol=1e-8, atol=1e-15)
+        t = np.logspace(-8, -2, 60)
+        y, avg, st = system.integrate(t, y_p[:, -1], pulse=False, rtol=1e-8, atol=1e-15, want_avg=True)
+        system.close()
+        runs.append((y_p, y, avg, [(s['n_steps'], s['n_rhs'], s['n_jv']) for s in st_p + st]))
+    for other in runs[1:]:
+        assert other[3] == runs[0][3]
+        for a, b in zip(runs[0][:3], other[:3]):
+            assert np.array_equal(a, b)
