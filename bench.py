@@ -108,11 +108,22 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------- CPU arms
+def _single_thread():
+    """LSODA's dense LU goes through LAPACK: pin the BLAS pool to one thread so that `cores`
+    means what it says (and N worker processes do not oversubscribe the box N-fold)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:   # pragma: no cover
+        pass
+
+
 def _cpu_solve_one(args):
     """One system of the sweep through the oracle port (reference callbacks + scipy LSODA)."""
     seed, power = args
     import warnings
     warnings.simplefilter('ignore')
+    _single_thread()
     from oracle import oracle_np as onp
     from simetuc_b200 import lattice
     from tests.helpers import oracle_operands
@@ -151,8 +162,9 @@ def run_reference(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = max(1, min(os.cpu_count() or 1, N_POWERS))
+    cores = max(1, min(len(os.sched_getaffinity(0)), 16))
     powers = powers_list()
+    # bounded sample: one system per core and step, evenly spaced powers of the sweep
     idx = [int(round(i)) for i in np.linspace(0, N_POWERS - 1, cores)]
     jobs = [(2000, powers[i]) for i in idx]
     ctx = mp.get_context('fork')

@@ -480,7 +480,7 @@ class Simulations:
     # ------------------------------------------------------------------ batched sweeps
     def _solve_batch(self, lat, ctes: List[Any], device: int, dynamics: bool,
                      strengths: Optional[np.ndarray] = None, keep_y: bool = True,
-                     average: bool = False):
+                     average: bool = False, gpu_busy: Optional[threading.Event] = None):
         """Integrate `len(ctes)` systems that share `lat` in one batch on `device`.
         Each cte supplies its own absorption / decay blocks (and optionally ET strengths).
         Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics."""
@@ -508,12 +508,16 @@ class Simulations:
                 t_pulse = np.linspace(0, tf_p, 2, dtype=np.float64)
                 y_p, _, st_p = system.integrate(t_pulse, y0, pulse=True, rtol=rtol, atol=atol)
                 t_sol = np.logspace(np.log10(tf_p), np.log10(tf), N_steps, dtype=np.float64)
+                if gpu_busy is not None:
+                    gpu_busy.set()      # the long call: the GIL is free until it returns
                 y, avg, st = system.integrate(t_sol, y_p[:, -1], pulse=False, rtol=rtol, atol=atol,
                                               want_y=keep_y, want_avg=True)
                 t_out = t_sol - t_sol[0]
                 stats = [dict(pulse=a, relax=b) for a, b in zip(st_p, st)]
             else:
                 t_out = np.linspace(0, tf, N_steps)
+                if gpu_busy is not None:
+                    gpu_busy.set()
                 y, avg, st = system.integrate(t_out, y0, pulse=True, rtol=rtol, atol=atol,
                                               nsteps=1000, want_y=keep_y, want_avg=True)
                 stats = [dict(pulse=a) for a in st]
@@ -523,7 +527,8 @@ class Simulations:
             system.close()
 
     def _sweep_same_lattice(self, ctes: List[Any], dynamics: bool, keep_y: bool = True,
-                            strengths: Optional[np.ndarray] = None, average: bool = False):
+                            strengths: Optional[np.ndarray] = None, average: bool = False,
+                            gpu_busy: Optional[threading.Event] = None):
         """Systems sharing one lattice, dealt round-robin over `self.devices`."""
         gen_lattice = self.cte.get('gen_lattice', False)
         if average:
@@ -534,6 +539,7 @@ class Simulations:
         shards = [list(range(d, len(ctes), n_dev)) for d in range(n_dev)]
         jobs = [(lambda d=d, ids=ids: self._solve_batch(
             lat, [ctes[i] for i in ids], self.devices[d], dynamics, keep_y=keep_y, average=average,
+            gpu_busy=gpu_busy,
             strengths=None if strengths is None else strengths[ids])) for d, ids in enumerate(shards)]
         results = _run_on_devices(jobs, n_dev)
         out = [None] * len(ctes)
@@ -566,8 +572,13 @@ class Simulations:
                     exc.power_dens = power_dens
             light.append(cte)
         with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
+            busy = threading.Event()
             pending = pool.submit(self._sweep_same_lattice, light, dynamics=pulsed, keep_y=keep_y,
-                                  average=average)
+                                  average=average, gpu_busy=busy)
+            # copy only once the worker sits in its long solver call: before that it needs the GIL
+            # every few microseconds and a copying main thread would hold it 5 ms at a time
+            while not busy.wait(0.002) and not pending.done():
+                pass
             ctes = []
             for power_dens in power_dens_list:
                 cte = copy.deepcopy(self.cte)
