@@ -120,10 +120,12 @@ def _single_thread():
 
 def _cpu_solve_one(args):
     """One system of the sweep through the oracle port (reference callbacks + scipy LSODA)."""
-    seed, power = args
+    seed, power = args[:2]
+    mp_worker = len(args) > 2 and bool(args[2])
     import warnings
     warnings.simplefilter('ignore')
-    _single_thread()
+    if mp_worker is False:
+        _single_thread()
     from oracle import oracle_np as onp
     from simetuc_b200 import lattice
     from tests.helpers import oracle_operands
@@ -166,11 +168,15 @@ def run_reference(args):
     powers = powers_list()
     # bounded sample: one system per core and step, evenly spaced powers of the sweep
     idx = [int(round(i)) for i in np.linspace(0, N_POWERS - 1, cores)]
-    jobs = [(2000, powers[i]) for i in idx]
-    ctx = mp.get_context('fork')
+    jobs = [(2000, powers[i], True) for i in idx]
+    # fresh interpreters (a forked copy of a process that already runs BLAS / OpenMP threads can
+    # deadlock), one BLAS thread each so that `cores` means what it says
+    for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[var] = '1'
+    ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
         for _ in range(min(args.warmup, 1)):           # CPU needs no warm-up beyond imports
-            pool.map(_cpu_solve_one, [(2000, powers[0])] * 1)
+            pool.map(_cpu_solve_one, [(2000, powers[0], True)] * 1)
         t0 = time.time()
         for _ in range(args.steps):
             pool.map(_cpu_solve_one, jobs)

@@ -14,6 +14,7 @@
 #include "stb_integrate.cuh"
 #include "stb_integrate_cl.cuh"
 #include "stb_kernels.cuh"
+#include "stb_tma.cuh"
 
 static thread_local std::string g_err;
 // see simetuc_b200/__init__.py: one hardware work queue per stream in flight, if nobody chose otherwise
@@ -957,12 +958,35 @@ extern "C" int stb_from_planes(const stb_system* S, int32_t n, const double* y_p
     return STB_OK;
 }
 
+template <class K> static cudaError_t allow_max_smem(K kernel);
+
+// The TMA-fed kernels (stb_tma.cuh) serve dense single-multipolarity blocks whose rows are read
+// by whole warps; by default from 64 MB of pair data upwards (below that the stream is L2-resident
+// and the register version has less fixed cost).  STB_TMA=0 / 1 forces the choice.
+static bool use_tma(const stb_system* S) {
+    const bool eligible = S->hL.dense && S->hL.n_mult == 1 && S->hL.lpr == 32;
+    if (const char* env = getenv("STB_TMA")) return eligible && atoi(env) != 0;
+    return eligible && S->stream_bytes >= (int64_t)64 << 20;
+}
+
+// one persistent CTA per SM; STB_TMA_GRID overrides the CTA count (tests: several row tiles per CTA)
+static dim3 tma_grid(const stb_system* S, int n) {
+    int bx = S->sm_count;
+    if (const char* env = getenv("STB_TMA_GRID")) bx = std::max(1, atoi(env));
+    return dim3(bx, n, 1);
+}
+
 static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* y, double* out, double* F) {
     OpArgs A;
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = nullptr; A.Fy = nullptr; A.out = out; A.F = F;
     g_launches++;
-    k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    if (use_tma(S)) {
+        CK(allow_max_smem(k_op_tma<false>));
+        k_op_tma<false><<<tma_grid(S, n), STB_TMA_NT, STB_TMA_DYN_BYTES, S->stream>>>(A);
+    } else {
+        k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    }
     CK(cudaGetLastError());
     if (S->hL.n_coop) {
         g_launches++;
@@ -979,7 +1003,12 @@ static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = v; A.Fy = Fy; A.out = out; A.F = nullptr;
     g_launches++;
-    k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    if (use_tma(S)) {
+        CK(allow_max_smem(k_op_tma<true>));
+        k_op_tma<true><<<tma_grid(S, n), STB_TMA_NT, STB_TMA_DYN_BYTES, S->stream>>>(A);
+    } else {
+        k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
+    }
     CK(cudaGetLastError());
     if (S->hL.n_coop) {
         g_launches++;

@@ -438,3 +438,61 @@ def test_solves_are_bit_reproducible():
         assert other[3] == runs[0][3]
         for a, b in zip(runs[0][:3], other[:3]):
             assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- TMA-fed RHS / Jv (stb_tma.cuh)
+@pytest.mark.parametrize('tag,pname', [('240S_108A', 'test'), ('240S_108A', 'sim')])
+def test_tma_kernels_vs_golden(tag, pname, monkeypatch):
+    """`STB_TMA=1` routes RHS / Jv of a dense lattice through the bulk-copy (TMA) kernels; they
+    must reproduce the reference's golden RHS / Jv like the register kernels do, for a batch."""
+    g = load_golden(tag)
+    cte = getattr(configs, pname + '_cte')()
+    system = make_system(g, cte)
+    system.set_batch(3)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    y, v = g[pname + '_y'], g[pname + '_v']
+    monkeypatch.setenv('STB_TMA', '0')
+    f0, j0 = system.rhs(y, pulse=True), system.jv(y, v, pulse=True)
+    monkeypatch.setenv('STB_TMA', '1')
+    for pulse, key in ((True, '_f_pulse'), (False, '_f_relax')):
+        f = system.rhs(y, pulse=pulse)
+        ref = g[pname + key]
+        assert np.all(np.abs(f - ref) <= 1e-12 * np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+    jv = system.jv(y, v, pulse=True)
+    ref = g[pname + '_jv_pulse']
+    assert np.all(np.abs(jv - ref) <= 1e-12 * np.abs(ref).max(axis=1, keepdims=True) + 1e-300)
+    assert np.all(np.abs(system.rhs(y, pulse=True) - f0) <= 1e-13 * np.abs(f0).max())
+    assert np.all(np.abs(jv - j0) <= 1e-13 * np.abs(j0).max())
+    system.close()
+
+
+def test_tma_kernels_multi_chunk_vs_oracle(monkeypatch):
+    """A lattice whose rows span several 512-column chunks and several row tiles per CTA range
+    (N_uc=14, 40 % Yb, 2 % Tm: about 1650 Yb + 80 Tm): TMA kernels against the oracle's
+    `rate_eq_pulse` / Jacobian-vector product on the same operands, and against the register kernels."""
+    cte = configs.yb_tm_cte(N_uc=14, S_conc=40.0, A_conc=2.0)
+    lat = lattice.generate(cte, seed=7100, with_distances=True)
+    g = dict(ion_type=lat.ion_type, dist_array=lat.distances(), info=np.array([2, 9]))
+    op = oracle_operands(g, cte)
+    system = precalculate.build_system(cte, lat, n_sys=1)
+    assert system.bytes_per_pair == 8
+    rng = np.random.default_rng(7100)
+    N = system.N
+    y = 10.0 ** rng.uniform(-12, 0, N)
+    v = rng.standard_normal(N)
+    cM, cN, cJ = op['coop']
+    f_ref = onp.rate_eq_pulse(0.0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], cM, cN)
+    jv_ref = onp.jac_vec(y, v, op['abs'] + op['decay'], op['ET'], op['N_indices'])
+    res = {}
+    for mode in ('0', '1', '37'):
+        monkeypatch.setenv('STB_TMA', mode)
+        if mode == '37':                 # 37 CTAs: 44 Yb rows per CTA = three row tiles each
+            monkeypatch.setenv('STB_TMA_GRID', mode)
+        res[mode] = (system.rhs(y, pulse=True), system.jv(y, v, pulse=True))
+        assert np.all(np.abs(res[mode][0] - f_ref) <= 1e-12 * np.abs(f_ref).max())
+        assert np.all(np.abs(res[mode][1] - jv_ref) <= 1e-12 * np.abs(jv_ref).max())
+    assert np.all(np.abs(res['1'][0] - res['0'][0]) <= 1e-13 * np.abs(f_ref).max())
+    assert np.all(np.abs(res['37'][1] - res['0'][1]) <= 1e-13 * np.abs(jv_ref).max())
+    assert not np.array_equal(res['1'][0], np.zeros(N))
+    system.close()

@@ -1,19 +1,32 @@
-"""RHS + Jv kernels on the HBM-bound lattice (N_uc=40, 25% Yb, 0.3% Tm) - ncu target."""
+"""RHS + Jv kernels on the HBM-bound lattice (N_uc=40, 25% Yb, 0.3% Tm) - timing and ncu target.
+Usage: prof_rhs_large.py [modes]   modes = comma list of STB_TMA values (default "0,1")."""
 import ctypes as C
+import os
 import sys
 sys.path.insert(0, '.')
 import torch
 from simetuc_b200 import _lib, configs, lattice, precalculate
-cte = configs.yb_tm_cte(N_uc=40, S_conc=25.0, A_conc=0.3)
+modes = (sys.argv[1] if len(sys.argv) > 1 else '0,1').split(',')
+n_uc = int(os.environ.get('PROF_NUC', '40'))
+cte = configs.yb_tm_cte(N_uc=n_uc, S_conc=25.0, A_conc=0.3)
 lat = lattice.generate(cte, seed=4000)
 system = precalculate.build_system(cte, lat, n_sys=1)
 N = system.N
 y = torch.rand(1, N, dtype=torch.float64, device='cuda') * 1e-3
 v = torch.rand(1, N, dtype=torch.float64, device='cuda')
 out = torch.empty_like(y)
+ref = None
 ms = C.c_float()
-for _ in range(2):
-    _lib.check(system.lib.stb_rhs_dev(system.handle, 0, 1, 1, y.data_ptr(), out.data_ptr(), 3, C.byref(ms)))
-    r = ms.value
-    _lib.check(system.lib.stb_jv_dev(system.handle, 0, 1, 1, y.data_ptr(), v.data_ptr(), out.data_ptr(), 3, C.byref(ms)))
-print('pairs', system.n_pairs, 'N', N, 'rhs ms', r, 'jv ms', ms.value)
+for mode in modes:
+    os.environ['STB_TMA'] = mode
+    for _ in range(2):
+        _lib.check(system.lib.stb_rhs_dev(system.handle, 0, 1, 1, y.data_ptr(), out.data_ptr(), 5, C.byref(ms)))
+        r = ms.value
+        f = out.clone()
+        _lib.check(system.lib.stb_jv_dev(system.handle, 0, 1, 1, y.data_ptr(), v.data_ptr(), out.data_ptr(), 5, C.byref(ms)))
+    gb = system.n_pairs * 8 / 1e9
+    if ref is None:
+        ref = (f, out.clone())
+    err = max(float((f - ref[0]).abs().max() / ref[0].abs().max()), float((out - ref[1]).abs().max() / ref[1].abs().max()))
+    print('STB_TMA=%s pairs %d N %d rhs %.4f ms %.0f GB/s  jv %.4f ms %.0f GB/s  max rel diff vs first mode %.2e' % (
+        mode, system.n_pairs, N, r, gb / r * 1e3, ms.value, gb / ms.value * 1e3, err))
