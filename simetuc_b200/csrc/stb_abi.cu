@@ -976,6 +976,18 @@ static dim3 tma_grid(const stb_system* S, int n) {
     return dim3(bx, n, 1);
 }
 
+// ring geometry of the TMA kernels: STB_TMA_KC columns per stage (multiple of 32), STB_TMA_STAGES
+static size_t tma_setup(OpArgs& A) {
+    int kc = STB_TMA_KC, st = STB_TMA_STAGES;
+    if (const char* env = getenv("STB_TMA_KC")) kc = std::max(32, atoi(env) / 32 * 32);
+    if (const char* env = getenv("STB_TMA_STAGES")) st = std::min(STB_TMA_MAX_STAGES, std::max(2, atoi(env)));
+    while (st > 2 && tma_dyn_bytes(kc, st) > 220 * 1024) --st;
+    A.tma_kc = kc; A.tma_stages = st;
+    const char* diag = getenv("STB_TMA_DIAG");
+    A.tma_diag = diag ? atoi(diag) : 0;
+    return tma_dyn_bytes(kc, st);
+}
+
 static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* y, double* out, double* F) {
     OpArgs A;
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
@@ -983,7 +995,8 @@ static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* 
     g_launches++;
     if (use_tma(S)) {
         CK(allow_max_smem(k_op_tma<false>));
-        k_op_tma<false><<<tma_grid(S, n), STB_TMA_NT, STB_TMA_DYN_BYTES, S->stream>>>(A);
+        const size_t dyn = tma_setup(A);
+        k_op_tma<false><<<tma_grid(S, n), STB_TMA_NT, dyn, S->stream>>>(A);
     } else {
         k_rhs<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     }
@@ -1005,7 +1018,8 @@ static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y
     g_launches++;
     if (use_tma(S)) {
         CK(allow_max_smem(k_op_tma<true>));
-        k_op_tma<true><<<tma_grid(S, n), STB_TMA_NT, STB_TMA_DYN_BYTES, S->stream>>>(A);
+        const size_t dyn = tma_setup(A);
+        k_op_tma<true><<<tma_grid(S, n), STB_TMA_NT, dyn, S->stream>>>(A);
     } else {
         k_jv<<<op_grid(S, n), STB_NT, 0, S->stream>>>(A);
     }
@@ -1464,6 +1478,15 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         if (stage_bytes + own_bytes(G) + 64 <= smem_cap) resident = 1;
     }
     if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64;
+    // dense rows read by whole warps: the pair stream goes through the TMA ring (stb_tma.cuh), the
+    // gathered vector stays in global memory / L1
+    OpArgs tma_args;
+    const int tma = use_tma(S) ? 1 : 0;
+    if (tma) {
+        staged = 0;
+        resident = 0;
+        dyn_bytes = tma_setup(tma_args);
+    }
     int n_groups = std::max(1, std::min(max_ctas / G, n));
     const int grid = n_groups * G;
     CK(allow_max_smem(k_integrate));
@@ -1527,6 +1550,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.nsteps = nsteps > 0 ? nsteps : 1000;
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
+    A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKI(cudaEventRecord(e0, S->stream));

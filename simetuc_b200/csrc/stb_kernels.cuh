@@ -14,6 +14,7 @@ struct OpArgs {
     const double* Fy;// [n][NF]  (Jv: fields at y, from a previous RHS pass)
     double* out;     // [n][N]
     double* F;       // [n][NF] (RHS: fields at y, may be null)
+    int tma_kc, tma_stages, tma_diag;   // stb_tma.cuh only
 };
 
 // dy = (abs +) decay y + ET (y_i * y_j): odesolver._rate_eq / _rate_eq_pulse (odesolver.py:33-71)

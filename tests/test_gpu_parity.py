@@ -496,3 +496,27 @@ def test_tma_kernels_multi_chunk_vs_oracle(monkeypatch):
     assert np.all(np.abs(res['37'][1] - res['0'][1]) <= 1e-13 * np.abs(jv_ref).max())
     assert not np.array_equal(res['1'][0], np.zeros(N))
     system.close()
+
+
+def test_tma_inside_grid_integrator(monkeypatch):
+    """The persistent grid integrator (`k_integrate`, large lattices) with its pair rows fed by the
+    TMA ring must integrate exactly like the register-fed version: same rows per CTA, same
+    per-lane summation order.  Forced onto a small dense lattice (cluster integrator off)."""
+    g = load_golden('240S_108A')
+    cte = configs.test_cte()
+    system = make_system(g, cte)
+    _, _, pop = system.ground_states()
+    tf = onp.t_simulation(cte['decay'])
+    t_pulse, t_sol = onp.time_grids(1e-8, tf, 50)
+    monkeypatch.setenv('STB_CLUSTER', '0')
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('STB_TMA', mode)
+        y_p, _, st_p = system.integrate(t_pulse, pop.astype(float), pulse=True, rtol=1e-8, atol=1e-15)
+        y, _, st = system.integrate(t_sol, y_p[0, -1], pulse=False, rtol=1e-8, atol=1e-15)
+        assert st_p[0]['status'] == 0 and st[0]['status'] == 0
+        res[mode] = (y_p[0, -1], y[0], st[0]['n_steps'])
+    assert res['0'][2] == res['1'][2]
+    assert np.all(np.abs(res['1'][0] - res['0'][0]) <= 1e-12 * np.abs(res['0'][0]) + 1e-300)
+    assert np.all(np.abs(res['1'][1] - res['0'][1]) <= 1e-9 * np.abs(res['0'][1]) + 1e-18)
+    system.close()

@@ -26,7 +26,7 @@ def main(rep, out):
                     vals[k] = (r[hdr.index(k)], units[hdr.index(k)])
                     fh.write('  %-62s %s %s\n' % (k, r[hdr.index(k)], units[hdr.index(k)]))
             try:
-                t_ms = float(vals['gpu__time_duration.sum'][0])
+                t_ms = float(vals['gpu__time_duration.sum'][0]) * {'ms': 1.0, 'us': 1e-3, 'ns': 1e-6, 's': 1e3}[vals['gpu__time_duration.sum'][1]]
                 scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}
                 rd = float(vals['dram__bytes_read.sum'][0]) * scale[vals['dram__bytes_read.sum'][1]]
                 wr = float(vals['dram__bytes_write.sum'][0]) * scale[vals['dram__bytes_write.sum'][1]]
