@@ -413,8 +413,8 @@ def large_lattice_roofline(device, peaks, peak_src):
         res[name] = {'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                      'frac': gbs / peaks['hbm_gbs'], 'ms_per_launch': ms.value,
                      'algorithmic_bytes_per_launch': alg, 'frac_of_8TBs_nominal': gbs / 8000.0,
-                     'traffic': 4.70e9,
-                     'traffic_source': 'profiles/r01_ncu_rhs_jv_dense.txt (ncu --set full: dram read+write per launch)'}
+                     'traffic': 4.71e9,
+                     'traffic_source': 'profiles/r01_ncu_rhs_jv_tma.txt (ncu --set full of k_op_tma: dram read+write per launch)'}
     res['workload'] = 'N_uc=40 25%%Yb 0.3%%Tm: %d ions, %d states, %d ordered pairs, %.2f GB pair stream; ' \
                       'inputs >> L2' % (system.n_ions, N, system.n_pairs, system.stream_bytes / 1e9)
     res['peak_source'] = peak_src

@@ -985,7 +985,7 @@ static size_t tma_setup(OpArgs& A) {
     A.tma_kc = kc; A.tma_stages = st;
     const char* diag = getenv("STB_TMA_DIAG");
     A.tma_diag = diag ? atoi(diag) : 0;
-    return tma_dyn_bytes(kc, st);
+    return tma_dyn_bytes(kc, st) + 128;   // slack: see cl_choose
 }
 
 static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* y, double* out, double* F) {
@@ -1197,7 +1197,7 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
     cudaFuncAttributes fa;
     ClKernel kern = cl_kernel(S);
     if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return false; }
-    const size_t cap = 232448 - fa.sharedSizeBytes - 64;   // 227 KB per CTA
+    const size_t cap = 232448 - fa.sharedSizeBytes - 256;  // 227 KB per CTA, minus the slack below
     int want_res = 1;
     if (const char* env = getenv("STB_RESIDENT")) want_res = atoi(env) != 0;
     ClPlan best;
@@ -1243,7 +1243,10 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
             }
         }
         cl_layout(L, G, mask, v_smem, d_smem, Y);
-        const size_t bytes = (size_t)Y.total * sizeof(double);
+        // 128 B of slack: the compiler may align the dynamic shared memory base above the end of the
+        // static variables (any `extern __shared__ __align__(n)` in the library does it for every
+        // kernel), and the layout must still fit behind it
+        const size_t bytes = (size_t)Y.total * sizeof(double) + 128;
         int maxc = 0;
         cudaError_t e = cl_max_clusters(kern, G, bytes, S->sm_count, &maxc);
         if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
@@ -1449,7 +1452,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     int staged = stage_bytes <= 96 * 1024;
     if (const char* env = getenv("STB_STAGE")) staged = atoi(env) != 0 && stage_bytes <= 160 * 1024;
     int resident = 0;
-    size_t dyn_bytes = staged ? stage_bytes : 0;
+    size_t dyn_bytes = staged ? stage_bytes + 128 : 0;     // slack: see cl_choose
     auto own_bytes = [&](int Gc) -> size_t {     // largest resident footprint of a CTA in a group of Gc
         size_t worst = 0;
         for (int c = 0; c < Gc; ++c) {
@@ -1477,7 +1480,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         // resident costs more concurrency than it gains, so residency is used when it is free
         if (stage_bytes + own_bytes(G) + 64 <= smem_cap) resident = 1;
     }
-    if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64;
+    if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64 + 128;
     int n_groups = std::max(1, std::min(max_ctas / G, n));
     const int grid = n_groups * G;
     CK(allow_max_smem(k_integrate));

@@ -462,6 +462,12 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     };
     double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(STB_KRYLOV + 1) * PO;
 
+#ifndef STB_CL_NO_ZEROFILL
+    // start from a defined state: nothing below may depend on what an earlier kernel left in the
+    // SM's shared memory (padding columns are multiplied by g = 0, and 0 * NaN is not 0)
+    for (int i = tid; i < Y.total; i += STB_NT) dyn[i] = 0.0;
+    __syncthreads();
+#endif
     for (int i = tid; i < 2 * Y.NZ; i += STB_NT) zy[i] = 0.0;     // zy and zv are contiguous
     for (int i = tid; i < Y.part - Y.F; i += STB_NT) F[i] = 0.0;  // unused field slots and pieces of idle warps stay 0
     for (int k = tid; k < n_own; k += STB_NT) {
