@@ -466,6 +466,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     // start from a defined state: nothing below may depend on what an earlier kernel left in the
     // SM's shared memory (padding columns are multiplied by g = 0, and 0 * NaN is not 0)
     for (int i = tid; i < Y.total; i += STB_NT) dyn[i] = 0.0;
+#ifdef STB_TEST_ALIGN128           // test builds only: the 32 B gap the alignment request opens below dyn
+    if (tid < 4) dyn[-1 - tid] = 0.0;
+#endif
     __syncthreads();
 #endif
     for (int i = tid; i < 2 * Y.NZ; i += STB_NT) zy[i] = 0.0;     // zy and zv are contiguous
