@@ -1481,6 +1481,16 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         if (stage_bytes + own_bytes(G) + 64 <= smem_cap) resident = 1;
     }
     if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64 + 128;
+    // dense rows read by whole warps: the pair stream goes through the TMA ring (stb_tma.cuh), the
+    // gathered vector stays in global memory / L1.  STB_TMA_INT=0 keeps the register-fed passes.
+    OpArgs tma_args;
+    int tma = use_tma(S) ? 1 : 0;
+    if (const char* env = getenv("STB_TMA_INT")) tma = tma && atoi(env) != 0;
+    if (tma) {
+        staged = 0;
+        resident = 0;
+        dyn_bytes = tma_setup(tma_args);
+    }
     int n_groups = std::max(1, std::min(max_ctas / G, n));
     const int grid = n_groups * G;
     CK(allow_max_smem(k_integrate));
@@ -1544,6 +1554,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.nsteps = nsteps > 0 ? nsteps : 1000;
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
+    A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKI(cudaEventRecord(e0, S->stream));

@@ -10,6 +10,7 @@
 // uniform across the group by construction.
 #pragma once
 #include "stb_coop.cuh"
+#include "stb_tma.cuh"
 
 #define STB_KRED (STB_KRYLOV + 4)
 #define STB_NEWTON_MAXIT 4
@@ -46,6 +47,8 @@ struct IntArgs {
     int resident;             // the CTA's pair rows are copied to shared memory once
     int staged;               // gather vector staged in shared memory (N*8 bytes dynamic smem)
     long long* prof;          // [n_sys][8] clock64 cycles per phase (thread 0 of CTA 0), may be null
+    int tma;                  // dense rows fed by bulk copies through a shared-memory ring (stb_tma.cuh)
+    int tma_kc, tma_stages;
 };
 
 __host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
@@ -345,44 +348,59 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         return zs;
     };
     const int n_own_A = sl_hi[1] - sl_lo[1];
+    // ---- dense rows fed by the TMA engine (stb_tma.cuh): the CTA's own rows in tiles of <= 16,
+    //      every warp reduces one row per tile and runs `epi` on it -----------------------------
+    TmaRing R;
+    if (A.tma) tma_ring_init(R, zs, A.tma_kc, A.tma_stages, 0);
+    auto tma_rows = [&](const double* zg, double fscale, auto&& epi) {
+        tma_rows_pass(R, L, r_lo, r_hi, 1, zg, fscale, warp, lane, epi);   // activator rows first
+    };
     auto rhs_phase = [&](const double* z, double* fout, int mode, double c, double (&part)[2]) {
         part[0] = 0.0;
         part[1] = 0.0;
         const double* zg = stage(z);
+        // per-ion epilogue of a row handled by W >= 16 lanes: lane j <-> state j of the ion
+        auto rhs_row = [&](int T, int q, bool valid, int W, int gl, double fl) {
+            const int s = L.s[T], nT = L.n[T];
+            const bool act = valid && gl < s;
+            const int e = L.off[T] + (gl < s ? gl : 0) * nT + (valid ? q : nT - 1);
+            const double yj = gl < s ? z[e] : 0.0;
+            const double fj = coop_rhs(L, P, T, W, gl, yj, fl);
+            if (act) fout[e] = fj;
+            if (valid && gl < L.nf[T]) F[L.foff[T] + gl * nT + q] = fl;
+            if (mode == 1) {
+                double ai[STB_MAXS];
+                coop_block_inverse(L, P, T, W, gl, fl, c, ai);
+                double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
+                if (act) {
+#pragma unroll
+                    for (int b = 0; b < STB_MAXS; ++b)
+                        if (b < s) Mp[(int64_t)(gl * s + b) * nT] = ai[b];
+                }
+                const double rj = act ? c * fj - psi[e] - dd[e] : 0.0;
+                const double xy = coop_apply_rows(ai, s, W, rj);
+                if (act) {
+                    const double x = xy / scale[e];
+                    wv[e] = x;
+                    gv[e] = xy;
+                    part[0] = fma(x, x, part[0]);
+                    if (!isfinite(fj)) part[1] = 1.0;
+                }
+            }
+        };
+        if (A.tma) {
+            tma_rows(zg, 1.0, rhs_row);
+            return;
+        }
         for (int task = warp; task < n_own_slices; task += STB_NW) {
             int T = task < n_own_A;          // activator rows first (the expensive epilogues)
             int slice = T ? sl_lo[1] + task : sl_lo[0] + task - n_own_A;
             if (L.lpr >= 16) {      // warp-cooperative epilogue: lane j <-> state j of the ion
-                const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+                const int W = L.lpr, gl = lane & (W - 1);
                 const double fl = A.resident ? slice_fields_resident(L, T, slice, zg, lane, 1.0, nullptr)
                                              : slice_fields(L, T, slice, zg, lane, 1.0, nullptr);
                 const int q = slice * L.R + lane / W;
-                const bool valid = q < nT;
-                const bool act = valid && gl < s;
-                const int e = L.off[T] + (gl < s ? gl : 0) * nT + (valid ? q : nT - 1);
-                const double yj = gl < s ? z[e] : 0.0;
-                const double fj = coop_rhs(L, P, T, W, gl, yj, fl);
-                if (act) fout[e] = fj;
-                if (valid && gl < L.nf[T]) F[L.foff[T] + gl * nT + q] = fl;
-                if (mode == 1) {
-                    double ai[STB_MAXS];
-                    coop_block_inverse(L, P, T, W, gl, fl, c, ai);
-                    double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
-                    if (act) {
-#pragma unroll
-                        for (int b = 0; b < STB_MAXS; ++b)
-                            if (b < s) Mp[(int64_t)(gl * s + b) * nT] = ai[b];
-                    }
-                    const double rj = act ? c * fj - psi[e] - dd[e] : 0.0;
-                    const double xy = coop_apply_rows(ai, s, W, rj);
-                    if (act) {
-                        const double x = xy / scale[e];
-                        wv[e] = x;
-                        gv[e] = xy;
-                        part[0] = fma(x, x, part[0]);
-                        if (!isfinite(fj)) part[1] = 1.0;
-                    }
-                }
+                rhs_row(T, q, q < L.n[T], W, gl, fl);
                 continue;
             }
             double Fq[2 * STB_MAXC];
@@ -426,29 +444,38 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     // ---- Arnoldi phase: wbuf = Minv (v - c J v) / scale with v = inrm * gv ------------------
     auto arnoldi_phase = [&](double inrm, double c) {
         const double* zg = stage(gv);
+        // M^-1 (I - cJ) v = v - c Minv k,  k = coupling of the ion to its partners' v
+        auto arn_row = [&](int T, int q, bool valid, int W, int gl, double fvl) {
+            const int s = L.s[T], nT = L.n[T];
+            const bool act = valid && gl < s;
+            const int qc = valid ? q : nT - 1;
+            const int e = L.off[T] + (gl < s ? gl : 0) * nT + qc;
+            const double yj = gl < s ? yk[e] : 0.0;
+            const double kj = coop_coupling(L, P, T, W, gl, yj, fvl);
+            const double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + qc;
+            const int row = gl < s ? gl : 0;
+            double mk = 0.0;
+            for (int b = 0; b < s; ++b)
+                mk = fma(Mp[(int64_t)(row * s + b) * nT], __shfl_sync(FULL, kj, b, W), mk);
+            if (act) wbuf[e] = (inrm * gv[e] - c * mk) / scale[e];
+        };
+        if (A.tma) {
+            long long t0_ = clock64();
+            tma_rows(zg, inrm, arn_row);
+            if (threadIdx.x == 0) C.prof[6] += clock64() - t0_;
+            return;
+        }
         for (int task = warp; task < n_own_slices; task += STB_NW) {
             int T = task < n_own_A;
             int slice = T ? sl_lo[1] + task : sl_lo[0] + task - n_own_A;
             if (L.lpr >= 16) {
-                // M^-1 (I - cJ) v = v - c Minv k,  k = coupling of the ion to its partners' v
-                const int W = L.lpr, gl = lane & (W - 1), s = L.s[T], nT = L.n[T];
+                const int W = L.lpr, gl = lane & (W - 1);
                 long long t0_ = clock64();
                 const double fvl = A.resident ? slice_fields_resident(L, T, slice, zg, lane, inrm, nullptr)
                                                : slice_fields(L, T, slice, zg, lane, inrm, nullptr);
                 if (threadIdx.x == 0) C.prof[6] += clock64() - t0_;
                 const int q = slice * L.R + lane / W;
-                const bool valid = q < nT;
-                const bool act = valid && gl < s;
-                const int qc = valid ? q : nT - 1;
-                const int e = L.off[T] + (gl < s ? gl : 0) * nT + qc;
-                const double yj = gl < s ? yk[e] : 0.0;
-                const double kj = coop_coupling(L, P, T, W, gl, yj, fvl);
-                const double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + qc;
-                const int row = gl < s ? gl : 0;
-                double mk = 0.0;
-                for (int b = 0; b < s; ++b)
-                    mk = fma(Mp[(int64_t)(row * s + b) * nT], __shfl_sync(FULL, kj, b, W), mk);
-                if (act) wbuf[e] = (inrm * gv[e] - c * mk) / scale[e];
+                arn_row(T, q, q < L.n[T], W, gl, fvl);
                 continue;
             }
             double Fv[2 * STB_MAXC];

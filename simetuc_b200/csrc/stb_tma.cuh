@@ -192,53 +192,35 @@ __device__ __forceinline__ void tma_produce_block(TmaRing& R, const PairBlock& B
     }
 }
 
-template <bool JV>
-__global__ void __launch_bounds__(STB_TMA_NT, 1) k_op_tma(OpArgs A) {
-    // NB: no __align__ here.  All `extern __shared__` arrays of a translation unit share one symbol,
-    // and a 128 B alignment request moved the dynamic shared memory base of EVERY kernel of the
-    // library (the cluster integrator's by 32 B).  Bulk copies need 16 B, which the base has.
-#ifdef STB_TEST_ALIGN128       // test builds only: reproduces the shifted base (tools/repro_check.py)
-    extern __shared__ __align__(128) double tma_smem_d[];
-#else
-    extern __shared__ double tma_smem_d[];
-#endif
-    unsigned char* tma_smem = (unsigned char*)tma_smem_d;
-    __shared__ DevLattice L;
-    __shared__ SysParams P;
-    TmaRing R;
-    R.kc = A.tma_kc;
-    R.stages = A.tma_stages;
-    R.diag = A.tma_diag;
-    R.stage = 0;
-    R.ph = 0;
-    R.ring = (double*)tma_smem;
-    R.full = (uint64_t*)(tma_smem + tma_ring_bytes(R.kc, R.stages));
+// carve the ring out of dynamic shared memory and initialise its barriers (all threads call)
+__device__ __forceinline__ void tma_ring_init(TmaRing& R, void* smem, int kc, int stages, int diag) {
+    R.kc = kc; R.stages = stages; R.diag = diag;
+    R.stage = 0; R.ph = 0;
+    R.ring = (double*)smem;
+    R.full = (uint64_t*)((unsigned char*)smem + tma_ring_bytes(kc, stages));
     R.empty = R.full + STB_TMA_MAX_STAGES;
-    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
-        ((int*)&L)[i] = ((const int*)A.L)[i];
     if (threadIdx.x == 0) {
-        for (int s = 0; s < R.stages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&R.full[s], STB_TMA_PROD);
             mbar_init(&R.empty[s], STB_TMA_ROWS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int b = blockIdx.y;
-    load_sys_params(L, A.blocks, A.strengths, A.first + b, A.pulse, P);
-    __syncthreads();
-    const double* y = A.y + (int64_t)b * L.N;
-    const double* x = JV ? A.v + (int64_t)b * L.N : y;       // the vector whose fields are streamed
-    const double* Fy = JV ? A.Fy + (int64_t)b * L.NF : nullptr;
-    double* out = A.out + (int64_t)b * L.N;
-    double* F = (!JV && A.F) ? A.F + (int64_t)b * L.NF : nullptr;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+}
+
+// One pass over the CTA's rows [r_lo[T], r_hi[T]) of both types (type `first_T` first): for every
+// row, `epi(T, q, true, 32, lane, fl)` is called by the row's consumer warp with lane k holding
+// field slot k (times fscale) of the row, gathered from `x`.  All 16 warps of the CTA call this
+// together with the same arguments; warps 14, 15 produce and never call `epi`.
+template <class Epi>
+__device__ __forceinline__ void tma_rows_pass(TmaRing& R, const DevLattice& L, const int* r_lo, const int* r_hi,
+                                              int first_T, const double* x, double fscale, int w, int lane,
+                                              Epi&& epi) {
     const bool producer = w >= STB_TMA_ROWS;
-    for (int T = 0; T < 2; ++T) {
-        const int nT = L.n[T];
-        const int r0 = (int)((int64_t)blockIdx.x * nT / gridDim.x);
-        const int r1 = (int)((int64_t)(blockIdx.x + 1) * nT / gridDim.x);
-        const int rows = r1 - r0;
+    for (int Ti = 0; Ti < 2; ++Ti) {
+        const int T = Ti == 0 ? first_T : 1 - first_T;
+        const int r0 = r_lo[T], rows = r_hi[T] - r_lo[T];
         if (rows <= 0) continue;
         const int ntile = (rows + STB_TMA_ROWS - 1) / STB_TMA_ROWS;
         for (int tile = 0; tile < ntile; ++tile) {
@@ -253,7 +235,6 @@ __global__ void __launch_bounds__(STB_TMA_NT, 1) k_op_tma(OpArgs A) {
                 continue;
             }
             const bool has_row = w < RT;
-            const int q = has_row ? t0 + w : t0;
             int slot0 = 0;
             double fl = 0.0;
             for (int U = 0; U < 2; ++U) {
@@ -280,25 +261,59 @@ __global__ void __launch_bounds__(STB_TMA_NT, 1) k_op_tma(OpArgs A) {
                     }
 #pragma unroll
                     for (int s = 0; s < STB_MAXC; ++s)
-                        if (s < ns && lane == slot0 + s) fl = acc[s];
+                        if (s < ns && lane == slot0 + s) fl = acc[s] * fscale;
                 }
                 slot0 += ns;
             }
-            if (!has_row) continue;
-            // warp-cooperative epilogue: lane j <-> state j of ion q, lane k <-> field slot k
-            const int s = L.s[T];
-            const int e = L.off[T] + (lane < s ? lane : 0) * nT + q;
-            if (!JV) {
-                const double yj = lane < s ? y[e] : 0.0;
-                const double fj = coop_rhs(L, P, T, 32, lane, yj, fl);
-                if (lane < s) out[e] = fj;
-                if (F && lane < L.nf[T]) F[L.foff[T] + lane * nT + q] = fl;
-            } else {
-                const double yj = lane < s ? y[e] : 0.0, vj = lane < s ? x[e] : 0.0;
-                const double fyl = lane < L.nf[T] ? Fy[L.foff[T] + lane * nT + q] : 0.0;
-                const double oj = coop_jv(L, P, T, 32, lane, yj, vj, fyl, fl);
-                if (lane < s) out[e] = oj;
-            }
+            if (has_row) epi(T, t0 + w, true, 32, lane, fl);
         }
     }
+}
+
+template <bool JV>
+__global__ void __launch_bounds__(STB_TMA_NT, 1) k_op_tma(OpArgs A) {
+    // NB: no __align__ here.  All `extern __shared__` arrays of a translation unit share one symbol,
+    // and a 128 B alignment request moved the dynamic shared memory base of EVERY kernel of the
+    // library (the cluster integrator's by 32 B).  Bulk copies need 16 B, which the base has.
+#ifdef STB_TEST_ALIGN128       // test builds only: reproduces the shifted base (tools/repro_check.py)
+    extern __shared__ __align__(128) double tma_smem_d[];
+#else
+    extern __shared__ double tma_smem_d[];
+#endif
+    __shared__ DevLattice L;
+    __shared__ SysParams P;
+    for (int i = threadIdx.x; i < (int)(sizeof(DevLattice) / 4); i += blockDim.x)
+        ((int*)&L)[i] = ((const int*)A.L)[i];
+    TmaRing R;
+    tma_ring_init(R, tma_smem_d, A.tma_kc, A.tma_stages, A.tma_diag);     // includes __syncthreads
+    const int b = blockIdx.y;
+    load_sys_params(L, A.blocks, A.strengths, A.first + b, A.pulse, P);
+    __syncthreads();
+    const double* y = A.y + (int64_t)b * L.N;
+    const double* x = JV ? A.v + (int64_t)b * L.N : y;       // the vector whose fields are streamed
+    const double* Fy = JV ? A.Fy + (int64_t)b * L.NF : nullptr;
+    double* out = A.out + (int64_t)b * L.N;
+    double* F = (!JV && A.F) ? A.F + (int64_t)b * L.NF : nullptr;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int r_lo[2], r_hi[2];
+    for (int T = 0; T < 2; ++T) {
+        r_lo[T] = (int)((int64_t)blockIdx.x * L.n[T] / gridDim.x);
+        r_hi[T] = (int)((int64_t)(blockIdx.x + 1) * L.n[T] / gridDim.x);
+    }
+    // warp-cooperative epilogue: lane j <-> state j of ion q, lane k <-> field slot k
+    tma_rows_pass(R, L, r_lo, r_hi, 0, x, 1.0, w, lane, [&](int T, int q, bool, int, int, double fl) {
+        const int s = L.s[T], nT = L.n[T];
+        const int e = L.off[T] + (lane < s ? lane : 0) * nT + q;
+        if (!JV) {
+            const double yj = lane < s ? y[e] : 0.0;
+            const double fj = coop_rhs(L, P, T, 32, lane, yj, fl);
+            if (lane < s) out[e] = fj;
+            if (F && lane < L.nf[T]) F[L.foff[T] + lane * nT + q] = fl;
+        } else {
+            const double yj = lane < s ? y[e] : 0.0, vj = lane < s ? x[e] : 0.0;
+            const double fyl = lane < L.nf[T] ? Fy[L.foff[T] + lane * nT + q] : 0.0;
+            const double oj = coop_jv(L, P, T, 32, lane, yj, vj, fyl, fl);
+            if (lane < s) out[e] = oj;
+        }
+    });
 }
