@@ -523,3 +523,32 @@ def test_tma_inside_grid_integrator(monkeypatch):
     assert parity_metric(res['1'][0], res['0'][0]) <= 1.0
     assert parity_metric(res['1'][1], res['0'][1]) <= 1.0
     system.close()
+
+
+def test_tma_kernels_single_species(monkeypatch):
+    """Sensitizer-only lattice (no activator rows, no S<-A / A<-S blocks): the TMA item sequence must
+    skip the empty blocks on both the producer and the consumer side.  RHS / Jv against the oracle
+    and against the register kernels."""
+    cte = configs.yb_tm_cte(N_uc=14, S_conc=30.0, A_conc=0.0)
+    lat = lattice.generate(cte, seed=7200, with_distances=True)
+    assert lat.n_A == 0 and lat.n_S > 600
+    g = dict(ion_type=lat.ion_type, dist_array=lat.distances(), info=np.array([2, 9]))
+    op = oracle_operands(g, cte)
+    system = precalculate.build_system(cte, lat, n_sys=2)
+    rng = np.random.default_rng(7200)
+    N = system.N
+    y = 10.0 ** rng.uniform(-12, 0, (2, N))
+    v = rng.standard_normal((2, N))
+    cM, cN, cJ = op['coop']
+    res = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('STB_TMA', mode)
+        res[mode] = (system.rhs(y, pulse=True), system.jv(y, v, pulse=True))
+    for b in range(2):
+        f_ref = onp.rate_eq_pulse(0.0, y[b], op['abs'], op['decay'], op['ET'], op['N_indices'], cM, cN)
+        jv_ref = onp.jac_vec(y[b], v[b], op['abs'] + op['decay'], op['ET'], op['N_indices'])
+        for mode in ('0', '1'):
+            assert np.all(np.abs(res[mode][0][b] - f_ref) <= 1e-12 * np.abs(f_ref).max())
+            assert np.all(np.abs(res[mode][1][b] - jv_ref) <= 1e-12 * np.abs(jv_ref).max())
+    assert np.array_equal(res['0'][0], res['1'][0]) and np.array_equal(res['0'][1], res['1'][1])
+    system.close()
