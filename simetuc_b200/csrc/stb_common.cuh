@@ -30,6 +30,15 @@
 #define STB_NT 512    // threads per CTA of the integrator / rhs kernels
 #define STB_NW (STB_NT / 32)
 
+// Dynamic shared memory: EVERY `extern __shared__` declaration of the library goes through this
+// macro.  nvcc places each such declaration at the end of the static variables rounded up to the
+// declaration's OWN alignment, so two declarations with different alignments inside one kernel
+// (say `dyn` in the kernel, `dynb` in an inlined device function, a third array elsewhere in the
+// translation unit with `__align__(128)`) stop aliasing: measured, the cluster integrator then
+// addressed its arrays from two bases 32 B apart ("Dynamic shared memory base").
+// 16 B is what LDS.128 and `cp.async.bulk` destinations need.
+#define STB_DYN_SMEM(name) extern __shared__ __align__(16) double name[]
+
 struct PairBlock {
     const uint32_t* col;         // [lines*32] partner index, type-local (null: dense block)
     const double* g[STB_MAXM];   // [lines*32] d^-mult, or dense [n[T]][ld[U]]

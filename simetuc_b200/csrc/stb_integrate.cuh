@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     __shared__ double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
     __shared__ double red[STB_NW * 4];
     __shared__ double rv[STB_KRED];
-    extern __shared__ double zs[];   // staged gather vector (N doubles) when A.staged
+    STB_DYN_SMEM(zs);                // staged gather vector (N doubles) when A.staged, or the TMA ring
 
     const int gid = blockIdx.x / A.G;
     if (gid >= A.n_groups) return;

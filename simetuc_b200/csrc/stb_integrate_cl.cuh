@@ -68,7 +68,11 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.NZ = ((Y.zoff[1] + L.s[1] * Y.ldz[1] + 8) + 1) & ~1;     // + slack for padded partner steps
     const int n_own = L.s[0] * Y.cntm[0] + L.s[1] * Y.cntm[1];
     Y.PO = (n_own + 31) & ~31;
+#ifdef STB_TEST_SHIFT4              // test builds only: every array 32 B higher, base unchanged (known defect)
+    int o = 4;
+#else
     int o = 0;
+#endif
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     Y.zy = take(Y.NZ);
     Y.zv = take(Y.NZ);
@@ -171,7 +175,7 @@ template <int NS, bool RES>
 __device__ __forceinline__ void cl_piece(int g_off, const double* gb, int64_t pitch, int row, int z_off,
                                       int ldz, const int* slot_col, int nkp, int kk, int s0, int s1,
                                       double mult, int dst_off, int dpitch) {
-    extern __shared__ __align__(16) double dynb[];
+    STB_DYN_SMEM(dynb);
     double* dst = dynb + dst_off;
     double acc[NS], acc2[NS];       // two chains per slot: the FP64 FMA latency, not its rate, binds
     int zo[NS];
@@ -251,7 +255,7 @@ __device__ __forceinline__ void cl_piece_ns(int ns, int g_off, const double* gb,
 __device__ __noinline__ void cl_coop_fields(const DevLattice& L, const ClLayout& Y, const int* r_lo,
                                             const int* cnt, int zb, double mult, int lin_at, int warp,
                                             int lane) {
-    extern __shared__ __align__(16) double dynb[];
+    STB_DYN_SMEM(dynb);
     double* F = dynb + Y.F;
     for (int r = 0; r < L.n_coop; ++r) {
         const CoopList& Cl = L.coop[r];
@@ -352,7 +356,7 @@ struct ClShared {
 // carries none of that code (it costs registers: +5 % on the C2 sweep when compiled in).
 template <bool COOP>
 __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
-    extern __shared__ __align__(16) double dyn[];
+    STB_DYN_SMEM(dyn);
     __shared__ ClShared S;
     DevLattice& L = S.L;
     SysParams& P = S.P;

@@ -272,13 +272,10 @@ __device__ __forceinline__ void tma_rows_pass(TmaRing& R, const DevLattice& L, c
 
 template <bool JV>
 __global__ void __launch_bounds__(STB_TMA_NT, 1) k_op_tma(OpArgs A) {
-    // NB: no __align__ here.  All `extern __shared__` arrays of a translation unit share one symbol,
-    // and a 128 B alignment request moved the dynamic shared memory base of EVERY kernel of the
-    // library (the cluster integrator's by 32 B).  Bulk copies need 16 B, which the base has.
-#ifdef STB_TEST_ALIGN128       // test builds only: reproduces the shifted base (tools/repro_check.py)
+#ifdef STB_TEST_ALIGN128       // test builds only: a declaration with another alignment (see STB_DYN_SMEM)
     extern __shared__ __align__(128) double tma_smem_d[];
 #else
-    extern __shared__ double tma_smem_d[];
+    STB_DYN_SMEM(tma_smem_d);
 #endif
     __shared__ DevLattice L;
     __shared__ SysParams P;
