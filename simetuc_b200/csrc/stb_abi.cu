@@ -989,7 +989,7 @@ static size_t tma_setup(OpArgs& A) {
 }
 
 static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* y, double* out, double* F) {
-    OpArgs A;
+    OpArgs A = {};
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = nullptr; A.Fy = nullptr; A.out = out; A.F = F;
     g_launches++;
@@ -1012,7 +1012,7 @@ static int launch_rhs(stb_system* S, int first, int n, int pulse, const double* 
 
 static int launch_jv(stb_system* S, int first, int n, int pulse, const double* y, const double* v,
                      const double* Fy, double* out) {
-    OpArgs A;
+    OpArgs A = {};
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.pulse = pulse; A.y = y; A.v = v; A.Fy = Fy; A.out = out; A.F = nullptr;
     g_launches++;
@@ -1483,7 +1483,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     if (resident) dyn_bytes = stage_bytes + own_bytes(G) + 64 + 128;
     // dense rows read by whole warps: the pair stream goes through the TMA ring (stb_tma.cuh), the
     // gathered vector stays in global memory / L1.  STB_TMA_INT=0 keeps the register-fed passes.
-    OpArgs tma_args;
+    OpArgs tma_args = {};
     int tma = use_tma(S) ? 1 : 0;
     if (const char* env = getenv("STB_TMA_INT")) tma = tma && atoi(env) != 0;
     if (tma) {
