@@ -487,7 +487,7 @@ def test_tma_kernels_multi_chunk_vs_oracle(monkeypatch):
     res = {}
     for mode in ('0', '1', '37'):
         monkeypatch.setenv('STB_TMA', mode)
-        if mode == '37':                 # 37 CTAs: 44 Yb rows per CTA = three row tiles each
+        if mode == '37':                 # 37 CTAs: 44 Yb rows per CTA = four row tiles each
             monkeypatch.setenv('STB_TMA_GRID', mode)
         res[mode] = (system.rhs(y, pulse=True), system.jv(y, v, pulse=True))
         assert np.all(np.abs(res[mode][0] - f_ref) <= 1e-12 * np.abs(f_ref).max())
