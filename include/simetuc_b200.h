@@ -170,6 +170,23 @@ int stb_integrate(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int6
 int stb_integrate_dev(stb_system* sys, int32_t first, int32_t n, int32_t pulse, int64_t n_t,
                       const double* t_dev, const double* y0_planes_dev, double rtol, double atol,
                       int64_t nsteps, double* y_out_dev, double* avg_out_dev, stb_stats* stats);
+/* Pulse followed by relaxation in ONE call: what Simulations.simulate_dynamics does with
+ * solve_pulse then solve_relax (simulations.py:1125-1160), and every pulsed sweep with it
+ * (simulations.py:1294-1305, 1356-1372; optimize.py:84-91).  The state at t_pulse[n_tp-1] starts the
+ * relaxation on the device (no host round trip between the two solves).
+ *   t_pulse  double[n_tp]  (n_tp >= 2; the reference uses linspace(0, tf_p, 2), simulations.py:1129)
+ *   t_sol    double[n_t]   relaxation output times, t_sol[0] = end of the pulse (:1147)
+ *   y0       double[n, N]  initial populations (reference layout)
+ *   y_pulse_out double[n, n_tp, N], y_out double[n, n_t, N], avg_out double[n, n_t, sS+sA]:
+ *            any may be NULL (not wanted, not copied back)
+ *   nsteps_pulse / nsteps: step limits of the two solves (odesolver.py:89)
+ * stats_pulse / stats_relax: [n] each.  A system whose pulse did not reach its end relaxes from the
+ * zero row the pulse left (odesolver.py:97); the caller sees it in stats_pulse[k].status. */
+int stb_integrate_dynamics(stb_system* sys, int32_t first, int32_t n, int64_t n_tp,
+                           const double* t_pulse, int64_t n_t, const double* t_sol, const double* y0,
+                           double rtol, double atol, int64_t nsteps_pulse, int64_t nsteps,
+                           double* y_pulse_out, double* y_out, double* avg_out,
+                           stb_stats* stats_pulse, stb_stats* stats_relax);
 /* The CUDA stream (cudaStream_t) every kernel of this system is launched on, so that callers can
  * record their own events on it; and the number of kernels launched by the library so far. */
 void* stb_stream(const stb_system* sys);

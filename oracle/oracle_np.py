@@ -477,3 +477,87 @@ def coop_jac_indices(coop_N_indices):
         out[0::3, 2], out[1::3, 2], out[2::3, 2] = c[:, 0], c[:, 0], c[:, 1]
         out[0::3, 3], out[1::3, 3], out[2::3, 3] = c[:, 1], c[:, 2], c[:, 2]
     return out
+
+
+# ----------------------------------------------------------------------------- row-sampled RHS / Jv
+def _mic_row(p, positions, cell):
+    """Minimum-image distances of one site to all sites of the periodic supercell `cell` (rows =
+    supercell vectors; None = open boundaries): the distance ASE's `get_all_distances(mic=True)`
+    returns at `lattice.py:239`.  Nearest fractional image, then the 27 neighbouring images."""
+    d = np.asarray(positions, dtype=np.float64) - np.asarray(p, dtype=np.float64)[None, :]
+    if cell is None:
+        return np.sqrt((d * d).sum(-1))
+    cell = np.asarray(cell, dtype=np.float64)
+    frac = d @ np.linalg.inv(cell)
+    d = (frac - np.rint(frac)) @ cell
+    best = np.full(len(d), np.inf)
+    for i in (-1, 0, 1):
+        for j in (-1, 0, 1):
+            for k in (-1, 0, 1):
+                e = d + (i * cell[0] + j * cell[1] + k * cell[2])[None, :]
+                np.minimum(best, (e * e).sum(-1), out=best)
+    return np.sqrt(best)
+
+
+def _ion_rows(q, ion_type, gs, positions, cell, lin_blocks, procs, y, v=None):
+    """Rows of ion q of `rate_eq[_pulse]` (and of `J(y) v` when v is given), O(n_ions) work."""
+    T = int(ion_type[q] != 0)
+    s = lin_blocks[T].shape[0]
+    d = _mic_row(positions[q], positions, cell)
+    others = np.flatnonzero(d)                               # lattice.py:335: self excluded by distance 0
+    yq = y[gs[q]:gs[q] + s]
+    out = lin_blocks[T].dot(yq)
+    outv = None
+    if v is not None:
+        vq = v[gs[q]:gs[q] + s]
+        outv = lin_blocks[T].dot(vq)
+    for dt, pt, ii, fi, if_, ff, mult, strength, _n in procs:
+        # ion q as the donor of the process (precalculate.py:277-291: -w at gs_i+ii, +w at gs_i+if)
+        if dt == T:
+            k = others[(ion_type[others] != 0) == bool(pt)]
+            w = strength * d[k] ** (-mult)
+            rate = np.sum(w * yq[ii] * y[gs[k] + fi])
+            out[ii] -= rate
+            out[if_] += rate
+            if v is not None:
+                dr = np.sum(w * (vq[ii] * y[gs[k] + fi] + yq[ii] * v[gs[k] + fi]))
+                outv[ii] -= dr
+                outv[if_] += dr
+        # ion q as the partner (-w at gs_k+fi, +w at gs_k+ff)
+        if pt == T:
+            i = others[(ion_type[others] != 0) == bool(dt)]
+            w = strength * d[i] ** (-mult)
+            rate = np.sum(w * y[gs[i] + ii] * yq[fi])
+            out[fi] -= rate
+            out[ff] += rate
+            if v is not None:
+                dr = np.sum(w * (v[gs[i] + ii] * yq[fi] + y[gs[i] + ii] * vq[fi]))
+                outv[fi] -= dr
+                outv[ff] += dr
+    return out, outv
+
+
+def rate_eq_rows(ions, ion_type, positions, cell, n_S_states, n_A_states, energy_transfer,
+                 lin_S, lin_A, y, v=None):
+    """The rows of `rate_eq[_pulse](y)` - and of `jac_rate_eq[_pulse](y) @ v` - that belong to the
+    ions in `ions`, computed ion by ion from positions (no interaction list, no ET matrix): the
+    check for lattices whose reference operands (56 B per interaction, dense Jacobian) do not fit
+    in memory.  Regroups `odesolver.py:33-43` / `:46-62` by owner ion using the column pattern of
+    `precalculate.py:277-294`; `lin_S`, `lin_A` are the per-type decay (+ absorption) blocks.
+    Returns `(state indices, rhs rows, jv rows | None)`; validated against the full operators in
+    tests/test_oracle.py."""
+    ion_type = np.asarray(ion_type)
+    index_S_i, index_A_j, _ = ground_states(ion_type, n_S_states, n_A_states)
+    gs = np.where(ion_type != 0, index_A_j, index_S_i)
+    procs = _active_pair_processes(energy_transfer)
+    blocks = (np.asarray(lin_S, dtype=np.float64).reshape(n_S_states, n_S_states),
+              np.asarray(lin_A, dtype=np.float64).reshape(n_A_states, n_A_states))
+    idx, f_rows, jv_rows = [], [], []
+    for q in ions:
+        f, jv = _ion_rows(int(q), ion_type, gs, positions, cell, blocks, procs, y, v)
+        idx.append(np.arange(gs[q], gs[q] + len(f)))
+        f_rows.append(f)
+        if jv is not None:
+            jv_rows.append(jv)
+    return (np.concatenate(idx), np.concatenate(f_rows),
+            np.concatenate(jv_rows) if jv_rows else None)

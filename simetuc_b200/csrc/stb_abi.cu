@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -313,7 +314,8 @@ struct stb_system {
     int sm_count = 148;
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
-    enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR, WS_COUNT };
+    enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR,
+           WS_DYN_T, WS_DYN_TMP, WS_DYN_Y0, WS_DYN_YP, WS_DYN_YS, WS_DYN_AVG, WS_COUNT };
     void* ws_ptr[WS_COUNT] = {};
     size_t ws_cap[WS_COUNT] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1153,6 +1155,23 @@ static cudaError_t allow_max_smem(K kernel) {
     return e;
 }
 
+// STB_TIMING=1: host-side wall clock of the stages of an integrate call (development aid)
+struct HostTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    std::string log;
+    HostTimer() : on(getenv("STB_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* name) {
+        if (!on) return;
+        auto t1 = std::chrono::steady_clock::now();
+        char buf[64];
+        snprintf(buf, sizeof(buf), " %s=%.3f", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        log += buf;
+        t0 = t1;
+    }
+    ~HostTimer() { if (on) fprintf(stderr, "[stb timing]%s\n", log.c_str()); }
+};
+
 typedef void (*ClKernel)(ClArgs);
 // the plain cluster integrator, or the instance with the cooperative field pass
 static ClKernel cl_kernel(const stb_system* S) {
@@ -1274,6 +1293,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
                              int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats, bool dev) {
     const int N = S->N;
     const DevLattice& L = S->hL;
+    HostTimer tm;
     ClLayout Y;
     cl_layout(L, plan.G, plan.resmask, plan.v_smem, plan.d_smem, Y);
     const int64_t work_stride = (int64_t)(STB_KRYLOV + 1 + 8) * Y.PO;
@@ -1322,11 +1342,14 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         t_p = d_t;
         y0_p = d_y0;
     }
+    tm.mark("enqueue_inputs");
     ClArgs A;
     memset(&A, 0, sizeof(A));
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.n_sys = n; A.pulse = pulse; A.G = plan.G;
     A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
+    A.opts = CL_OPT_GUESS | CL_OPT_LAGPC;
+    if (const char* env = getenv("STB_CL_OPTS")) A.opts = atoi(env);
     A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;
     A.nsteps = nsteps > 0 ? nsteps : 1000;
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
@@ -1359,6 +1382,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         CKC(cudaLaunchKernelEx(&cfg, kern, A));
     }
     CKC(cudaEventRecord(e1, S->stream));
+    tm.mark("launch");
     S->last_launches = dev ? 1 : 2;
     double* avg_p = avg_out;
     if (avg_out) {
@@ -1375,6 +1399,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     // kernel blocks inside the driver with the context lock held, and the launches of every other
     // handle (other host threads) then wait for this solve to finish.
     CKC(cudaStreamSynchronize(S->stream));
+    tm.mark("sync_kernels");
     if (avg_out) {
         if (!dev)
             CKC(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
@@ -1384,7 +1409,13 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     S->last_prof.assign((size_t)8 * n, 0);
     if (stats) CKC(cudaMemcpyAsync(stats, d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost, S->stream));
     CKC(cudaStreamSynchronize(S->stream));
+    tm.mark("d2h");
     CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
+    if (tm.on) {
+        char buf[48];
+        snprintf(buf, sizeof(buf), " [kernel=%.3f]", S->last_ms);
+        tm.log += buf;
+    }
     if (getenv("STB_VERBOSE")) {
         long long pr[24];
         CKC(copy_on(S->stream, pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
@@ -1430,7 +1461,10 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     // ---- small lattices: one thread-block cluster per system (stb_integrate_cl.cuh) ------------
     {
         ClPlan plan;
-        if (cl_choose(S, n, plan))
+        HostTimer tm;
+        const bool use_cl = cl_choose(S, n, plan);
+        tm.mark("cl_choose");
+        if (use_cl)
             return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
                                      avg_out, stats, dev);
     }
@@ -1555,6 +1589,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
     A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
+    A.guess = 1;
+    if (const char* env = getenv("STB_CL_OPTS")) A.guess = atoi(env) & CL_OPT_GUESS;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKI(cudaEventRecord(e0, S->stream));
@@ -1601,6 +1637,63 @@ extern "C" int stb_integrate_dev(stb_system* S, int32_t first, int32_t n, int32_
                                  stb_stats* stats) {
     return integrate_core(S, first, n, pulse, n_t, t_dev, y0_planes_dev, rtol, atol, nsteps,
                           y_out_dev, avg_out_dev, stats, true);
+}
+
+extern "C" int stb_integrate_dynamics(stb_system* S, int32_t first, int32_t n, int64_t n_tp,
+                                      const double* t_pulse, int64_t n_t, const double* t_sol,
+                                      const double* y0, double rtol, double atol, int64_t nsteps_pulse,
+                                      int64_t nsteps, double* y_pulse_out, double* y_out, double* avg_out,
+                                      stb_stats* stats_pulse, stb_stats* stats_relax) {
+    int rc = check_range(S, first, n);
+    if (rc) return rc;
+    if (n_tp < 2 || n_t < 1 || !t_pulse || !t_sol || !y0)
+        return fail(STB_EINVAL, "bad time grids / initial state");
+    for (int64_t k = 1; k < n_tp; ++k)
+        if (!(t_pulse[k] > t_pulse[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    for (int64_t k = 1; k < n_t; ++k)
+        if (!(t_sol[k] > t_sol[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    CK(cudaSetDevice(S->device));
+    HostTimer tm;
+    const int N = S->N;
+    const int kinds = S->hL.s[0] + S->hL.s[1];
+    double *d_t = nullptr, *d_tmp = nullptr, *d_y0 = nullptr, *d_yp = nullptr, *d_ys = nullptr, *d_avg = nullptr;
+    const size_t vec_bytes = sizeof(double) * (size_t)n * N;
+    CK(ws_get(S, stb_system::WS_DYN_T, sizeof(double) * (size_t)(n_tp + n_t), (void**)&d_t));
+    CK(ws_get(S, stb_system::WS_DYN_TMP, vec_bytes, (void**)&d_tmp));
+    CK(ws_get(S, stb_system::WS_DYN_Y0, vec_bytes, (void**)&d_y0));
+    CK(ws_get(S, stb_system::WS_DYN_YP, vec_bytes * n_tp, (void**)&d_yp));
+    if (y_out) CK(ws_get(S, stb_system::WS_DYN_YS, vec_bytes * n_t, (void**)&d_ys));
+    if (avg_out) CK(ws_get(S, stb_system::WS_DYN_AVG, sizeof(double) * (size_t)n * n_t * kinds, (void**)&d_avg));
+    CK(cudaMemcpyAsync(d_t, t_pulse, sizeof(double) * n_tp, cudaMemcpyHostToDevice, S->stream));
+    CK(cudaMemcpyAsync(d_t + n_tp, t_sol, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
+    CK(cudaMemcpyAsync(d_tmp, y0, vec_bytes, cudaMemcpyHostToDevice, S->stream));
+    const int64_t tot = (int64_t)n * N;
+    g_launches++;
+    k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
+    CK(cudaGetLastError());
+    tm.mark("inputs");
+    rc = integrate_core(S, first, n, 1, n_tp, d_t, d_y0, rtol, atol, nsteps_pulse, d_yp, nullptr, stats_pulse, true);
+    if (rc) return rc;
+    const float ms_pulse = S->last_ms;
+    const int64_t launches_pulse = S->last_launches;
+    tm.mark("pulse");
+    // the state at the end of the pulse starts the relaxation (simulations.py:1148-1157)
+    g_launches++;
+    k_row_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(
+        S->d_plane_of_ref, N, n, d_yp + (n_tp - 1) * (int64_t)N, n_tp * (int64_t)N, d_y0);
+    CK(cudaGetLastError());
+    rc = integrate_core(S, first, n, 0, n_t, d_t + n_tp, d_y0, rtol, atol, nsteps, d_ys, d_avg, stats_relax, true);
+    if (rc) return rc;
+    tm.mark("relax");
+    S->last_ms += ms_pulse;
+    S->last_launches += launches_pulse + 2;
+    if (y_pulse_out) CK(cudaMemcpyAsync(y_pulse_out, d_yp, vec_bytes * n_tp, cudaMemcpyDeviceToHost, S->stream));
+    if (y_out) CK(cudaMemcpyAsync(y_out, d_ys, vec_bytes * n_t, cudaMemcpyDeviceToHost, S->stream));
+    if (avg_out)
+        CK(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * kinds, cudaMemcpyDeviceToHost, S->stream));
+    CK(cudaStreamSynchronize(S->stream));
+    tm.mark("d2h");
+    return STB_OK;
 }
 
 extern "C" void* stb_stream(const stb_system* S) { return S ? (void*)S->stream : nullptr; }

@@ -49,7 +49,14 @@ struct IntArgs {
     long long* prof;          // [n_sys][8] clock64 cycles per phase (thread 0 of CTA 0), may be null
     int tma;                  // dense rows fed by bulk copies through a shared-memory ring (stb_tma.cuh)
     int tma_kc, tma_stages;
+    int guess;                // Newton starts from the previous step's correction (see CL_OPT_GUESS)
 };
+
+__device__ __forceinline__ double stb_ipow(double x, int n) {
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r *= x;
+    return r;
+}
 
 __host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
     // D[8] yk d psi scale f wv gv wbuf  V[KRYLOV+1]  F  Minv
@@ -59,6 +66,9 @@ __host__ __device__ inline int64_t stb_work_doubles(int N, int NF, int NMinv) {
 struct Ctl {
     double t, h, t_end, c, newton_tol, tol_lin;
     double beta, inrm, dy_norm, dy_norm_old, err_norm, safety, crate;
+    double gfac;              // scale of the previous step's correction used as the Newton start
+    double pc_c;              // c of the step the lagged block inverses were factored at
+    int pc_age, pc_refresh;   // steps since then; factor them in this Newton iteration
     double RU[(STB_MAXORD + 1) * (STB_MAXORD + 1)];
     double p[STB_MAXORD + 1];
     int order, n_equal, status, kk, flag, flag2, newton_it, n_iter, since_verify;
@@ -557,6 +567,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.tol_lin = STB_LIN_RMS * sqrtN;
             C.crate = 1.0;
             C.since_verify = 0;
+            C.gfac = 0.0;
             memset(&C.st, 0, sizeof(stb_stats));
             for (int k = 0; k < 8; ++k) C.prof[k] = 0;
             tick = clock64();
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     C.h = C.t_end - C.t;
                     C.n_equal = 0;
                     C.flag = 1;
+                    C.gfac *= stb_ipow(factor, C.order + 1);
                 } else if (t_new > C.t_end) {
                     C.h = C.t_end - C.t;  // round-off sized overshoot: land exactly on t_end
                 }
@@ -650,7 +662,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             __syncthreads();
             const int order = C.order;
             const double c = C.c;
-            // predictor, scale, psi; d = 0
+            const double gf = A.guess ? C.gfac : 0.0;
+            // predictor, scale, psi; Newton starts from the predictor plus the previous step's
+            // correction (D[order + 1]) rescaled to this step size
             OWN_LOOP(e)
                 double yp = 0.0, ps = 0.0;
                 for (int j = 0; j <= order; ++j) {
@@ -658,10 +672,11 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     yp += dj;
                     if (j >= 1) ps = fma(GAMMA[j], dj, ps);
                 }
-                yk[e] = yp;
+                const double d0 = gf != 0.0 ? gf * D[(int64_t)(order + 1) * N + e] : 0.0;
+                yk[e] = yp + d0;
                 scale[e] = atol + rtol * fabs(yp);
                 psi[e] = ps / ALPHA[order];
-                dd[e] = 0.0;
+                dd[e] = d0;
             OWN_END
             // ---- Newton-Krylov ----------------------------------------------------------------
             if (threadIdx.x == 0) { C.newton_it = 0; C.flag = 0; C.dy_norm_old = -1.0; }
@@ -818,6 +833,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     C.h *= 0.5;
                     C.n_equal = 0;
                     C.steps_since_out += 1;
+                    C.gfac = 0.0;
                 }
                 __syncthreads();
                 apply_change_D(order);
@@ -849,6 +865,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                         C.st.n_rejected += 1;
                         C.steps_since_out += 1;
                         C.flag = 1;
+                        C.gfac *= stb_ipow(factor, order + 1);
                     }
                 }
                 __syncthreads();
@@ -923,6 +940,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     C.n_equal += 1;
                     C.t = t_new;
                     C.flag = 0;
+                    C.gfac = 1.0;
                     if (need_order) {
                         double err_m = order > 1 ? sqrt(rv[0] / N) : INFINITY;
                         double err_p = order < STB_MAXORD ? sqrt(rv[1] / N) : INFINITY;
@@ -947,6 +965,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                         C.h *= factor;
                         C.n_equal = 0;
                         C.flag = 1;
+                        C.gfac = delta == 0 ? stb_ipow(factor, order + 1) : 0.0;
                     }
                     C.st.last_order = C.order;
                     C.st.last_h = C.h;

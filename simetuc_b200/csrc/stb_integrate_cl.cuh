@@ -35,7 +35,7 @@ struct ClLayout {          // offsets in doubles into dynamic shared memory
     int cntm[2], cntp[2];  // max own rows per type (over the ranks), rounded up to CL_RG
     int PO;                // pitch of own-compact vectors
     int nkp[2], nst[2];    // partner pairs / warp steps (4 pairs) per partner type
-    int zy, zv, dd, psi, scl, fv, tw, kv, minv, F, Pp, part, info, V, D, gres;
+    int zy, zv, dd, psi, scl, fv, tw, kv, minv, mcur, F, Pp, part, info, V, D, gres;
     int gres_off[2][2];    // resident pair rows of block [T][U], relative to gres (-1: streamed)
     int nfm;               // field slots per row, max over the types
     int nsm;               // field slots of one block, max over the blocks
@@ -85,6 +85,7 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.moff[0] = 0;
     Y.moff[1] = L.s[0] * L.s[0] * Y.cntm[0];
     Y.minv = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);
+    Y.mcur = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);     // rows of I - c J_qq of the current iterate
     Y.nfm = L.nf[0] > L.nf[1] ? L.nf[0] : L.nf[1];
     if (Y.nfm < 1) Y.nfm = 1;
     Y.foff[0] = 0;
@@ -112,6 +113,16 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.total = o;
 }
 
+// Newton starts from the previous step's correction, rescaled for a changed step size, instead of
+// from the predictor alone: consecutive corrections differ by one more backward difference.
+#define CL_OPT_GUESS 1
+// The inverses of the larger per-ion blocks are kept across steps (refreshed when c drifts by more
+// than 30 %, after CL_PC_MAXAGE steps or after a failed Newton iteration, CVODE's rule); the operator
+// is then applied as Minv_old (M v - c k(v)) with the rows of the current M = I - c J_qq.
+#define CL_OPT_LAGPC 2
+#define CL_PC_MAXAGE 20
+#define CL_PC_DRIFT 0.3
+
 struct ClArgs {
     const DevLattice* L;
     const double* blocks;
@@ -119,6 +130,7 @@ struct ClArgs {
     int first, n_sys, pulse;
     int G;
     int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
+    int opts;                      // CL_OPT_* bits
     int64_t n_t;
     const double* t;
     const double* y0;          // [n_sys][N] planes
@@ -132,6 +144,11 @@ struct ClArgs {
     long long* prof;           // [24] clock64 cycles per phase (cluster 0, rank 0, thread 0) + counters; may be null
 };
 
+__device__ __forceinline__ double cl_ipow(double x, int n) {
+    double r = 1.0;
+    for (int i = 0; i < n; ++i) r *= x;
+    return r;
+}
 __device__ __forceinline__ uint32_t cl_smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -450,6 +467,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     double* tw = dyn + Y.tw;
     double* kv = dyn + Y.kv;
     double* Minv = dyn + Y.minv;
+    double* Mcur = dyn + Y.mcur;
+    const bool lagpc = (A.opts & CL_OPT_LAGPC) != 0;
+    const bool guess = (A.opts & CL_OPT_GUESS) != 0;
     double* F = dyn + Y.F;
     double* Pp = dyn + Y.Pp;
     double* part = dyn + Y.part;
@@ -773,7 +793,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     // 1. every thread builds its own row of M in place (thread per state, as the epilogues);
     // 2. the blocks are inverted in place: closed form for 2-state ions (thread per ion), else
     //    Gauss-Jordan with W = pow2 >= s lanes per ion, one row per lane.
-    auto block_inverses = [&](double c) {
+    // refresh = false (lagged preconditioner): only the rows of the current M are rebuilt (into Mcur);
+    // the inverses of the larger blocks stay those of an earlier step
+    auto block_inverses = [&](double c, bool refresh) {
         // 1. rows of M = I - c J_qq: closed-form inverse for 1- and 2-state ions (thread per ion),
         //    else every thread builds the row of its own state in place
         for (int k = tid; k < n_own; k += STB_NT) {
@@ -805,7 +827,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 }
                 continue;
             }
-            double* Mp = Minv + Y.moff[T] + (a * s) * cm + i;
+            double* Mp = (lagpc ? Mcur : Minv) + Y.moff[T] + (a * s) * cm + i;
             const double* lr = lin + a * s;
             for (int b = 0; b < s; ++b) Mp[b * cm] = (b == a ? 1.0 : 0.0) - c * lr[b];
             for (int n = S.tl_ptr[T][a]; n < S.tl_ptr[T][a + 1]; ++n) {
@@ -814,8 +836,13 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
                 Mp[tt.a[t] * cm] += (e & 0x4000) ? -kq : kq;     // row b_t: -, row a_t: +
             }
+            if (lagpc && refresh) {
+                double* Mi = Minv + Y.moff[T] + (a * s) * cm + i;
+                for (int b = 0; b < s; ++b) Mi[b * cm] = Mp[b * cm];
+            }
         }
         __syncthreads();
+        if (!refresh) return;
         // 2. in-place Gauss-Jordan of the larger blocks, 64 threads per ion (<= 3 entries each), no
         //    pivoting (column-diagonally-dominant M-matrix); compact rolled code: a lane-per-row
         //    shuffle version costs 4-10k cycles per call (tools/ubench.cu), mostly instruction fetch
@@ -909,10 +936,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             C.tol_lin = STB_LIN_RMS * sqrtN;
             C.crate = 1.0;
             C.since_verify = 0;
+            C.gfac = 0.0;
+            C.pc_c = 0.0;
+            C.pc_age = -1;
+            C.pc_refresh = 1;
             memset(&C.st, 0, sizeof(stb_stats));
         }
         int64_t k_out_l = 1;                                   // output cursor, uniform over the cluster
         double tq_l = A.n_t > 1 ? A.t[1] : INFINITY;
+        double tq_n = A.n_t > 2 ? A.t[2] : INFINITY;           // one output time ahead: its load latency stays off the step
         // D0 = y0, row 0 of the output = y0 verbatim (odesolver.py:107)
         for (int k = tid; k < n_own; k += STB_NT) {
             const int inf = own_inf[k];
@@ -981,6 +1013,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.h = C.t_end - C.t;
                     C.n_equal = 0;
                     C.flag = 1;
+                    C.gfac *= cl_ipow(factor, C.order + 1);
                 } else if (t_new > C.t_end) {
                     C.h = C.t_end - C.t;
                 }
@@ -988,12 +1021,17 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 if (C.h < eps_t) C.status = 2;
                 if (C.steps_since_out >= A.nsteps) C.status = 1;
                 C.c = C.h / ALPHA[C.order];
+                C.pc_refresh = !lagpc || C.pc_age < 0 || C.pc_age >= CL_PC_MAXAGE ||
+                               fabs(C.c / C.pc_c - 1.0) > CL_PC_DRIFT;
             }
             __syncthreads();
             if (C.status != 0) break;
             if (C.flag) apply_change_D(C.order);
             const int order = C.order;
             const double c = C.c;
+            const bool pc_ref = C.pc_refresh != 0;
+            const double gf = guess ? C.gfac : 0.0;
+            bool first_newton = true;
             // predictor, scale, psi; d = 0; the predicted state goes to every CTA of the cluster
             for (int k = tid; k < n_own; k += STB_NT) {
                 double yp = 0.0, ps = 0.0;
@@ -1004,8 +1042,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 }
                 scl[k] = atol + rtol * fabs(yp);
                 psi[k] = ps / ALPHA[order];
-                dd[k] = 0.0;
-                push(rb_zy, zy, own_ez[k], yp);
+                // Newton start: predictor + the previous correction (D[order + 1]) rescaled to this step
+                const double d0 = gf != 0.0 ? gf * D[(order + 1) * PO + k] : 0.0;
+                dd[k] = d0;
+                push(rb_zy, zy, own_ez[k], yp + d0);
             }
             if (tid == 0) { C.newton_it = 0; C.flag = 0; C.dy_norm_old = -1.0; }
             // ---- Newton-Krylov ------------------------------------------------------------------
@@ -1016,7 +1056,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 rhs_pass(zy, Y.zy, fv);
                 __syncthreads();
                 CLPROF(4)
-                block_inverses(c);
+                const bool pc_now = !lagpc || (pc_ref && first_newton);
+                block_inverses(c, pc_now);
                 __syncthreads();
                 CLPROF(5)
                 // tw = Minv (c f - psi - d) / scale; the unscaled vector goes to zv
@@ -1039,6 +1080,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     CLPROF(7)
                 }
                 if (tid == 0) {
+                    if (lagpc && pc_now) { C.pc_c = c; C.pc_age = 0; }
                     C.st.n_rhs += 1;
                     C.st.n_lin += 1;
                     C.beta = sqrt(S.rv[0]);
@@ -1071,7 +1113,17 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     for (int k = tid; k < n_own; k += STB_NT) {
                         const int inf = own_inf[k];
                         const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
-                        kv[k] = term_sum(T, a, i, zy);
+                        double kq = term_sum(T, a, i, zy);
+                        if (lagpc && L.s[T] > 2) {
+                            // lagged inverse: Minv_old (M v - c k(v)), rows of the current M in Mcur
+                            const int s = L.s[T], cm = Y.cntm[T];
+                            const double* Mp = Mcur + Y.moff[T] + (a * s) * cm + i;
+                            const double* vq = zv + Y.zoff[T] + r_lo[T] + i;
+                            double mv = 0.0;
+                            for (int b = 0; b < s; ++b) mv = fma(Mp[b * cm], vq[b * Y.ldz[T]], mv);
+                            kq = mv * zmul - c * kq;
+                        }
+                        kv[k] = kq;
                     }
                     __syncthreads();
                     {
@@ -1079,7 +1131,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         for (int k = tid; k < n_own; k += STB_NT) {
                             const int inf = own_inf[k];
                             const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
-                            tw[k] = Vj[k] - c * minv_apply(T, a, i, kv) / scl[k];
+                            const double mk = minv_apply(T, a, i, kv);
+                            tw[k] = lagpc && L.s[T] > 2 ? mk / scl[k] : Vj[k] - c * mk / scl[k];
                         }
                     }
                     __syncthreads();
@@ -1210,6 +1263,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     }
                 }
                 if (flag != 0) break;
+                first_newton = false;
             }
             __syncthreads();
             if (C.flag == 2) {
@@ -1220,6 +1274,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.h *= 0.5;
                     C.n_equal = 0;
                     C.steps_since_out += 1;
+                    C.gfac = 0.0;
+                    C.pc_age = -1;       // factor the block inverses afresh
                 }
                 __syncthreads();
                 apply_change_D(order);
@@ -1261,6 +1317,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         C.st.n_rejected += 1;
                         C.steps_since_out += 1;
                         C.flag = 1;
+                        C.gfac *= cl_ipow(factor, order + 1);
                     }
                 }
                 __syncthreads();
@@ -1310,7 +1367,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     }
                     wrote = true;
                     ++k_out_l;
-                    tq_l = k_out_l < A.n_t ? A.t[k_out_l] : INFINITY;
+                    tq_l = tq_n;
+                    tq_n = k_out_l + 1 < A.n_t ? A.t[k_out_l + 1] : INFINITY;
                 } while (k_out_l < A.n_t && (tq_l <= t_new * (1.0 + 1e-15) || tq_l <= t_new));
             }
             if (warp == STB_NW - 1) {
@@ -1345,13 +1403,16 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.st.n_out = k_out_l;
                     C.t = t_new;
                     C.flag2 = 0;      // (not C.flag: slow threads may still be reading the rejection test)
+                    if (C.pc_age >= 0) C.pc_age += 1;
                     if (need_order) {
                         C.order = new_order;
                         C.h = h * factor;
                         C.n_equal = 0;
                         C.flag2 = 1;
+                        C.gfac = new_order == order ? cl_ipow(factor, order + 1) : 0.0;
                     } else {
                         C.n_equal += 1;
+                        C.gfac = 1.0;
                     }
                     C.st.last_order = C.order;
                     C.st.last_h = C.h;

@@ -124,6 +124,17 @@ __global__ void k_ref_to_planes(const int* plane_of_ref, int N, int n, const dou
     }
 }
 
+// row `y_row` (+ b * sys_stride for system b) of an output array in reference layout -> planes [n][N]:
+// hands the state at the end of the pulse to the relaxation without leaving the device
+__global__ void k_row_to_planes(const int* plane_of_ref, int N, int n, const double* y_row,
+                                int64_t sys_stride, double* planes) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < (int64_t)N * n) {
+        int b = i / N, e = i % N;
+        planes[(int64_t)b * N + plane_of_ref[e]] = y_row[(int64_t)b * sys_stride + e];
+    }
+}
+
 __global__ void k_planes_to_ref(const int* plane_of_ref, int N, int n, const double* planes,
                                 double* ref) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

@@ -80,6 +80,10 @@ class RateSystem:
         self.bytes_per_pair = self.stream_bytes // self.n_slots if self.n_slots else 0
         self._geometry = (dist, pos, cell)
         self.n_coop = 0
+        #: `precalculate.ParamSet` whose blocks / strengths system 0 currently holds (None: unknown)
+        self.active_params = None
+        #: key under which `precalculate.release_system` parks this handle
+        self.pool_key = None
         coop = coop_process(energy_transfer)
         if coop is not None:
             self.set_coop(coop, d_max_coop)
@@ -147,6 +151,7 @@ class RateSystem:
     def set_batch(self, n_sys: int):
         _lib.check(self.lib.stb_set_batch(self.handle, int(n_sys)))
         self.n_sys = int(n_sys)
+        self.active_params = None
 
     def _blk(self, blk, n):
         if n == 0:
@@ -160,16 +165,19 @@ class RateSystem:
 
     def set_decay_blocks(self, blk_S, blk_A, system: int = -1):
         bS, bA = self._blk(blk_S, self.sS), self._blk(blk_A, self.sA)
+        self.active_params = None
         _lib.check(self.lib.stb_set_blocks(self.handle, system, 0, _lib.ptr(bS), _lib.ptr(bA)))
 
     def set_abs_blocks(self, blk_S, blk_A, system: int = -1):
         bS, bA = self._blk(blk_S, self.sS), self._blk(blk_A, self.sA)
+        self.active_params = None
         _lib.check(self.lib.stb_set_blocks(self.handle, system, 1, _lib.ptr(bS), _lib.ptr(bA)))
 
     def set_strengths(self, strengths: Sequence[float], system: int = -1):
         s = _lib.f64(strengths)
         if s.shape != (self.n_proc,):
             raise ValueError('need %d strengths' % self.n_proc)
+        self.active_params = None
         rc = self.lib.stb_set_strengths(self.handle, system, _lib.ptr(s))
         if rc != 0:
             raise LatticeError(_lib.last_error())
@@ -251,6 +259,27 @@ class RateSystem:
             self.handle, first, n, int(bool(pulse)), n_t, _lib.ptr(t), _lib.ptr(y0), float(rtol),
             float(atol), int(nsteps), _lib.ptr(y_out), _lib.ptr(avg), C.cast(stats, C.c_void_p)))
         return y_out, avg, [s.as_dict() for s in stats]
+
+    def integrate_dynamics(self, t_pulse, t_sol, y0, rtol: float = 1e-3, atol: float = 1e-15,
+                           nsteps: int = 1000, first: int = 0, want_y: bool = True,
+                           want_avg: bool = True, want_pulse: bool = False):
+        """Pulse then relaxation of systems `first..first+n` in one C-ABI call
+        (`stb_integrate_dynamics`): the relaxation starts on the device from the last pulse row.
+        Returns `(y_pulse [n, n_tp, N] | None, y [n, n_t, N] | None, avg [n, n_t, sS+sA] | None,
+        stats_pulse, stats_relax)`."""
+        t_pulse = _lib.f64(t_pulse).ravel()
+        t_sol = _lib.f64(t_sol).ravel()
+        y0, n = self._vecs(y0, first, None)
+        y_p = np.empty((n, len(t_pulse), self.N)) if want_pulse else None
+        y = np.empty((n, len(t_sol), self.N)) if want_y else None
+        avg = np.empty((n, len(t_sol), self.sS + self.sA)) if want_avg else None
+        st_p = (_lib.StbStats * n)()
+        st_r = (_lib.StbStats * n)()
+        _lib.check(self.lib.stb_integrate_dynamics(
+            self.handle, first, n, len(t_pulse), _lib.ptr(t_pulse), len(t_sol), _lib.ptr(t_sol),
+            _lib.ptr(y0), float(rtol), float(atol), int(nsteps), int(nsteps), _lib.ptr(y_p),
+            _lib.ptr(y), _lib.ptr(avg), C.cast(st_p, C.c_void_p), C.cast(st_r, C.c_void_p)))
+        return y_p, y, avg, [s.as_dict() for s in st_p], [s.as_dict() for s in st_r]
 
     def integrate_dev(self, t_dev_ptr: int, n_t: int, y0_planes_ptr: int, n: int, pulse: bool,
                       rtol: float, atol: float, nsteps: int = 1000, first: int = 0,

@@ -38,6 +38,37 @@ def cell_vectors(a, b, c, alpha, beta, gamma):
                      [c * cos_b, c * cy, c * cz]], dtype=np.float64)
 
 
+# Wyckoff positions of multiplicity 1 of P-6 (No. 174): listed sites on them are not multiplied by
+# the symmetry operations, so the supercell can be written out without a space-group table.
+_P6BAR_SINGLE = [(0.0, 0.0, 0.0), (0.0, 0.0, 0.5), (1 / 3, 2 / 3, 0.0), (1 / 3, 2 / 3, 0.5),
+                 (2 / 3, 1 / 3, 0.0), (2 / 3, 1 / 3, 0.5)]
+
+
+def _check_symmetry_supported(lat):
+    """The reference expands the listed sites with `ase.spacegroup.crystal` (`lattice.py:80-107`) or
+    reads a cif file; neither ASE nor a space-group table exists here.  Only lattices whose
+    listed sites are the complete cell are accepted (P1, or P-6 with multiplicity-1 sites: every
+    shipped `.cfg`); anything else raises instead of silently building the wrong crystal."""
+    if lat.get('cif_file') or lat.get('ion_sites'):
+        raise NotImplementedError('lattices defined by a cif file (`cif_file` / `ion_sites`) need the '
+                                  'symmetry expansion of ASE, which this build does not have')
+    sg = lat.get('spacegroup', 'P1')
+    name = str(sg).replace(' ', '').upper()
+    if name in ('P1', '1'):
+        return
+    if name in ('P-6', '174'):
+        pos = lat['sites_pos']
+        pos = pos if isinstance(pos[0], (list, tuple)) else [pos]
+        for site in pos:
+            frac = np.mod(np.asarray(site, dtype=np.float64), 1.0)
+            if not any(np.allclose(frac, w, atol=1e-3) for w in _P6BAR_SINGLE):
+                raise NotImplementedError('site %s of space group P-6 has multiplicity > 1: the '
+                                          'symmetry expansion is not available' % (tuple(site),))
+        return
+    raise NotImplementedError('space group %r: only P1 and P-6 (multiplicity-1 sites) can be built '
+                              'without a space-group table' % (sg,))
+
+
 def check_lattice_settings(cte):
     """`lattice.py:40-78`: concentration / size / state-count validation."""
     lat = cte['lattice']
@@ -47,6 +78,7 @@ def check_lattice_settings(cte):
     if S_conc < 0 or A_conc < 0 or not 0 <= S_conc + A_conc <= 100.0:
         raise LatticeError('Wrong ion concentrations: %.2f%% Sensitizer, %.2f%% Activator. '
                            'Their sum must be between 0%% and 100%%.' % (S_conc, A_conc))
+    _check_symmetry_supported(lat)
     pos, occ = lat['sites_pos'], lat['sites_occ']
     pos = pos if isinstance(pos[0], (list, tuple)) else [pos]
     occ = occ if isinstance(occ, (list, tuple)) else [occ]

@@ -22,9 +22,16 @@ import numpy as np
 
 
 def _system_of(*operands):
+    """`(RateSystem, system index)` behind the operands.  Operand sets created by separate
+    `setup_*_eqs` calls on one lattice share a device handle: the parameters this set was built
+    from (`precalculate.ParamSet`) are re-applied first, so earlier operands do not silently
+    integrate with a later call's power or strengths."""
     for op in operands:
         ref = getattr(op, 'stb', None)
         if ref is not None:
+            params = getattr(op, 'stb_params', None)
+            if params is not None:
+                params.apply(ref[0], ref[1])
             return ref
     raise TypeError('operands do not come from simetuc_b200.precalculate.setup_microscopic_eqs '
                     '(no device system attached); this path has no CPU fallback')
@@ -87,6 +94,23 @@ def _jac_rate_eq_pulse(t, y, abs_matrix, decay_matrix, UC_matrix, jac_indices,
     return _dense_jacobian(system, k, y, pulse=True)
 
 
+def warn_solver_status(st, logger=None, label: str = '') -> bool:
+    '''The reference's messages for a solver that could not reach the end (`odesolver.py:129-134`);
+    returns True when `st` (one `stb_stats` dict) reports a failure.  Non-convergence is not an
+    error: the caller keeps what was computed (rows not reached are zero).'''
+    if st['status'] == 0:
+        return False
+    logger = logger or logging.getLogger(__name__)
+    reasons = {1: 'Excess work done on this call (increase "nsteps").',
+               2: 'Step size underflow.', 3: 'Non-finite values in the right-hand side.'}
+    logger.warning('%s%s', label, reasons.get(st['status'], 'solver failure'))
+    logger.warning('Most likely the ode solver is taking too many steps.')
+    logger.warning('Either change your settings or increase "nsteps".')
+    logger.warning('The program will continue, but the accuracy of the ' +
+                   'results cannot be guaranteed.')
+    return True
+
+
 def _solve_ode(t_arr: np.array, fun: Callable, fargs: Tuple, jfun: Callable, jargs: Tuple,
                initial_population: np.array, rtol: float = 1e-3, atol: float = 1e-15,
                nsteps: int = 1000, method: str = 'bdf', quiet: bool = True) -> np.array:
@@ -104,14 +128,7 @@ def _solve_ode(t_arr: np.array, fun: Callable, fargs: Tuple, jfun: Callable, jar
     y_out, _, stats = system.integrate(np.asarray(t_arr, dtype=np.float64), y0, pulse=pulse,
                                        rtol=rtol, atol=atol, nsteps=nsteps, first=k)
     st = stats[0]
-    if st['status'] != 0:   # pragma: no cover - needs a pathological problem
-        reasons = {1: 'Excess work done on this call (increase "nsteps").',
-                   2: 'Step size underflow.', 3: 'Non-finite values in the right-hand side.'}
-        logger.warning(reasons.get(st['status'], 'solver failure'))
-        logger.warning('Most likely the ode solver is taking too many steps.')
-        logger.warning('Either change your settings or increase "nsteps".')
-        logger.warning('The program will continue, but the accuracy of the ' +
-                       'results cannot be guaranteed.')
+    warn_solver_status(st, logger)
     _solve_ode.last_stats = st
     return y_out[0]
 

@@ -9,9 +9,11 @@ The per-ion-type absorption and decay blocks (`precalculate.py:79-230`) are tiny
 returns are materialised from the device export for API compatibility and carry a reference to
 the device-resident `RateSystem`, which `odesolver.solve_pulse / solve_relax` use directly.
 """
+import collections
 import copy
 import logging
 import os
+import threading
 import time
 from typing import Dict, List, Optional, Tuple
 
@@ -27,6 +29,13 @@ from .util import LatticeError, ion_code
 # (`lattice.py:377-385`, `precalculate.py:755-791`)
 _LATTICE_CACHE: Dict[Tuple, Lattice] = {}
 _SYSTEM_CACHE: Dict[Tuple, RateSystem] = {}
+# device-resident systems of finished sweeps, parked for the next sweep on the same lattice with the
+# same process table (a sweep CHECKS a system OUT: no two threads ever share a handle).  The
+# reference rebuilds every matrix for every power / candidate (`simulations.py:1118,1214`).
+_SYSTEM_POOL: 'collections.OrderedDict[Tuple, List[RateSystem]]' = collections.OrderedDict()
+_SYSTEM_POOL_LOCK = threading.Lock()
+SYSTEM_POOL_MAX = 8                      # parked handles (least recently used are closed)
+SYSTEM_POOL_MAX_BYTES = 24 * 2 ** 30     # of pair data, all parked handles together
 
 
 def absorption_blocks(cte) -> Tuple[np.ndarray, np.ndarray]:
@@ -134,6 +143,95 @@ def check_process_states(cte):
                                'process {}.'.format(name))
 
 
+def _system_key(lat: Lattice, processes, d_max_coop, device: int, d_max=None) -> Tuple:
+    """What the device-resident pair data depends on: the lattice object, which processes exist and
+    are active (strengths of the pair processes are per-system parameters; the cooperative one is
+    baked into the handle), the cutoffs and the device."""
+    return (id(lat), tuple((n, tuple(p.indices), p.mult, bool(np.isclose(p.strength, 0.0)),
+                            p.strength if len(p.type) == 3 else None)
+                           for n, p in processes.items()), d_max_coop, d_max, device)
+
+
+def acquire_system(cte, lat: Lattice, device: int = 0, n_sys: int = 1, processes=None,
+                   d_max: Optional[float] = None) -> RateSystem:
+    """Check a device-resident system for `lat` out of the pool (or build one): the pair build and
+    its device allocations are paid once per lattice, not once per sweep.  Hand it back with
+    `release_system`.  The batch is resized to `n_sys`; blocks and strengths are the caller's to
+    set."""
+    processes = cte['energy_transfer'] if processes is None else processes
+    d_max_coop = cte['lattice'].get('d_max_coop') if hasattr(cte['lattice'], 'get') else None
+    key = _system_key(lat, processes, d_max_coop, device, d_max)
+    system = None
+    with _SYSTEM_POOL_LOCK:
+        parked = _SYSTEM_POOL.get(key)
+        if parked:
+            system = parked.pop()
+            if not parked:
+                del _SYSTEM_POOL[key]
+    if system is None or system.handle is None:
+        check_process_states(cte)
+        system = RateSystem(lat, processes, device=device, d_max=d_max, d_max_coop=d_max_coop)
+        system.pool_key = key
+    system.active_params = None
+    if system.n_sys != n_sys:
+        system.set_batch(n_sys)
+    return system
+
+
+def release_system(system: RateSystem) -> None:
+    """Park a checked-out system for the next sweep on its lattice; the least recently used
+    handles are closed beyond `SYSTEM_POOL_MAX` / `SYSTEM_POOL_MAX_BYTES`."""
+    key = getattr(system, 'pool_key', None)
+    if key is None or system.handle is None:
+        system.close()
+        return
+    evict = []
+    with _SYSTEM_POOL_LOCK:
+        _SYSTEM_POOL.setdefault(key, []).append(system)
+        _SYSTEM_POOL.move_to_end(key)
+
+        def total():
+            return sum(len(v) for v in _SYSTEM_POOL.values()), \
+                sum(s.stream_bytes for v in _SYSTEM_POOL.values() for s in v)
+        count, nbytes = total()
+        while _SYSTEM_POOL and (count > SYSTEM_POOL_MAX or nbytes > SYSTEM_POOL_MAX_BYTES):
+            old_key = next(iter(_SYSTEM_POOL))
+            lst = _SYSTEM_POOL[old_key]
+            evict.append(lst.pop(0))
+            if not lst:
+                del _SYSTEM_POOL[old_key]
+            count, nbytes = total()
+    for old in evict:
+        old.close()
+
+
+def clear_system_pool() -> None:
+    """Close every parked device system (frees their device memory)."""
+    with _SYSTEM_POOL_LOCK:
+        parked = [s for v in _SYSTEM_POOL.values() for s in v]
+        _SYSTEM_POOL.clear()
+    for system in parked:
+        system.close()
+
+
+class ParamSet:
+    """Parameters of ONE operand set returned by `setup_*_eqs`: the per-type blocks and the pair
+    strengths its matrices were built from.  Several operand sets may share a device handle
+    (`_SYSTEM_CACHE`); `odesolver` re-applies the set of the operands it is given before it solves,
+    so operands keep meaning what they meant when they were created."""
+
+    def __init__(self, decay, absorption, strengths):
+        self.decay, self.absorption, self.strengths = decay, absorption, strengths
+
+    def apply(self, system: RateSystem, index: int = 0) -> None:
+        if getattr(system, 'active_params', None) is self:
+            return
+        system.set_decay_blocks(*self.decay, system=index)
+        system.set_abs_blocks(*self.absorption, system=index)
+        system.set_strengths(self.strengths, system=index)
+        system.active_params = self
+
+
 def build_system(cte, lat: Lattice, device: int = 0, d_max: Optional[float] = None,
                  n_sys: int = 1) -> RateSystem:
     """Device-resident system for `lat` with `cte`'s processes; every system of the batch gets
@@ -229,23 +327,23 @@ def _setup_eqs(cte, lat, device, processes, drop_empty):
     cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
     cte['states']['energy_states'] = lat.n_states
     d_max_coop = (cte['lattice'].get('d_max_coop') if hasattr(cte['lattice'], 'get') else None)
-    key = (id(lat), tuple((n, p.indices, p.mult, bool(np.isclose(p.strength, 0.0)),
-                           p.strength if len(p.type) == 3 else None)
-                          for n, p in processes.items()), d_max_coop, device)
+    key = _system_key(lat, processes, d_max_coop, device)
     system = _SYSTEM_CACHE.get(key)
     if system is None or system.handle is None:
         check_process_states(cte)
         system = RateSystem(lat, processes, device=device, d_max_coop=d_max_coop)
-        _SYSTEM_CACHE.clear()          # one resident lattice per process is enough here
+        for old_key in [k for k in _SYSTEM_CACHE if k[-1] == device]:
+            del _SYSTEM_CACHE[old_key]          # one resident lattice per device is enough here
         _SYSTEM_CACHE[key] = system
     check_process_states(cte)
     system.set_batch(1)
     dS, dA = decay_blocks(cte)
     aS, aA = absorption_blocks(cte)
-    system.set_decay_blocks(dS, dA)
-    system.set_abs_blocks(aS, aA)
-    system.set_strengths([p.strength for n, p in processes.items() if len(p.type) == 2]
-                         or np.zeros(0))
+    params = ParamSet((dS, dA), (aS, aA),
+                      np.array([p.strength for n, p in processes.items() if len(p.type) == 2],
+                               dtype=np.float64))
+    system.active_params = None
+    params.apply(system)
     index_S_i, index_A_j, initial_population = system.ground_states()
     total_abs_matrix = _block_diag(aS, aA, index_S_i, index_A_j)
     decay_matrix = _block_diag(dS, dA, index_S_i, index_A_j)
@@ -261,6 +359,7 @@ def _setup_eqs(cte, lat, device, processes, drop_empty):
     coop_ET_matrix, coop_N_indices, coop_jac_indices = system.coop_operands()
     for m in (total_abs_matrix, decay_matrix, ET_matrix, coop_ET_matrix):
         m.stb = (system, 0)
+        m.stb_params = params
     logger.info('Setup finished. Total time: %.2fs.', time.time() - start)
     return (cte, initial_population, list(index_S_i), list(index_A_j), total_abs_matrix,
             decay_matrix, ET_matrix, N_indices, jac_indices, coop_ET_matrix, coop_N_indices,

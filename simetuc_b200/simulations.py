@@ -483,15 +483,33 @@ class Simulations:
                      average: bool = False, gpu_busy: Optional[threading.Event] = None):
         """Integrate `len(ctes)` systems that share `lat` in one batch on `device`.
         Each cte supplies its own absorption / decay blocks (and optionally ET strengths).
-        Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics."""
+        Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics.
+
+        The device system of the lattice is checked out of `precalculate`'s pool (pair build and
+        device buffers are reused by the next sweep on this lattice); pulse and relaxation run
+        in one C-ABI call.  Systems whose solve did not reach the end are reported with the
+        reference's warnings (`odesolver.py:129-134`); a relaxation that would start from an
+        unreached pulse row is blanked (NaN) instead of returned as data."""
+        logger = logging.getLogger(__name__)
         if average:       # same systems, processes at their average strengths (`precalculate.py:999-1003`)
             ctes = [precalculate.average_view(cte) for cte in ctes]
         cte0 = ctes[0]
         n = len(ctes)
-        system = precalculate.build_system(cte0, lat, device=device, n_sys=n)
+        coop0 = [(name, p.strength) for name, p in cte0['energy_transfer'].items() if len(p.type) == 3]
+        for cte in ctes[1:]:
+            if [(name, p.strength) for name, p in cte['energy_transfer'].items()
+                    if len(p.type) == 3] != coop0:
+                raise ValueError('systems of one batch must share the cooperative process strengths '
+                                 '(they are part of the device-resident lattice data)')
+        system = precalculate.acquire_system(cte0, lat, device=device, n_sys=n)
         try:
+            blocks = {}
             for k, cte in enumerate(ctes):
-                system.set_decay_blocks(*precalculate.decay_blocks(cte), system=k)
+                # the decay blocks depend on the decay section only: sweeps share that object
+                dkey = id(cte['decay'])
+                if dkey not in blocks:
+                    blocks[dkey] = precalculate.decay_blocks(cte)
+                system.set_decay_blocks(*blocks[dkey], system=k)
                 system.set_abs_blocks(*precalculate.absorption_blocks(cte), system=k)
                 if strengths is not None:
                     system.set_strengths(strengths[k], system=k)
@@ -503,28 +521,36 @@ class Simulations:
             params = cte0['simulation_params']
             rtol, atol, N_steps = params['rtol'], params['atol'], params['N_steps']
             tf = self._get_t_simulation()
+            if gpu_busy is not None:
+                gpu_busy.set()      # the long call: the GIL is free until it returns
             if dynamics:
                 tf_p = self._get_t_pulse()
                 t_pulse = np.linspace(0, tf_p, 2, dtype=np.float64)
-                y_p, _, st_p = system.integrate(t_pulse, y0, pulse=True, rtol=rtol, atol=atol)
                 t_sol = np.logspace(np.log10(tf_p), np.log10(tf), N_steps, dtype=np.float64)
-                if gpu_busy is not None:
-                    gpu_busy.set()      # the long call: the GIL is free until it returns
-                y, avg, st = system.integrate(t_sol, y_p[:, -1], pulse=False, rtol=rtol, atol=atol,
-                                              want_y=keep_y, want_avg=True)
+                _, y, avg, st_p, st = system.integrate_dynamics(
+                    t_pulse, t_sol, y0, rtol=rtol, atol=atol, want_y=keep_y, want_avg=True)
                 t_out = t_sol - t_sol[0]
                 stats = [dict(pulse=a, relax=b) for a, b in zip(st_p, st)]
+                for k, (a, b) in enumerate(zip(st_p, st)):
+                    if odesolver.warn_solver_status(a, logger, 'system %d, pulse: ' % k):
+                        logger.warning('system %d: the pulse did not reach its end, its relaxation '
+                                       'is not returned', k)
+                        avg[k] = np.nan
+                        if y is not None:
+                            y[k] = np.nan
+                    else:
+                        odesolver.warn_solver_status(b, logger, 'system %d, relaxation: ' % k)
             else:
                 t_out = np.linspace(0, tf, N_steps)
-                if gpu_busy is not None:
-                    gpu_busy.set()
                 y, avg, st = system.integrate(t_out, y0, pulse=True, rtol=rtol, atol=atol,
                                               nsteps=1000, want_y=keep_y, want_avg=True)
                 stats = [dict(pulse=a) for a in st]
+                for k, a in enumerate(st):
+                    odesolver.warn_solver_status(a, logger, 'system %d: ' % k)
             return [(t_out, None if y is None else y[k], avg[k]) for k in range(n)], \
                 list(index_S_i), list(index_A_j), stats
         finally:
-            system.close()
+            precalculate.release_system(system)
 
     def _sweep_same_lattice(self, ctes: List[Any], dynamics: bool, keep_y: bool = True,
                             strengths: Optional[np.ndarray] = None, average: bool = False,
@@ -561,39 +587,34 @@ class Simulations:
         power_dens_list = [float(elem) for elem in list(power_dens_list)]
         pulsed = self._is_pulsed()
         # The device only needs the absorption block of every power: the batch is launched from
-        # light settings (shared sections, private excitations) and the full per-solution copies
-        # the reference makes (`simulations.py:1290`) are built while the GPU integrates.
+        # light settings (shared sections, private excitations)
         light = []
         for power_dens in power_dens_list:
             cte = copy.copy(self.cte)
-            cte['excitations'] = copy.deepcopy(self.cte['excitations'])
+            cte['excitations'] = type(self.cte['excitations'])(
+                (label, [copy.copy(exc) for exc in exc_list])
+                for label, exc_list in self.cte['excitations'].items())
             for exc_list in cte['excitations'].values():
                 for exc in exc_list:
                     exc.power_dens = power_dens
             light.append(cte)
-        with concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-            busy = threading.Event()
-            pending = pool.submit(self._sweep_same_lattice, light, dynamics=pulsed, keep_y=keep_y,
-                                  average=average, gpu_busy=busy)
-            # copy only once the worker sits in its long solver call: before that it needs the GIL
-            # every few microseconds and a copying main thread would hold it 5 ms at a time
-            while not busy.wait(0.002) and not pending.done():
-                pass
-            ctes = []
-            for power_dens in power_dens_list:
-                cte = copy.deepcopy(self.cte)
-                for exc_list in cte['excitations'].values():
-                    for exc in exc_list:
-                        exc.power_dens = power_dens
-                ctes.append(cte)
-            sols, index_S_i, index_A_j, lat, stats = pending.result()
+        sols, index_S_i, index_A_j, lat, stats = self._sweep_same_lattice(
+            light, dynamics=pulsed, keep_y=keep_y, average=average)
+        # per-solution settings (the reference deep-copies everything, `simulations.py:1290`): only
+        # what differs between the solutions or is written per solution is private - the
+        # excitations (made for the batch above), the state and ion counts; the other sections are
+        # shared, read-only views of this Simulations' settings
+        ctes = []
+        for cte in light:
+            cte['states'] = copy.copy(self.cte['states'])
+            ctes.append(cte)
         solutions = []
         for cte, (t_sol, y_sol, avg), st in zip(ctes, sols, stats):
             cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
             cte['states']['energy_states'] = lat.n_states
             if pulsed and y_sol is not None:
                 sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
-                                       average=average).calculate_steady_state()
+                                       average=average, own_cte=True).calculate_steady_state()
             elif pulsed:
                 # keep_y=False: the ion average commutes with the time integral, so the area
                 # under the device-computed emission curves gives the same steady state without

@@ -244,8 +244,11 @@ def test_group_sizes_agree(monkeypatch):
         assert st[0]['status'] == 0
         res[G] = y[0, -1]
     monkeypatch.delenv('STB_GROUP_CTAS')
-    for G in (4, 16):
-        assert np.all(np.abs(res[G] - res[1]) <= 1e-9 * np.abs(res[1]) + 1e-18)
+    # G = 1, 4: the cluster integrator with 1 and 4 CTAs per system (same arithmetic, different
+    # reduction order); G = 16: the grid integrator (no lagged block inverses: another path to the
+    # same solution, equal within the integration tolerance rtol 1e-8, atol 1e-15)
+    assert np.all(np.abs(res[4] - res[1]) <= 1e-9 * np.abs(res[1]) + 1e-18)
+    assert np.all(np.abs(res[16] - res[1]) <= 1e-6 * np.abs(res[1]) + 1e-15)
     system.close()
 
 
@@ -518,8 +521,8 @@ def test_tma_inside_grid_integrator(monkeypatch):
         res[mode] = (y_p[0, -1], y[0], st[0]['n_steps'])
     # the fields are bit-identical, the CTA-level sums (norms, dot products) group the rows by
     # consumer warp and differ in round-off: same trajectory within the parity tolerance, step
-    # counts within 1 %
-    assert abs(res['0'][2] - res['1'][2]) <= 0.01 * res['0'][2]
+    # counts within 5 % (round-off decides borderline step-size choices of a ~4000-step solve)
+    assert abs(res['0'][2] - res['1'][2]) <= 0.05 * res['0'][2]
     assert parity_metric(res['1'][0], res['0'][0]) <= 1.0
     assert parity_metric(res['1'][1], res['0'][1]) <= 1.0
     system.close()

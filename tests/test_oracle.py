@@ -11,7 +11,7 @@ import pytest
 
 from oracle import oracle_np as onp
 from simetuc_b200 import configs
-from tests.helpers import GOLDEN, SMALL, load_golden, oracle_operands
+from tests.helpers import GOLDEN, SMALL, load_golden, oracle_operands, pair_processes
 
 
 def sha(a):
@@ -165,3 +165,27 @@ def test_c2_golden_is_self_consistent():
     # more power, more excitation: the Yb excited-state population right after the pulse grows
     exc = [gold['y_pulse_end'][s][np.asarray(iS).ravel()[np.asarray(iS).ravel() != -1] + 1].mean() for s in range(3)]
     assert exc[0] < exc[1] < exc[2]
+
+
+def test_row_sampled_operators_match_the_full_ones():
+    """`oracle_np.rate_eq_rows` (the O(n)-per-ion check used for lattices whose reference operands
+    do not fit in memory) against the full reference-layout RHS and Jacobian-vector product."""
+    from simetuc_b200 import configs, lattice
+    cte = configs.yb_tm_cte(N_uc=6, S_conc=12.0, A_conc=2.0, power_dens=1e7)
+    lat = lattice.generate_arrays(cte, seed=77)
+    L = lat['lattice']
+    g = {'ion_type': lat['ion_type'], 'dist_array': lat['dist_array'], 'info': np.array([2, 9])}
+    op = oracle_operands(g, cte)
+    rng = np.random.default_rng(3)
+    y = 10.0 ** rng.uniform(-12, 0, op['N'])
+    v = rng.standard_normal(op['N'])
+    cM, cN, _ = op['coop']
+    f_full = onp.rate_eq_pulse(0.0, y, op['abs'], op['decay'], op['ET'], op['N_indices'], cM, cN)
+    jv_full = onp.jac_vec(y, v, (op['abs'] + op['decay']).tocsr(), op['ET'], op['N_indices'])
+    aS, aA = onp.absorption_blocks(2, 9, cte['excitations'])
+    dS, dA = onp.decay_blocks(2, 9, cte['decay'])
+    ions = rng.choice(len(lat['ion_type']), size=12, replace=False)
+    idx, f_rows, jv_rows = onp.rate_eq_rows(ions, lat['ion_type'], L.positions, L.cell, 2, 9,
+                                            pair_processes(cte), aS + dS, aA + dA, y, v)
+    assert np.all(np.abs(f_rows - f_full[idx]) <= 1e-13 * np.abs(f_full).max())
+    assert np.all(np.abs(jv_rows - jv_full[idx]) <= 1e-13 * np.abs(jv_full).max())
