@@ -187,6 +187,38 @@ int stb_integrate_dynamics(stb_system* sys, int32_t first, int32_t n, int64_t n_
                            double rtol, double atol, int64_t nsteps_pulse, int64_t nsteps,
                            double* y_pulse_out, double* y_out, double* avg_out,
                            stb_stats* stats_pulse, stb_stats* stats_relax);
+/* Same with DEVICE buffers (bench.py: operands resident in HBM): t_pulse_dev [n_tp], t_sol_dev [n_t],
+ * y0 in the internal plane layout [n, N] (left untouched), outputs in reference layout (any may be
+ * NULL).  stats_* are HOST pointers. */
+int stb_integrate_dynamics_dev(stb_system* sys, int32_t first, int32_t n, int64_t n_tp,
+                               const double* t_pulse_dev, int64_t n_t, const double* t_sol_dev,
+                               const double* y0_planes_dev, double rtol, double atol,
+                               int64_t nsteps_pulse, int64_t nsteps, double* y_pulse_out_dev,
+                               double* y_out_dev, double* avg_out_dev, stb_stats* stats_pulse,
+                               stb_stats* stats_relax);
+/* ---- optimisation objective on the device ------------------------------------------------------
+ * Replaces DynamicsSolution._get_background / _interpolate_sim_data / _calc_errors
+ * (simulations.py:425-527) for batches of candidate parameter sets (optimize.py:79-107): the
+ * emission curves never leave the device, only [n, sS+sA] deviations come back.
+ * stb_set_experiment: the experimental decay curve of state kind `kind` (0..sS+sA-1, S states
+ * first): n_e points (t_exp seconds, y_exp normalised as DynamicsSolution._load_exp_data does on
+ * the host, simulations.py:354-422) and tail_mean = mean of the last 50 non-zero counts
+ * (simulations.py:437-441).  n_e = 0 removes the curve (deviation 0, simulations.py:520-522).
+ * stb_objective: errors[n, sS+sA] of the curves of the last stb_integrate_dynamics call (n = its
+ * batch size): 1/mean(sim) * sqrt(mean((sim - exp * max(sim))^2)) with sim interpolated onto the
+ * experimental times, the scaled background outside the simulated range. */
+int stb_set_experiment(stb_system* sys, int32_t kind, int64_t n_e, const double* t_exp,
+                       const double* y_exp, double tail_mean);
+int stb_objective(stb_system* sys, int32_t n, double* errors);
+/* Per-handle options.  "sm_budget": number of SMs one solve of this handle may occupy (default: all).
+ * Callers that run several handles concurrently on one GPU - one lattice each, as in
+ * Simulations.simulate_concentration_dependence (simulations.py:1356-1372) and sample_simulation
+ * (:1412-1417) - give every handle its share, so that the launches are co-resident and the
+ * integrator is chosen for throughput of the whole sweep rather than for the latency of one solve. */
+int stb_set_option(stb_system* sys, const char* name, double value);
+/* Device time (ms, CUDA events) of the pulse and of the relaxation kernel of the last
+ * stb_integrate_dynamics[_dev] call. */
+int stb_last_timing_dynamics(const stb_system* sys, float* ms_pulse, float* ms_relax);
 /* The CUDA stream (cudaStream_t) every kernel of this system is launched on, so that callers can
  * record their own events on it; and the number of kernels launched by the library so far. */
 void* stb_stream(const stb_system* sys);

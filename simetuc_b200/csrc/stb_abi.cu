@@ -14,6 +14,7 @@
 #include "stb_build.cuh"
 #include "stb_integrate.cuh"
 #include "stb_integrate_cl.cuh"
+#include "stb_integrate_cl2.cuh"
 #include "stb_kernels.cuh"
 #include "stb_tma.cuh"
 
@@ -307,11 +308,12 @@ struct stb_system {
     // scratch for rhs/jv
     double *d_y = nullptr, *d_v = nullptr, *d_out = nullptr, *d_F = nullptr, *d_tmp = nullptr;
     int64_t scratch_n = 0;
-    float last_ms = 0.f;
+    float last_ms = 0.f, last_ms_pulse = 0.f, last_ms_relax = 0.f;
     std::vector<long long> last_prof;
     int last_G = 0, last_groups = 0;
     int64_t last_launches = 0;
     int sm_count = 148;
+    int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
     enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR,
@@ -326,6 +328,17 @@ struct stb_system {
     std::vector<double> h_coop_w;        // [Mc] strength * geometry
     void* d_coop[3][4] = {};             // per role: row_ptr, p1, p2, w
     int n_terms_pair[2] = {0, 0}, nf_pair[2] = {0, 0};
+    // optimisation objective: experimental decay curves per state kind (host copies; uploaded lazily)
+    std::vector<std::vector<double>> exp_t, exp_y;
+    std::vector<double> exp_tail;
+    bool exp_dirty = false;
+    double *d_exp_t = nullptr, *d_exp_y = nullptr, *d_exp_tail = nullptr, *d_obj = nullptr;
+    int64_t* d_exp_off = nullptr;
+    int64_t exp_cap = 0, obj_cap = 0;
+    // curves of the last stb_integrate_dynamics call (device): what stb_objective evaluates
+    const double *last_avg = nullptr, *last_ts = nullptr;
+    int last_dyn_n = 0;
+    int64_t last_dyn_nt = 0;
 };
 
 // grow-only workspace slot of the handle
@@ -427,6 +440,11 @@ extern "C" void stb_system_destroy(stb_system* S) {
     pool_free(S->d_F);
     pool_free(S->d_tmp);
     for (int k = 0; k < stb_system::WS_COUNT; ++k) pool_free(S->ws_ptr[k]);
+    pool_free(S->d_exp_t);
+    pool_free(S->d_exp_y);
+    pool_free(S->d_exp_tail);
+    pool_free(S->d_exp_off);
+    pool_free(S->d_obj);
     for (int r = 0; r < 3; ++r)
         for (int k = 0; k < 4; ++k) pool_free(S->d_coop[r][k]);
     if (S->ev0) cudaEventDestroy(S->ev0);
@@ -1174,15 +1192,30 @@ struct HostTimer {
 
 typedef void (*ClKernel)(ClArgs);
 // the plain cluster integrator, or the instance with the cooperative field pass
-static ClKernel cl_kernel(const stb_system* S) {
+// v2: the ion-major layout of the inner loops (stb_integrate_cl2.cuh)
+static ClKernel cl_kernel(const stb_system* S, bool v2) {
+    if (v2) return S->hL.n_coop ? (ClKernel)k_integrate_cl2_t<true> : (ClKernel)k_integrate_cl2_t<false>;
     return S->hL.n_coop ? (ClKernel)k_integrate_cl_t<true> : (ClKernel)k_integrate_cl_t<false>;
 }
 
 struct ClPlan {
     int G = 0, n_clusters = 0, resmask = 0, v_smem = 0, d_smem = 0;
+    bool v2 = false;           // k_integrate_cl2_t (every CTA's ion states fit its threads)
     size_t dyn_bytes = 0;
     double resident_frac = 0.0;
+    double est_us = 0.0;       // estimated time of one pair pass x rounds of the batch (see est_* below)
 };
+
+// Time model of one pair pass (microseconds), fitted to measurements on B200
+// (profiles/r02_midsize.txt): the cluster integrator pays a small fixed latency per pass and reads
+// the rows that do not fit in shared memory at ~20 GB/s per CTA; the grid integrator pays ~30 us of
+// group barriers / reductions per pass and streams at ~27 GB/s per CTA (L2-resident data, G <= 64).
+static double est_cluster_pass_us(int G, double stream_bytes, double resident_frac) {
+    return 4.0 + 16.0 / G + stream_bytes * (1.0 - resident_frac) / G / 20e3;
+}
+static double est_grid_pass_us(int G, double stream_bytes) {
+    return 28.0 + 0.1 * G + stream_bytes / (std::min(G, 64) * 27e3);
+}
 
 static cudaError_t cl_max_clusters(ClKernel kern, int G, size_t dyn_bytes, int sm_count, int* out) {
     cudaError_t e = allow_max_smem(kern);
@@ -1207,16 +1240,13 @@ static cudaError_t cl_max_clusters(ClKernel kern, int G, size_t dyn_bytes, int s
 static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
     const DevLattice& L = S->hL;
     if (!L.dense || L.n_mult != 1) return false;
-    if (const char* env = getenv("STB_CLUSTER")) if (atoi(env) == 0) return false;
     int forced = 0;
     if (const char* env = getenv("STB_GROUP_CTAS")) {
         forced = atoi(env);
         if (forced != 1 && forced != 2 && forced != 4 && forced != 8) return false;
     }
-    cudaFuncAttributes fa;
-    ClKernel kern = cl_kernel(S);
-    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); return false; }
-    const size_t cap = 232448 - fa.sharedSizeBytes - 256;  // 227 KB per CTA, minus the slack below
+    bool allow_v2 = true;
+    if (const char* env = getenv("STB_CL_V")) allow_v2 = atoi(env) != 1;
     int want_res = 1;
     if (const char* env = getenv("STB_RESIDENT")) want_res = atoi(env) != 0;
     ClPlan best;
@@ -1224,7 +1254,13 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
     for (int G = 8; G >= 1; G >>= 1) {
         if (forced && G != forced) continue;
         ClLayout Y;
-        cl_layout(L, G, 0, 0, 0, Y);
+        cl_layout(L, G, 0, 0, 0, Y);    // (ownership counts only)
+        const bool v2 = allow_v2 && cl2_threads(L, Y.cntm[0], Y.cntm[1]) <= STB_NT;
+        cudaFuncAttributes fa;
+        ClKernel kern = cl_kernel(S, v2);
+        if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) { cudaGetLastError(); continue; }
+        const size_t cap = 232448 - fa.sharedSizeBytes - 256;  // 227 KB per CTA, minus the slack below
+        cl_layout(L, G, 0, 0, 0, Y, v2);
         if ((Y.cntp[0] + Y.cntp[1]) / CL_RG > CL_MAXRG) continue;
         if ((size_t)Y.total * 8 > cap) continue;
         // shared memory goes first to the pair rows (largest block first), then to the Krylov
@@ -1243,25 +1279,29 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
             if (pick < 0) break;
             used[pick] = true;
             ClLayout Z;
-            cl_layout(L, G, mask | (1 << pick), 0, 0, Z);
+            cl_layout(L, G, mask | (1 << pick), 0, 0, Z, v2);
             if ((size_t)Z.total * 8 <= cap) { mask |= 1 << pick; res += pick_sz; }
         }
         {
             // then the first 8 Krylov basis vectors (touched in every iteration), then the BDF
             // difference array (touched once per step), then the rest of the basis
             ClLayout Z;
+            // the difference array is touched in every step, basis vectors beyond the first few
+            // only by long linear solves: D first (with at least 4 vectors), then more vectors
+            for (int c = 8; c >= 4 && !d_smem; --c) {
+                cl_layout(L, G, mask, c, 1, Z, v2);
+                if ((size_t)Z.total * 8 <= cap) { v_smem = c; d_smem = 1; }
+            }
             for (int c = 8; c >= 1 && !v_smem; --c) {
-                cl_layout(L, G, mask, c, 0, Z);
+                cl_layout(L, G, mask, c, 0, Z, v2);
                 if ((size_t)Z.total * 8 <= cap) v_smem = c;
             }
-            cl_layout(L, G, mask, v_smem, 1, Z);
-            if ((size_t)Z.total * 8 <= cap) d_smem = 1;
             for (int c = STB_KRYLOV + 1; c > v_smem; --c) {
-                cl_layout(L, G, mask, c, d_smem, Z);
+                cl_layout(L, G, mask, c, d_smem, Z, v2);
                 if ((size_t)Z.total * 8 <= cap) { v_smem = c; break; }
             }
         }
-        cl_layout(L, G, mask, v_smem, d_smem, Y);
+        cl_layout(L, G, mask, v_smem, d_smem, Y, v2);
         // 128 B of slack: the compiler may align the dynamic shared memory base above the end of the
         // static variables (any `extern __shared__ __align__(n)` in the library does it for every
         // kernel), and the layout must still fit behind it
@@ -1269,11 +1309,16 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
         int maxc = 0;
         cudaError_t e = cl_max_clusters(kern, G, bytes, S->sm_count, &maxc);
         if (e != cudaSuccess || maxc < 1) { cudaGetLastError(); continue; }
-        // rounds of the batch x time of one system (falls with G, less than linearly; streaming
-        // the pair rows from L2 instead of shared memory roughly doubles a pass)
+        maxc = std::max(1, std::min(maxc, S->sm_budget / G));
+        if (G > S->sm_budget && G > 1) continue;
+        // rounds of the batch x time of one pass of one system
         const int ncl = std::min(maxc, n);
         const double rounds = std::ceil((double)n / ncl);
         const double rf = all > 0 ? (double)res / (double)all : 1.0;
+        const double t_est = rounds * est_cluster_pass_us(G, (double)S->stream_bytes, rf);
+        // between cluster sizes: rounds of the batch x time of one system (falls with G, less than
+        // linearly; streaming the pair rows from L2 instead of shared memory roughly doubles a
+        // pass) - fitted on batches, where every SM streams at once
         const double t_sys = (2.0 - rf) * (0.35 + 1.0 / G);
         const double score = 1.0 / (rounds * t_sys);
         if (score > best_score) {
@@ -1281,6 +1326,8 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
             best.G = G; best.n_clusters = ncl; best.resmask = mask;
             best.v_smem = v_smem; best.d_smem = d_smem; best.dyn_bytes = bytes;
             best.resident_frac = rf;
+            best.v2 = v2;
+            best.est_us = t_est;
         }
     }
     if (best_score < 0.0) return false;
@@ -1295,7 +1342,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     const DevLattice& L = S->hL;
     HostTimer tm;
     ClLayout Y;
-    cl_layout(L, plan.G, plan.resmask, plan.v_smem, plan.d_smem, Y);
+    cl_layout(L, plan.G, plan.resmask, plan.v_smem, plan.d_smem, Y, plan.v2);
     const int64_t work_stride = (int64_t)(STB_KRYLOV + 1 + 8) * Y.PO;
     double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_tmp = nullptr,
            *d_avg = nullptr;
@@ -1348,6 +1395,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.L = S->dL; A.blocks = S->d_blocks; A.strengths = S->d_strengths;
     A.first = first; A.n_sys = n; A.pulse = pulse; A.G = plan.G;
     A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
+    A.compact = plan.v2 ? 1 : 0;
     A.opts = CL_OPT_GUESS | CL_OPT_LAGPC;
     if (const char* env = getenv("STB_CL_OPTS")) A.opts = atoi(env);
     A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;
@@ -1357,8 +1405,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.prof = d_prof;
     S->last_G = plan.G; S->last_groups = plan.n_clusters;
     if (getenv("STB_VERBOSE"))
-        fprintf(stderr, "[stb] cluster integrator: n=%d G=%d clusters=%d resmask=%x (%.0f%% of pair rows "
-                "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d\n", n, plan.G, plan.n_clusters,
+        fprintf(stderr, "[stb] cluster integrator v%d: n=%d G=%d clusters=%d resmask=%x (%.0f%% of pair rows "
+                "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d\n", plan.v2 ? 2 : 1, n, plan.G, plan.n_clusters,
                 plan.resmask, 100.0 * plan.resident_frac, plan.v_smem, plan.d_smem, plan.dyn_bytes, Y.PO);
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKC(cudaEventRecord(e0, S->stream));
@@ -1377,7 +1425,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         cfg.attrs = &at;
         cfg.numAttrs = 1;
         g_launches++;
-        ClKernel kern = cl_kernel(S);
+        ClKernel kern = cl_kernel(S, plan.v2);
         CKC(allow_max_smem(kern));
         CKC(cudaLaunchKernelEx(&cfg, kern, A));
     }
@@ -1436,6 +1484,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
             const double den = unit[k] == 'p' ? nrhs + njv : unit[k] == 'n' ? nrhs : unit[k] == 'k' ? njv : steps;
             fprintf(stderr, " %s=%.0f/%c(%.0f%%)", names[k], pr[k] / den, unit[k], 100.0 * pr[k] / std::max(tot, 1.0));
         }
+        fprintf(stderr, " | extra probes [20..23] per Krylov it: %.0f %.0f %.0f %.0f", pr[20] / njv, pr[21] / njv, pr[22] / njv, pr[23] / njv);
         fprintf(stderr, "\n");
     }
     return STB_OK;
@@ -1459,10 +1508,28 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     const int NMinv = L.s[0] * L.s[0] * L.n[0] + L.s[1] * L.s[1] * L.n[1];
 
     // ---- small lattices: one thread-block cluster per system (stb_integrate_cl.cuh) ------------
+    // ---- launch shape of the persistent cooperative grid: groups of G CTAs ------------------------
+    const int max_ctas = std::max(1, std::min(S->sm_count, S->sm_budget));   // one CTA per SM
+    const int total_slices = L.n_slices[0] + L.n_slices[1];
+    // a CTA wants at least ~2 slices per warp; never more CTAs per group than that allows
+    int G_work = std::max(1, total_slices / (2 * STB_NW));
+    int G = std::max(1, std::min(max_ctas / std::min(n, max_ctas), G_work));
+    // ---- small lattices: one thread-block cluster per system (stb_integrate_cl.cuh), unless the
+    //      grid is estimated faster (pair rows that do not fit in shared memory: est_*_pass_us) ----
     {
         ClPlan plan;
         HostTimer tm;
-        const bool use_cl = cl_choose(S, n, plan);
+        bool use_cl = cl_choose(S, n, plan);
+        if (use_cl && !S->hL.n_coop && n <= plan.n_clusters) {
+            // the whole batch runs at once: the latency of one solve decides
+            const int groups = std::max(1, std::min(max_ctas / G, n));
+            const double grid_us = std::ceil((double)n / groups) * est_grid_pass_us(G, (double)S->stream_bytes);
+            if (grid_us < plan.est_us) use_cl = false;
+        }
+        if (const char* env = getenv("STB_CLUSTER")) {
+            if (atoi(env) == 0) use_cl = false;
+            else if (plan.G > 0) use_cl = true;
+        }
         tm.mark("cl_choose");
         if (use_cl)
             return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
@@ -1472,12 +1539,6 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         return fail(STB_EINVAL, "cooperative energy transfer is integrated by the cluster integrator only, "
                                 "and this lattice does not fit it (all-to-all pairs, one multipolarity, "
                                 "state vector within the shared memory of 8 SMs)");
-    // ---- launch shape: persistent cooperative grid split into groups of G CTAs ------------------
-    const int max_ctas = S->sm_count;   // one CTA per SM
-    const int total_slices = L.n_slices[0] + L.n_slices[1];
-    // a CTA wants at least ~2 slices per warp; never more CTAs per group than that allows
-    int G_work = std::max(1, total_slices / (2 * STB_NW));
-    int G = std::max(1, std::min(max_ctas / std::min(n, max_ctas), G_work));
     // small systems: the gathered vector is staged in shared memory and barriers leave L1 warm;
     // if, with a few more CTAs per group, every CTA's own pair rows also fit in shared memory,
     // they are made resident there (the Krylov loop then runs out of shared memory)
@@ -1639,40 +1700,56 @@ extern "C" int stb_integrate_dev(stb_system* S, int32_t first, int32_t n, int32_
                           y_out_dev, avg_out_dev, stats, true);
 }
 
-extern "C" int stb_integrate_dynamics(stb_system* S, int32_t first, int32_t n, int64_t n_tp,
-                                      const double* t_pulse, int64_t n_t, const double* t_sol,
-                                      const double* y0, double rtol, double atol, int64_t nsteps_pulse,
-                                      int64_t nsteps, double* y_pulse_out, double* y_out, double* avg_out,
-                                      stb_stats* stats_pulse, stb_stats* stats_relax) {
+// pulse + relaxation; dev: every array pointer except the statistics is a device pointer
+// (t_pulse, t_sol; y0 in the plane layout; outputs in the reference layout) and nothing is copied
+static int integrate_dynamics_core(stb_system* S, int32_t first, int32_t n, int64_t n_tp,
+                                   const double* t_pulse, int64_t n_t, const double* t_sol,
+                                   const double* y0, double rtol, double atol, int64_t nsteps_pulse,
+                                   int64_t nsteps, double* y_pulse_out, double* y_out, double* avg_out,
+                                   stb_stats* stats_pulse, stb_stats* stats_relax, bool dev) {
     int rc = check_range(S, first, n);
     if (rc) return rc;
     if (n_tp < 2 || n_t < 1 || !t_pulse || !t_sol || !y0)
         return fail(STB_EINVAL, "bad time grids / initial state");
-    for (int64_t k = 1; k < n_tp; ++k)
-        if (!(t_pulse[k] > t_pulse[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
-    for (int64_t k = 1; k < n_t; ++k)
-        if (!(t_sol[k] > t_sol[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    if (!dev) {
+        for (int64_t k = 1; k < n_tp; ++k)
+            if (!(t_pulse[k] > t_pulse[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+        for (int64_t k = 1; k < n_t; ++k)
+            if (!(t_sol[k] > t_sol[k - 1])) return fail(STB_EINVAL, "output times must increase strictly");
+    }
     CK(cudaSetDevice(S->device));
     HostTimer tm;
     const int N = S->N;
     const int kinds = S->hL.s[0] + S->hL.s[1];
     double *d_t = nullptr, *d_tmp = nullptr, *d_y0 = nullptr, *d_yp = nullptr, *d_ys = nullptr, *d_avg = nullptr;
     const size_t vec_bytes = sizeof(double) * (size_t)n * N;
-    CK(ws_get(S, stb_system::WS_DYN_T, sizeof(double) * (size_t)(n_tp + n_t), (void**)&d_t));
-    CK(ws_get(S, stb_system::WS_DYN_TMP, vec_bytes, (void**)&d_tmp));
-    CK(ws_get(S, stb_system::WS_DYN_Y0, vec_bytes, (void**)&d_y0));
-    CK(ws_get(S, stb_system::WS_DYN_YP, vec_bytes * n_tp, (void**)&d_yp));
-    if (y_out) CK(ws_get(S, stb_system::WS_DYN_YS, vec_bytes * n_t, (void**)&d_ys));
-    if (avg_out) CK(ws_get(S, stb_system::WS_DYN_AVG, sizeof(double) * (size_t)n * n_t * kinds, (void**)&d_avg));
-    CK(cudaMemcpyAsync(d_t, t_pulse, sizeof(double) * n_tp, cudaMemcpyHostToDevice, S->stream));
-    CK(cudaMemcpyAsync(d_t + n_tp, t_sol, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
-    CK(cudaMemcpyAsync(d_tmp, y0, vec_bytes, cudaMemcpyHostToDevice, S->stream));
     const int64_t tot = (int64_t)n * N;
-    g_launches++;
-    k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
-    CK(cudaGetLastError());
+    const double *tp_p = t_pulse, *ts_p = t_sol;
+    CK(ws_get(S, stb_system::WS_DYN_Y0, vec_bytes, (void**)&d_y0));
+    if (dev) {
+        // the relaxation overwrites its start vector's buffer: keep the caller's y0 intact
+        d_yp = y_pulse_out;
+        d_ys = y_out;
+        d_avg = avg_out;
+    } else {
+        CK(ws_get(S, stb_system::WS_DYN_T, sizeof(double) * (size_t)(n_tp + n_t), (void**)&d_t));
+        CK(ws_get(S, stb_system::WS_DYN_TMP, vec_bytes, (void**)&d_tmp));
+        if (y_out) CK(ws_get(S, stb_system::WS_DYN_YS, vec_bytes * n_t, (void**)&d_ys));
+        if (avg_out || !S->exp_t.empty())
+            CK(ws_get(S, stb_system::WS_DYN_AVG, sizeof(double) * (size_t)n * n_t * kinds, (void**)&d_avg));
+        CK(cudaMemcpyAsync(d_t, t_pulse, sizeof(double) * n_tp, cudaMemcpyHostToDevice, S->stream));
+        CK(cudaMemcpyAsync(d_t + n_tp, t_sol, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
+        CK(cudaMemcpyAsync(d_tmp, y0, vec_bytes, cudaMemcpyHostToDevice, S->stream));
+        g_launches++;
+        k_ref_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(S->d_plane_of_ref, N, n, d_tmp, d_y0);
+        CK(cudaGetLastError());
+        tp_p = d_t;
+        ts_p = d_t + n_tp;
+    }
+    if (!d_yp) CK(ws_get(S, stb_system::WS_DYN_YP, vec_bytes * n_tp, (void**)&d_yp));
     tm.mark("inputs");
-    rc = integrate_core(S, first, n, 1, n_tp, d_t, d_y0, rtol, atol, nsteps_pulse, d_yp, nullptr, stats_pulse, true);
+    rc = integrate_core(S, first, n, 1, n_tp, tp_p, dev ? y0 : d_y0, rtol, atol, nsteps_pulse, d_yp, nullptr,
+                        stats_pulse, true);
     if (rc) return rc;
     const float ms_pulse = S->last_ms;
     const int64_t launches_pulse = S->last_launches;
@@ -1682,17 +1759,125 @@ extern "C" int stb_integrate_dynamics(stb_system* S, int32_t first, int32_t n, i
     k_row_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(
         S->d_plane_of_ref, N, n, d_yp + (n_tp - 1) * (int64_t)N, n_tp * (int64_t)N, d_y0);
     CK(cudaGetLastError());
-    rc = integrate_core(S, first, n, 0, n_t, d_t + n_tp, d_y0, rtol, atol, nsteps, d_ys, d_avg, stats_relax, true);
+    rc = integrate_core(S, first, n, 0, n_t, ts_p, d_y0, rtol, atol, nsteps, d_ys, d_avg, stats_relax, true);
     if (rc) return rc;
     tm.mark("relax");
+    S->last_avg = d_avg;
+    S->last_ts = ts_p;
+    S->last_dyn_n = n;
+    S->last_dyn_nt = n_t;
+    S->last_ms_pulse = ms_pulse;
+    S->last_ms_relax = S->last_ms;
     S->last_ms += ms_pulse;
-    S->last_launches += launches_pulse + 2;
-    if (y_pulse_out) CK(cudaMemcpyAsync(y_pulse_out, d_yp, vec_bytes * n_tp, cudaMemcpyDeviceToHost, S->stream));
-    if (y_out) CK(cudaMemcpyAsync(y_out, d_ys, vec_bytes * n_t, cudaMemcpyDeviceToHost, S->stream));
-    if (avg_out)
-        CK(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * kinds, cudaMemcpyDeviceToHost, S->stream));
-    CK(cudaStreamSynchronize(S->stream));
-    tm.mark("d2h");
+    S->last_launches += launches_pulse + (dev ? 1 : 2);
+    if (!dev) {
+        if (y_pulse_out) CK(cudaMemcpyAsync(y_pulse_out, d_yp, vec_bytes * n_tp, cudaMemcpyDeviceToHost, S->stream));
+        if (y_out) CK(cudaMemcpyAsync(y_out, d_ys, vec_bytes * n_t, cudaMemcpyDeviceToHost, S->stream));
+        if (avg_out)
+            CK(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * kinds, cudaMemcpyDeviceToHost, S->stream));
+        CK(cudaStreamSynchronize(S->stream));
+        tm.mark("d2h");
+    }
+    return STB_OK;
+}
+
+extern "C" int stb_integrate_dynamics(stb_system* S, int32_t first, int32_t n, int64_t n_tp,
+                                      const double* t_pulse, int64_t n_t, const double* t_sol,
+                                      const double* y0, double rtol, double atol, int64_t nsteps_pulse,
+                                      int64_t nsteps, double* y_pulse_out, double* y_out, double* avg_out,
+                                      stb_stats* stats_pulse, stb_stats* stats_relax) {
+    return integrate_dynamics_core(S, first, n, n_tp, t_pulse, n_t, t_sol, y0, rtol, atol, nsteps_pulse, nsteps,
+                                   y_pulse_out, y_out, avg_out, stats_pulse, stats_relax, false);
+}
+
+extern "C" int stb_integrate_dynamics_dev(stb_system* S, int32_t first, int32_t n, int64_t n_tp,
+                                          const double* t_pulse_dev, int64_t n_t, const double* t_sol_dev,
+                                          const double* y0_planes_dev, double rtol, double atol,
+                                          int64_t nsteps_pulse, int64_t nsteps, double* y_pulse_out_dev,
+                                          double* y_out_dev, double* avg_out_dev, stb_stats* stats_pulse,
+                                          stb_stats* stats_relax) {
+    return integrate_dynamics_core(S, first, n, n_tp, t_pulse_dev, n_t, t_sol_dev, y0_planes_dev, rtol, atol,
+                                   nsteps_pulse, nsteps, y_pulse_out_dev, y_out_dev, avg_out_dev, stats_pulse,
+                                   stats_relax, true);
+}
+
+extern "C" int stb_set_experiment(stb_system* S, int32_t kind, int64_t n_e, const double* t_exp,
+                                  const double* y_exp, double tail_mean) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    const int kinds = S->hL.s[0] + S->hL.s[1];
+    if (kind < 0 || kind >= kinds) return fail(STB_EINVAL, "state kind out of range");
+    if (n_e < 0 || (n_e > 0 && (!t_exp || !y_exp))) return fail(STB_EINVAL, "bad experimental curve");
+    if (S->exp_t.empty()) {
+        S->exp_t.assign(kinds, {});
+        S->exp_y.assign(kinds, {});
+        S->exp_tail.assign(kinds, 0.0);
+    }
+    S->exp_t[kind].assign(t_exp, t_exp + n_e);
+    S->exp_y[kind].assign(y_exp, y_exp + n_e);
+    S->exp_tail[kind] = tail_mean;
+    S->exp_dirty = true;
+    return STB_OK;
+}
+
+extern "C" int stb_objective(stb_system* S, int32_t n, double* errors) {
+    if (!S || !errors) return fail(STB_EINVAL, "null argument");
+    if (S->exp_t.empty()) return fail(STB_ESTATE, "no experimental curve set (stb_set_experiment)");
+    if (!S->last_avg || n != S->last_dyn_n)
+        return fail(STB_ESTATE, "stb_objective evaluates the curves of the last stb_integrate_dynamics call");
+    CK(cudaSetDevice(S->device));
+    const int kinds = S->hL.s[0] + S->hL.s[1];
+    if (S->exp_dirty) {
+        std::vector<int64_t> off(kinds + 1, 0);
+        for (int k = 0; k < kinds; ++k) off[k + 1] = off[k] + (int64_t)S->exp_t[k].size();
+        const int64_t tot = std::max<int64_t>(off[kinds], 1);
+        if (tot > S->exp_cap) {
+            if (S->d_exp_t) pool_free(S->d_exp_t);
+            if (S->d_exp_y) pool_free(S->d_exp_y);
+            S->d_exp_t = S->d_exp_y = nullptr;
+            CK(pool_malloc(&S->d_exp_t, sizeof(double) * tot));
+            CK(pool_malloc(&S->d_exp_y, sizeof(double) * tot));
+            S->exp_cap = tot;
+        }
+        if (!S->d_exp_off) CK(pool_malloc(&S->d_exp_off, sizeof(int64_t) * (kinds + 1)));
+        if (!S->d_exp_tail) CK(pool_malloc(&S->d_exp_tail, sizeof(double) * kinds));
+        for (int k = 0; k < kinds; ++k) {
+            const size_t nb = sizeof(double) * S->exp_t[k].size();
+            if (!nb) continue;
+            CK(copy_on(S->stream, S->d_exp_t + off[k], S->exp_t[k].data(), nb, cudaMemcpyHostToDevice));
+            CK(copy_on(S->stream, S->d_exp_y + off[k], S->exp_y[k].data(), nb, cudaMemcpyHostToDevice));
+        }
+        CK(copy_on(S->stream, S->d_exp_off, off.data(), sizeof(int64_t) * (kinds + 1), cudaMemcpyHostToDevice));
+        CK(copy_on(S->stream, S->d_exp_tail, S->exp_tail.data(), sizeof(double) * kinds, cudaMemcpyHostToDevice));
+        S->exp_dirty = false;
+    }
+    if ((int64_t)n * kinds > S->obj_cap) {
+        if (S->d_obj) pool_free(S->d_obj);
+        S->d_obj = nullptr;
+        CK(pool_malloc(&S->d_obj, sizeof(double) * (size_t)n * kinds));
+        S->obj_cap = (int64_t)n * kinds;
+    }
+    g_launches++;
+    k_objective<<<dim3((unsigned)kinds, (unsigned)n), 256, 0, S->stream>>>(
+        S->last_avg, S->last_ts, S->last_dyn_nt, kinds, S->d_exp_t, S->d_exp_y, S->d_exp_off, S->d_exp_tail,
+        S->d_obj);
+    CK(cudaGetLastError());
+    CK(copy_on(S->stream, errors, S->d_obj, sizeof(double) * (size_t)n * kinds, cudaMemcpyDeviceToHost));
+    return STB_OK;
+}
+
+extern "C" int stb_set_option(stb_system* S, const char* name, double value) {
+    if (!S || !name) return fail(STB_EINVAL, "null argument");
+    if (!strcmp(name, "sm_budget")) {
+        S->sm_budget = (int)std::max(1.0, std::min((double)S->sm_count, value));
+        return STB_OK;
+    }
+    return fail(STB_EINVAL, std::string("unknown option ") + name);
+}
+
+extern "C" int stb_last_timing_dynamics(const stb_system* S, float* ms_pulse, float* ms_relax) {
+    if (!S) return fail(STB_EINVAL, "null system");
+    if (ms_pulse) *ms_pulse = S->last_ms_pulse;
+    if (ms_relax) *ms_relax = S->last_ms_relax;
     return STB_OK;
 }
 

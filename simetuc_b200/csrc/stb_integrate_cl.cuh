@@ -54,8 +54,9 @@ __host__ __device__ inline int cl_block_doubles(const DevLattice& L, const ClLay
 // Layout shared by the host (sizing, feasibility) and the kernel.  v_smem (number of leading
 // Krylov basis vectors) / d_smem / resident say
 // whether the Krylov basis, the difference array and the pair rows live in shared memory.
+// compact (k_integrate_cl2_t): the per-element work vectors live in registers of the owner threads
 __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmask, int v_smem,
-                                          int d_smem, ClLayout& Y) {
+                                          int d_smem, ClLayout& Y, int compact = 0) {
     for (int U = 0; U < 2; ++U) {
         Y.ldz[U] = (L.n[U] + 1) & ~1;
         Y.nkp[U] = Y.ldz[U] / 2;
@@ -76,12 +77,13 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     Y.zy = take(Y.NZ);
     Y.zv = take(Y.NZ);
-    Y.dd = take(Y.PO);
-    Y.psi = take(Y.PO);
-    Y.scl = take(Y.PO);
-    Y.fv = take(Y.PO);
-    Y.tw = take(Y.PO);
-    Y.kv = take(Y.PO);
+    const int wv = compact ? 0 : Y.PO;
+    Y.dd = take(wv);
+    Y.psi = take(wv);
+    Y.scl = take(wv);
+    Y.fv = take(wv);
+    Y.tw = take(wv);
+    Y.kv = take(wv);
     Y.moff[0] = 0;
     Y.moff[1] = L.s[0] * L.s[0] * Y.cntm[0];
     Y.minv = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);
@@ -97,7 +99,7 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
             if (L.blk[T][U].n_slots > Y.nsm) Y.nsm = L.blk[T][U].n_slots;
     Y.Pp = take(STB_NW * 2 * Y.nsm * CL_RG);
     Y.part = take(2 * G * STB_KRED);
-    Y.info = take(Y.PO + Y.PO / 2);            // three int tables of PO entries
+    Y.info = take(compact ? 0 : Y.PO + Y.PO / 2);            // three int tables of PO entries
     Y.V = v_smem > 0 ? take(v_smem * Y.PO) : -1;       // the first v_smem basis vectors
     Y.D = d_smem ? take(8 * Y.PO) : -1;
     Y.gres = o;
@@ -131,6 +133,7 @@ struct ClArgs {
     int G;
     int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
     int opts;                      // CL_OPT_* bits
+    int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
     int64_t n_t;
     const double* t;
     const double* y0;          // [n_sys][N] planes
@@ -356,6 +359,7 @@ struct ClShared {
     double H[(STB_KRYLOV + 1) * STB_KRYLOV];
     double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV], rd[STB_KRYLOV];
     double red[STB_NW * 4];
+    double dred[2][STB_NW][8];                   // k_integrate_cl2_t: per-warp partials of 8 reduced values
     double rv[STB_KRED];
     int wb_g[STB_NW + 1], wb_t[STB_NW + 1];      // work-list boundaries of the warps
     int wpos[STB_NW + 1];                        // the same as linear step positions

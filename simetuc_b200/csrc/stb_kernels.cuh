@@ -223,3 +223,85 @@ __global__ void __launch_bounds__(256) k_coop_add(const DevLattice* Lp, const do
         }
     }
 }
+
+
+// Optimisation objective on the device: deviation of every emission curve from its experimental
+// decay curve, exactly as DynamicsSolution._get_background / _interpolate_sim_data / _calc_errors
+// compute it on the host (simulations.py:425-527):
+//   offset = tail_mean * max(sim)                (experimental background scaled to the simulation)
+//   interp = sim interpolated linearly onto the experimental times, `offset` outside [t[0], t[-1]]
+//   err    = 1 / mean(interp) * sqrt(mean((interp - exp * max(interp))^2))
+// avg [n][n_t][kinds] are the curves (k_avg_populations), t_sol [n_t] the solution times (the time
+// base of a solution is t_sol - t_sol[0], simulations.py:1156), exp_t / exp_y the normalised
+// experimental curves of all state kinds back to back (exp_off [kinds + 1]; an empty range = no
+// data = error 0).  One block per (state kind, system); fixed-order block reductions.
+__device__ __forceinline__ double obj_interp(const double* avg, int64_t stride, const double* t_sol, int64_t n_t,
+                                             double te, double offset) {
+    const double t0 = t_sol[0];
+    if (te < 0.0 || te > t_sol[n_t - 1] - t0) return offset;
+    int64_t lo = 0, hi = n_t - 1;                 // t[lo] <= te <= t[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (t_sol[mid] - t0 <= te) lo = mid; else hi = mid;
+    }
+    const double x0 = t_sol[lo] - t0, x1 = t_sol[hi] - t0;
+    const double f0 = avg[lo * stride], f1 = avg[hi * stride];
+    if (te == x1) return f1;
+    const double slope = (f1 - f0) / (x1 - x0);
+    return slope * (te - x0) + f0;
+}
+
+template <int OP>   // 0: sum, 1: max
+__device__ __forceinline__ double obj_block_reduce(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = OP ? fmax(v, u) : v + u;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double acc = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) acc = OP ? fmax(acc, red[w]) : acc + red[w];
+    return acc;
+}
+
+__global__ void k_objective(const double* avg, const double* t_sol, int64_t n_t, int kinds,
+                            const double* exp_t, const double* exp_y, const int64_t* exp_off,
+                            const double* tail_mean, double* err) {
+    __shared__ double red[32];
+    const int kind = blockIdx.x, sys = blockIdx.y;
+    const int64_t e0 = exp_off[kind], ne = exp_off[kind + 1] - e0;
+    if (ne <= 0) {
+        if (threadIdx.x == 0) err[(int64_t)sys * kinds + kind] = 0.0;
+        return;
+    }
+    const double* a = avg + (int64_t)sys * n_t * kinds + kind;
+    double m = -INFINITY;
+    bool any = false;
+    for (int64_t k = threadIdx.x; k < n_t; k += blockDim.x) {
+        const double v = a[k * kinds];
+        m = fmax(m, v);
+        any = any || v != 0.0;
+    }
+    const double sim_max = obj_block_reduce<1>(m, red);
+    const double nz = obj_block_reduce<1>(any ? 1.0 : 0.0, red);
+    double offset = nz != 0.0 ? tail_mean[kind] * sim_max : 0.0;
+    if (!(offset > 0.0) || !isfinite(offset)) offset = 0.0;
+    double s = 0.0, mx = -INFINITY;
+    for (int64_t e = threadIdx.x; e < ne; e += blockDim.x) {
+        const double v = obj_interp(a, kinds, t_sol, n_t, exp_t[e0 + e], offset);
+        s += v;
+        mx = fmax(mx, v);
+    }
+    const double sum_i = obj_block_reduce<0>(s, red);
+    const double max_i = obj_block_reduce<1>(mx, red);
+    double d = 0.0;
+    for (int64_t e = threadIdx.x; e < ne; e += blockDim.x) {
+        const double v = obj_interp(a, kinds, t_sol, n_t, exp_t[e0 + e], offset);
+        const double r = v - exp_y[e0 + e] * max_i;
+        d = fma(r, r, d);
+    }
+    const double dev = obj_block_reduce<0>(d, red);
+    if (threadIdx.x == 0)
+        err[(int64_t)sys * kinds + kind] = 1.0 / (sum_i / (double)ne) * sqrt(dev / (double)ne);
+}

@@ -138,6 +138,30 @@ class RateSystem:
         except Exception:   # pragma: no cover - interpreter shutdown
             pass
 
+    def set_option(self, name: str, value: float):
+        """`stb_set_option`, e.g. `('sm_budget', 18)`: SMs one solve of this handle may occupy."""
+        _lib.check(self.lib.stb_set_option(self.handle, name.encode(), float(value)))
+
+    def set_experiment(self, kind: int, exp_data):
+        """Experimental decay curve of state kind `kind` for `objective()`: `exp_data [n_e, 2]` as
+        `DynamicsSolution._load_exp_data` returns it (time, normalised counts), or None."""
+        if exp_data is None or not np.any(exp_data):
+            _lib.check(self.lib.stb_set_experiment(self.handle, int(kind), 0, None, None, 0.0))
+            return
+        t = _lib.f64(exp_data[:, 0])
+        y = _lib.f64(exp_data[:, 1])
+        tail = y[y > 0][-50:]                     # `simulations.py:437-441`
+        tail_mean = float(np.mean(tail)) if tail.size else 0.0
+        _lib.check(self.lib.stb_set_experiment(self.handle, int(kind), len(t), _lib.ptr(t), _lib.ptr(y),
+                                               tail_mean))
+
+    def objective(self, n: int):
+        """`[n, sS+sA]` deviations of the emission curves of the last `integrate_dynamics` call
+        from the experimental curves (`stb_objective`)."""
+        out = np.empty((n, self.sS + self.sA))
+        _lib.check(self.lib.stb_objective(self.handle, int(n), _lib.ptr(out)))
+        return out
+
     # ------------------------------------------------------------------ lattice-side outputs
     def ground_states(self):
         """`(index_S_i, index_A_j, initial_population)` as `lattice.create_ground_states`."""
@@ -280,6 +304,27 @@ class RateSystem:
             _lib.ptr(y0), float(rtol), float(atol), int(nsteps), int(nsteps), _lib.ptr(y_p),
             _lib.ptr(y), _lib.ptr(avg), C.cast(st_p, C.c_void_p), C.cast(st_r, C.c_void_p)))
         return y_p, y, avg, [s.as_dict() for s in st_p], [s.as_dict() for s in st_r]
+
+    def integrate_dynamics_dev(self, t_pulse_ptr: int, n_tp: int, t_sol_ptr: int, n_t: int,
+                               y0_planes_ptr: int, n: int, rtol: float, atol: float,
+                               nsteps: int = 1000, first: int = 0, y_pulse_ptr: int = 0,
+                               y_out_ptr: int = 0, avg_out_ptr: int = 0):
+        """`stb_integrate_dynamics_dev`: pulse + relaxation with every operand a raw device pointer;
+        only the per-system statistics come back to the host."""
+        st_p = (_lib.StbStats * n)()
+        st_r = (_lib.StbStats * n)()
+        _lib.check(self.lib.stb_integrate_dynamics_dev(
+            self.handle, first, n, n_tp, C.c_void_p(t_pulse_ptr), n_t, C.c_void_p(t_sol_ptr),
+            C.c_void_p(y0_planes_ptr), float(rtol), float(atol), int(nsteps), int(nsteps),
+            C.c_void_p(y_pulse_ptr or None), C.c_void_p(y_out_ptr or None),
+            C.c_void_p(avg_out_ptr or None), C.cast(st_p, C.c_void_p), C.cast(st_r, C.c_void_p)))
+        return [s.as_dict() for s in st_p], [s.as_dict() for s in st_r]
+
+    def last_timing_dynamics(self):
+        """`(pulse ms, relaxation ms)` of the kernels of the last `integrate_dynamics[_dev]` call."""
+        a, b = C.c_float(), C.c_float()
+        _lib.check(self.lib.stb_last_timing_dynamics(self.handle, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
     def integrate_dev(self, t_dev_ptr: int, n_t: int, y0_planes_ptr: int, n: int, pulse: bool,
                       rtol: float, atol: float, nsteps: int = 1000, first: int = 0,

@@ -75,33 +75,52 @@ def optim_fun_dynamics_conc(params, sim: simulations.Simulations, average: bool 
 
 
 def objective_batch(sim: simulations.Simulations, candidates: Sequence[Sequence[float]],
-                    keep_y: bool = False):
+                    keep_y: bool = False, on_device: bool = False):
     '''Evaluate the dynamics objective for many candidate parameter sets at once.
 
     `candidates[c][k]` is the value of `cte.optimization['processes'][k]` (an ET strength or a
     branching ratio / decay rate) for candidate c.  All candidates share the lattice and are
     dealt round-robin over `sim.devices`.  Returns `(errors [n_candidates, sS+sA], solutions)`,
     the per-state deviation from the experimental curves of every candidate exactly as
-    `optim_fun` would return it one by one.'''
+    `optim_fun` would return it one by one.
+
+    `on_device=True`: interpolation onto the experimental time base and the per-state deviations
+    (`simulations.py:425-527`) run on the GPU; the emission curves are not copied back and
+    `solutions` is None (an optimiser only needs the errors).'''
     candidates = [list(map(float, c)) for c in candidates]
+    shared = {key: sim.cte[key] for key in ('energy_transfer', 'decay', 'optimization')}
     ctes = []
     for values in candidates:
-        cte = copy.deepcopy(sim.cte)
+        # private copies of the sections a candidate changes, made in one deepcopy so that the
+        # optimised objects listed in `optimization.processes` stay the ones stored in
+        # `energy_transfer` / `decay`; every other section is shared (read-only)
+        cte = copy.copy(sim.cte)
+        cte.update(copy.deepcopy(shared))
+        cte['states'] = copy.copy(sim.cte['states'])
         for proc, value in zip(cte['optimization']['processes'], values):
             proc.value = value
-            # the optimised objects are the ones stored in cte.energy_transfer / cte.decay when
-            # the settings were parsed; after a deepcopy they still are (same memo), so nothing
-            # else has to be updated
         ctes.append(cte)
+    if on_device:
+        template = simulations.DynamicsSolution(np.zeros(1), np.zeros((1, 1)), [0], [0], ctes[0],
+                                                own_cte=True)
+        experiments = template.list_exp_data
+        sols, index_S_i, index_A_j, lat, stats = sim._sweep_same_lattice(
+            ctes, dynamics=True, keep_y=False, experiments=experiments)
+        return np.array([st['errors'] for st in stats]), None
     sols, index_S_i, index_A_j, lat, stats = sim._sweep_same_lattice(ctes, dynamics=True,
                                                                     keep_y=keep_y)
     solutions, errors = [], []
+    exp_data = None
     for cte, (t_sol, y_sol, avg), st in zip(ctes, sols, stats):
         cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
         cte['states']['energy_states'] = lat.n_states
         sol = simulations.DynamicsSolution(t_sol, y_sol if y_sol is not None else avg,
-                                           index_S_i, index_A_j, cte)
+                                           index_S_i, index_A_j, cte, own_cte=True)
         sol.set_avg_data(avg)
+        if exp_data is None:
+            exp_data = sol.list_exp_data       # the same files for every candidate: read them once
+        else:
+            sol.__dict__['list_exp_data'] = exp_data
         sol.solver_stats = st
         solutions.append(sol)
         errors.append(sol.errors)

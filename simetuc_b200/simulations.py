@@ -16,6 +16,7 @@ saved as `.npz`).
 import concurrent.futures
 import copy
 import csv
+import functools
 import logging
 import os
 import threading
@@ -480,14 +481,18 @@ class Simulations:
     # ------------------------------------------------------------------ batched sweeps
     def _solve_batch(self, lat, ctes: List[Any], device: int, dynamics: bool,
                      strengths: Optional[np.ndarray] = None, keep_y: bool = True,
-                     average: bool = False, gpu_busy: Optional[threading.Event] = None):
+                     average: bool = False, gpu_busy: Optional[threading.Event] = None,
+                     sm_budget: Optional[int] = None, experiments: Optional[list] = None):
         """Integrate `len(ctes)` systems that share `lat` in one batch on `device`.
         Each cte supplies its own absorption / decay blocks (and optionally ET strengths).
         Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics.
 
         The device system of the lattice is checked out of `precalculate`'s pool (pair build and
         device buffers are reused by the next sweep on this lattice); pulse and relaxation run
-        in one C-ABI call.  Systems whose solve did not reach the end are reported with the
+        in one C-ABI call.  `experiments` (dynamics only): one experimental curve or None per
+        state kind; the per-state deviations are then evaluated on the device and returned as
+        `stats[k]['errors']`, and the curves are not copied back (`avg` is None).
+        Systems whose solve did not reach the end are reported with the
         reference's warnings (`odesolver.py:129-134`); a relaxation that would start from an
         unreached pulse row is blanked (NaN) instead of returned as data."""
         logger = logging.getLogger(__name__)
@@ -503,6 +508,8 @@ class Simulations:
                                  '(they are part of the device-resident lattice data)')
         system = precalculate.acquire_system(cte0, lat, device=device, n_sys=n)
         try:
+            # share of the GPU of this solve when several lattices are in flight on the device
+            system.set_option('sm_budget', sm_budget if sm_budget else 1 << 20)
             blocks = {}
             for k, cte in enumerate(ctes):
                 # the decay blocks depend on the decay section only: sweeps share that object
@@ -527,15 +534,27 @@ class Simulations:
                 tf_p = self._get_t_pulse()
                 t_pulse = np.linspace(0, tf_p, 2, dtype=np.float64)
                 t_sol = np.logspace(np.log10(tf_p), np.log10(tf), N_steps, dtype=np.float64)
+                errors = None
+                if experiments is not None:
+                    for kind, exp in enumerate(experiments):
+                        system.set_experiment(kind, exp)
                 _, y, avg, st_p, st = system.integrate_dynamics(
-                    t_pulse, t_sol, y0, rtol=rtol, atol=atol, want_y=keep_y, want_avg=True)
+                    t_pulse, t_sol, y0, rtol=rtol, atol=atol, want_y=keep_y,
+                    want_avg=experiments is None)
+                if experiments is not None:
+                    errors = system.objective(n)
                 t_out = t_sol - t_sol[0]
                 stats = [dict(pulse=a, relax=b) for a, b in zip(st_p, st)]
                 for k, (a, b) in enumerate(zip(st_p, st)):
+                    if errors is not None:
+                        stats[k]['errors'] = errors[k]
                     if odesolver.warn_solver_status(a, logger, 'system %d, pulse: ' % k):
                         logger.warning('system %d: the pulse did not reach its end, its relaxation '
                                        'is not returned', k)
-                        avg[k] = np.nan
+                        if avg is not None:
+                            avg[k] = np.nan
+                        if errors is not None:
+                            errors[k] = np.nan
                         if y is not None:
                             y[k] = np.nan
                     else:
@@ -547,14 +566,15 @@ class Simulations:
                 stats = [dict(pulse=a) for a in st]
                 for k, a in enumerate(st):
                     odesolver.warn_solver_status(a, logger, 'system %d: ' % k)
-            return [(t_out, None if y is None else y[k], avg[k]) for k in range(n)], \
-                list(index_S_i), list(index_A_j), stats
+            return [(t_out, None if y is None else y[k], None if avg is None else avg[k])
+                    for k in range(n)], list(index_S_i), list(index_A_j), stats
         finally:
             precalculate.release_system(system)
 
     def _sweep_same_lattice(self, ctes: List[Any], dynamics: bool, keep_y: bool = True,
                             strengths: Optional[np.ndarray] = None, average: bool = False,
-                            gpu_busy: Optional[threading.Event] = None):
+                            gpu_busy: Optional[threading.Event] = None,
+                            experiments: Optional[list] = None):
         """Systems sharing one lattice, dealt round-robin over `self.devices`."""
         gen_lattice = self.cte.get('gen_lattice', False)
         if average:
@@ -565,7 +585,7 @@ class Simulations:
         shards = [list(range(d, len(ctes), n_dev)) for d in range(n_dev)]
         jobs = [(lambda d=d, ids=ids: self._solve_batch(
             lat, [ctes[i] for i in ids], self.devices[d], dynamics, keep_y=keep_y, average=average,
-            gpu_busy=gpu_busy,
+            gpu_busy=gpu_busy, experiments=experiments,
             strengths=None if strengths is None else strengths[ids])) for d, ids in enumerate(shards)]
         results = _run_on_devices(jobs, n_dev)
         out = [None] * len(ctes)
@@ -609,17 +629,21 @@ class Simulations:
             cte['states'] = copy.copy(self.cte['states'])
             ctes.append(cte)
         solutions = []
-        for cte, (t_sol, y_sol, avg), st in zip(ctes, sols, stats):
-            cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
+        steady_all = None
+        if pulsed and not keep_y:
+            # keep_y=False: the ion average commutes with the time integral, so the area under the
+            # device-computed emission curves gives the same steady state without moving the
+            # [n_t, N] trajectories to the host; one pass over the curves of all the systems
+            steady_all = cumulative_trapezoid(np.stack([avg for _, _, avg in sols], axis=1), sols[0][0])
+        ions = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
+        for k, (cte, (t_sol, y_sol, avg), st) in enumerate(zip(ctes, sols, stats)):
+            cte['ions'] = dict(ions)
             cte['states']['energy_states'] = lat.n_states
             if pulsed and y_sol is not None:
                 sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
                                        average=average, own_cte=True).calculate_steady_state()
             elif pulsed:
-                # keep_y=False: the ion average commutes with the time integral, so the area
-                # under the device-computed emission curves gives the same steady state without
-                # moving the [n_t, N] trajectory to the host
-                avg_steady = cumulative_trapezoid(avg, t_sol)
+                avg_steady = steady_all[:, k, :]
                 sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, average=average,
                                           own_cte=True)
                 sol.set_avg_data(avg_steady)
@@ -641,9 +665,12 @@ class Simulations:
 
     def simulate_concentration_dependence(self, concentrations: List[Tuple[float, float]],
                                           N_uc_list: List[int] = None, dynamics: bool = False,
-                                          average: bool = False) -> ConcentrationDependenceSolution:
+                                          average: bool = False, keep_y: bool = True
+                                          ) -> ConcentrationDependenceSolution:
         '''One lattice per (S_conc, A_conc) point (`simulations.py:1318-1385`); the points are
-        independent and are dealt round-robin over the devices.'''
+        independent and are dealt round-robin over the devices.  `keep_y=False` (dynamics only)
+        brings back the emission curves (`list_avg_data`, computed on the device) instead of the
+        `[n_t, N]` trajectories: `y_sol` of the solutions then holds the curves.'''
         start_time = time.time()
         concentrations = [(float(a), float(b)) for a, b in list(concentrations)]
         if N_uc_list is None:
@@ -653,22 +680,30 @@ class Simulations:
             N_uc_list.extend([N_uc_list[-1]] * (len(concentrations) - len(N_uc_list)))
         pulsed = self._is_pulsed()
 
+        base_seed = self.cte.get('lattice_seed')
+
         def solve_point(k, device):
             cte = copy.deepcopy(self.cte)
             cte['lattice']['N_uc'] = N_uc_list[k]
             cte['lattice']['S_conc'], cte['lattice']['A_conc'] = concentrations[k]
+            if base_seed is not None:
+                # every point is its own lattice realisation, also when a concentration repeats
+                cte['lattice_seed'] = base_seed + k
             sim = Simulations(cte, devices=[device])
             if average:
                 lat = precalculate.average_lattice(cte)
             else:
                 lat = precalculate.get_lattice(cte, gen_lattice=cte.get('gen_lattice', False))
-            sols, index_S_i, index_A_j, st = sim._solve_batch(lat, [cte], device,
-                                                              dynamics or pulsed, average=average)
+            want_y = keep_y or not dynamics
+            sols, index_S_i, index_A_j, st = sim._solve_batch(lat, [cte], device, dynamics or pulsed,
+                                                              average=average, keep_y=want_y,
+                                                              sm_budget=sm_budget)
             cte['ions'] = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
             cte['states']['energy_states'] = lat.n_states
             t_sol, y_sol, avg = sols[0]
             if dynamics:
-                sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte, average=average)
+                sol = DynamicsSolution(t_sol, y_sol if y_sol is not None else avg, index_S_i,
+                                       index_A_j, cte, average=average, own_cte=True)
                 sol.set_avg_data(avg)
             elif pulsed:
                 sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
@@ -676,12 +711,14 @@ class Simulations:
             else:
                 sol = SteadyStateSolution(t_sol, y_sol, index_S_i, index_A_j, cte, average=average)
                 sol.set_avg_data(avg)
+            sol.solver_stats = st[0]
             return sol
 
         # every point is its own lattice, i.e. its own handle and stream: several points are in
         # flight per device (a system of this size occupies one cluster of <= 8 SMs out of 148)
         n_dev = min(len(self.devices), len(concentrations))
         per_dev = max(1, min(self.streams_per_device, -(-len(concentrations) // n_dev)))
+        sm_budget = max(8, 148 // per_dev)
         jobs = [(lambda k=k: solve_point(k, self.devices[k % n_dev]))
                 for k in range(len(concentrations))]
         with disable_loggers([__name__ + '.dynamics', __name__ + '.steady_state']):
@@ -696,25 +733,48 @@ class Simulations:
     def sample_simulation(self, simulation_fun: Callable, N_samples: int, *args: Any,
                           **kwargs: Any):
         '''Repeat `simulation_fun` over `N_samples` fresh lattice realisations and average the
-        emission curves (`simulations.py:1387-1442`).'''
+        emission curves (`simulations.py:1387-1442`).
+
+        The reference runs the samples one after the other (`:1412-1417`); they are independent
+        lattices, so here they are dealt round-robin over `self.devices` and run concurrently,
+        `streams_per_device` at a time per GPU (every realisation has its own device handle and
+        stream).  `simulation_fun` must be a method of this object (or a `functools.partial` of
+        one): every sample runs it on a private copy of the settings with its own lattice seed
+        (`lattice_seed + i` when a seed is set, fresh entropy otherwise).  The result is the last
+        sample's solution carrying the averaged curves and errors, as in the reference.'''
         if not N_samples or N_samples <= 1:
             return simulation_fun(*args, **kwargs)
         self.cte['gen_lattice'] = True
-        errors, total_errors, acc, sol = [], [], None, None
         base_seed = self.cte.get('lattice_seed')
-        for i_sample in range(N_samples):
-            if base_seed is not None:
-                self.cte['lattice_seed'] = base_seed + i_sample
-            sol = simulation_fun(*args, **kwargs)
-            if isinstance(sol, DynamicsSolution):
-                errors.append(sol.errors)
-                total_errors.append(sol.total_error)
-                cur = np.array(sol.list_avg_data_ofs)
-                acc = cur if acc is None else acc + cur
-        if base_seed is not None:
-            self.cte['lattice_seed'] = base_seed
+        if base_seed is None:
+            seeds = [int(s.generate_state(1)[0]) for s in np.random.SeedSequence().spawn(N_samples)]
+        else:
+            seeds = [base_seed + i for i in range(N_samples)]
+        inner, extra_args, extra_kw = simulation_fun, (), {}
+        if isinstance(inner, functools.partial):
+            inner, extra_args, extra_kw = inner.func, inner.args, dict(inner.keywords or {})
+        if getattr(inner, '__self__', None) is not self:
+            raise TypeError('sample_simulation needs a method of this Simulations object')
+        name = inner.__name__
+        n_dev = min(len(self.devices), N_samples)
+
+        def run_sample(i):
+            cte = copy.deepcopy(self.cte)
+            cte['lattice_seed'] = seeds[i]
+            sim = Simulations(cte, full_path=self.full_path, devices=[self.devices[i % n_dev]],
+                              streams_per_device=self.streams_per_device)
+            sol = getattr(sim, name)(*extra_args, *args, **extra_kw, **kwargs)
+            if isinstance(sol, DynamicsSolution):       # evaluated in the worker: the GPU of the
+                _ = sol.errors, sol.total_error, sol.list_avg_data_ofs   # next sample is busy meanwhile
+            return sol
+
+        per_dev = max(1, min(self.streams_per_device, -(-N_samples // n_dev)))
+        jobs = [(lambda i=i: run_sample(i)) for i in range(N_samples)]
+        sols = _run_on_devices(jobs, n_dev * per_dev)
+        sol = sols[-1]
         if isinstance(sol, DynamicsSolution):
+            acc = sum(np.array(s.list_avg_data_ofs) for s in sols)
             sol.__dict__['list_avg_data_ofs'] = list(acc / N_samples)
-            sol.__dict__['total_error'] = float(np.mean(total_errors))
-            sol.__dict__['errors'] = np.mean(errors, axis=0)
+            sol.__dict__['total_error'] = float(np.mean([s.total_error for s in sols]))
+            sol.__dict__['errors'] = np.mean([s.errors for s in sols], axis=0)
         return sol

@@ -176,6 +176,37 @@ def test_objective_batch_equals_sequential_objective(tmp_path, monkeypatch):
         assert np.allclose(seq, err, rtol=1e-9, atol=1e-12)
 
 
+def test_objective_on_device_matches_host_objective(tmp_path, monkeypatch):
+    """`objective_batch(on_device=True)` (k_objective: background, interpolation onto the experimental
+    time base, per-state deviation on the GPU; only [n, sS+sA] numbers come back) against the host
+    objective, whose pieces are pinned against the unmodified reference in
+    tests/test_host.py::test_objective_pieces_match_the_reference.  Curves: the four decay curves
+    shipped for the config_file.cfg system (stored in tests/golden/expdata_objective.npz), renamed
+    to this lattice's concentrations."""
+    import os
+    from tests.helpers import GOLDEN
+    with np.load(os.path.join(GOLDEN, 'expdata_objective.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    cte = configs.yb_tm_cte(N_uc=6, S_conc=20.0, A_conc=2.0)
+    cte['lattice_seed'] = 6
+    cte['simulation_params']['N_steps'] = 300
+    exp_dir = tmp_path / 'expData' / 'bNaYF4'
+    exp_dir.mkdir(parents=True)
+    for state in (str(s) for s in gold['states']):
+        np.savetxt(exp_dir / ('decay_%s_exc_NIR_980_20.0Yb_2.0Tm.txt' % state), gold['raw_' + state],
+                   fmt='%.18e', delimiter='\t')
+    monkeypatch.chdir(tmp_path)
+    sim = Simulations(cte)
+    base = [p.strength for p in cte['optimization']['processes']]
+    rng = np.random.default_rng(77)
+    cands = [list(np.array(base) * 10.0 ** rng.uniform(-1, 1, len(base))) for _ in range(5)]
+    host, sols = optimize.objective_batch(sim, cands)
+    dev, none = optimize.objective_batch(sim, cands, on_device=True)
+    assert none is None and dev.shape == host.shape == (5, 11)
+    assert np.count_nonzero(host[0]) == 4                       # the four states with a curve
+    assert np.allclose(dev, host, rtol=1e-10, atol=0.0)
+
+
 def test_concurrent_handles_match_sequential():
     """Independent lattices solved from several host threads at once (what
     `simulate_concentration_dependence` does with `streams_per_device`) give bit-identical

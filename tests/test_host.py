@@ -211,3 +211,41 @@ def test_average_lattice_and_processes():
     assert [list(r) for r in lists[0]] == [[0]] and [list(r) for r in lists[3]] == [[2]]
     assert np.array_equal(precalculate.jac_indices_of(np.array([[1, 5], [3, 7]], np.uint32)),
                           onp.jac_indices(np.array([[1, 5], [3, 7]], np.uint32)))
+
+
+def test_objective_pieces_match_the_reference(tmp_path, monkeypatch):
+    """`DynamicsSolution._load_exp_data / _get_background / list_interp_data / errors` against the
+    UNMODIFIED reference's (`simulations.py:354-527`) on the four decay curves shipped for the
+    config_file.cfg system; vectors made by `oracle/make_golden_expdata.py`."""
+    from simetuc_b200 import simulations
+    with np.load(os.path.join(ROOT, 'tests', 'golden', 'expdata_objective.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    states = [str(s) for s in gold['states']]
+    exp_dir = tmp_path / 'expData' / 'bNaYF4'
+    exp_dir.mkdir(parents=True)
+    for state in states:
+        np.savetxt(exp_dir / ('decay_%s_exc_NIR_980_25.0Yb_0.3Tm.txt' % state), gold['raw_' + state],
+                   fmt='%.18e', delimiter='\t', header='t counts')
+    monkeypatch.chdir(tmp_path)
+    DS = simulations.DynamicsSolution
+    for state in states:
+        exp = DS._load_exp_data('decay_%s_exc_NIR_980_25.0Yb_0.3Tm.txt' % state, 'bNaYF4')
+        assert exp.shape == gold['exp_' + state].shape
+        assert np.allclose(exp, gold['exp_' + state], rtol=1e-12, atol=1e-15)
+        sim = gold['sim_' + state]
+        assert np.isclose(DS._get_background(exp, sim), gold['offset_' + state], rtol=1e-12)
+    # the whole chain through a solution object: Yb (GS, ES) + 9 Tm states, curves in state order
+    cte = configs.yb_tm_cte(N_uc=12, S_conc=25.0, A_conc=0.3)
+    labels = ['Yb_GS', 'Yb_ES'] + ['Tm_' + s for s in cte['states']['activator_states_labels']]
+    t_sol = gold['t_sol']
+    curves = np.stack([gold['sim_' + lab] if lab in states else np.full(len(t_sol), 1e-3)
+                       for lab in labels], axis=1)
+    sol = DS(t_sol, curves, [0, -1], [-1, 2], cte)
+    sol.set_avg_data(curves)
+    assert sol.state_labels == labels
+    for k, lab in enumerate(labels):
+        if lab in states:
+            assert np.allclose(sol.list_interp_data[k], gold['interp_' + lab], rtol=1e-12, atol=1e-300)
+            assert np.isclose(sol.errors[k], gold['err_' + lab], rtol=1e-10)
+        else:
+            assert sol.errors[k] == 0.0
