@@ -287,6 +287,9 @@ struct stb_system {
     std::vector<uint8_t> type;
     std::vector<int> local_idx, gs_ref, plane_of_ref, ref_of_plane;
     std::vector<int> gs_of_local[2];
+    std::vector<int> local_of_rank_S;    // quad lattices: type-local index of the r-th sensitizer
+    int* d_local_of_rank_S = nullptr;
+    stb_process* d_procs = nullptr;      // device copy of the process table (strengths: see d_strengths)
     std::vector<int> len;  // [2][n]
     DevLattice hL;         // host copy (device pointers inside)
     DevLattice* dL = nullptr;
@@ -420,6 +423,8 @@ extern "C" void stb_system_destroy(stb_system* S) {
     pool_free(S->dL);
     pool_free(S->d_type);
     pool_free(S->d_local_idx);
+    pool_free(S->d_local_of_rank_S);
+    pool_free(S->d_procs);
     pool_free(S->d_gs_ref);
     pool_free(S->d_plane_of_ref);
     pool_free(S->d_ref_of_plane);
@@ -515,6 +520,92 @@ static int build_tables(stb_system* S, DevLattice& L) {
     return STB_OK;
 }
 
+// Order of the sensitizers for the quad block preconditioner of the cluster integrator: strongly
+// coupled ions (the closest pairs: energy migration goes with d^-6) are put next to each other,
+// in quads of type-local indices 4m .. 4m+3.  Greedy: every sensitizer proposes its three nearest
+// sensitizers, the proposed pairs are merged closest first while a group holds at most four ions,
+// and the groups are packed into quads (4, 3+1, 2+2, 2+1+1, 1+1+1+1).  Only the ORDER of the ions
+// inside the library changes; every result is reported in the reference's order.
+// Returns false (identity order) for lattices it does not apply to.  out[r] = type-local index of
+// the r-th sensitizer in lattice order.
+static bool group_sensitizers(int n, const uint8_t* type, int sS, const double* dist, const double* pos,
+                              const double* cell, std::vector<int>& out) {
+    out.clear();
+    if (const char* env = getenv("STB_QUADS")) if (atoi(env) == 0) return false;
+    if (sS < 1 || 4 * sS > 12) return false;      // a quad block has at most 12 x 12 entries (Gauss-Jordan teams)
+    std::vector<int> ions;
+    for (int q = 0; q < n; ++q) if (type[q] == 0) ions.push_back(q);
+    const int nS = (int)ions.size();
+    if (nS < 2 || nS > 2048) return false;
+    double inv[9];
+    bool periodic = pos && cell && invert3(cell, inv);
+    auto d2 = [&](int a, int b) -> double {
+        if (dist) { const double d = dist[(size_t)ions[a] * n + ions[b]]; return d * d; }
+        double v[3] = {pos[3 * ions[b]] - pos[3 * ions[a]], pos[3 * ions[b] + 1] - pos[3 * ions[a] + 1],
+                       pos[3 * ions[b] + 2] - pos[3 * ions[a] + 2]};
+        if (periodic) {      // nearest image by fractional rounding (good enough to find neighbours)
+            double f[3];
+            for (int c = 0; c < 3; ++c) f[c] = v[0] * inv[c] + v[1] * inv[3 + c] + v[2] * inv[6 + c];
+            for (int c = 0; c < 3; ++c) f[c] -= std::nearbyint(f[c]);
+            for (int c = 0; c < 3; ++c) v[c] = f[0] * cell[c] + f[1] * cell[3 + c] + f[2] * cell[6 + c];
+        }
+        return v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    };
+    struct Cand { double d2; int a, b; };
+    std::vector<Cand> cand;
+    cand.reserve((size_t)nS * 3);
+    for (int a = 0; a < nS; ++a) {
+        double best[3] = {1e300, 1e300, 1e300};
+        int who[3] = {-1, -1, -1};
+        for (int b = 0; b < nS; ++b) {
+            if (b == a) continue;
+            const double d = d2(a, b);
+            if (!(d > 0.0)) continue;
+            for (int k = 0; k < 3; ++k)
+                if (d < best[k]) {
+                    for (int m = 2; m > k; --m) { best[m] = best[m - 1]; who[m] = who[m - 1]; }
+                    best[k] = d; who[k] = b;
+                    break;
+                }
+        }
+        for (int k = 0; k < 3; ++k)
+            if (who[k] >= 0 && a < who[k]) cand.push_back({best[k], a, who[k]});
+            else if (who[k] >= 0) cand.push_back({best[k], who[k], a});
+    }
+    std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) {
+        return x.d2 != y.d2 ? x.d2 < y.d2 : (x.a != y.a ? x.a < y.a : x.b < y.b);
+    });
+    std::vector<int> grp(nS);
+    std::vector<std::vector<int>> members(nS);
+    for (int a = 0; a < nS; ++a) { grp[a] = a; members[a] = {a}; }
+    for (const Cand& c : cand) {
+        const int ga = grp[c.a], gb = grp[c.b];
+        if (ga == gb || members[ga].size() + members[gb].size() > 4) continue;
+        for (int m : members[gb]) { grp[m] = ga; members[ga].push_back(m); }
+        members[gb].clear();
+    }
+    std::vector<std::vector<int>> by_size[5];
+    for (int a = 0; a < nS; ++a)
+        if (!members[a].empty()) by_size[members[a].size()].push_back(members[a]);
+    std::vector<int> order;          // sensitizer ranks in storage order
+    order.reserve(nS);
+    auto take = [&](int sz) {
+        std::vector<int> g = by_size[sz].back();
+        by_size[sz].pop_back();
+        order.insert(order.end(), g.begin(), g.end());
+    };
+    while (!by_size[4].empty()) take(4);
+    while (!by_size[3].empty()) { take(3); if (!by_size[1].empty()) take(1); else break; }
+    // (a triple without a single left over starts the tail: everything after it is packed as it comes)
+    while (by_size[3].empty() && by_size[2].size() >= 2) { take(2); take(2); }
+    while (by_size[3].empty() && !by_size[2].empty() && by_size[1].size() >= 2) { take(2); take(1); take(1); }
+    for (int sz = 3; sz >= 1; --sz)
+        while (!by_size[sz].empty()) take(sz);
+    out.assign(nS, 0);
+    for (int p = 0; p < nS; ++p) out[order[p]] = p;
+    return true;
+}
+
 extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const uint8_t* ion_type,
                                          int32_t n_S_states, int32_t n_A_states,
                                          const double* dist_array, const double* positions,
@@ -570,12 +661,21 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
         S->type[q] = (uint8_t)T;
         S->local_idx[q] = cnt[T]++;
         S->gs_ref[q] = gs;
-        S->gs_of_local[T].push_back(gs);
         gs += S->s[T];
     }
     S->n[0] = cnt[0];
     S->n[1] = cnt[1];
     S->N = gs;
+    // quad lattices: strongly coupled sensitizers become neighbours in the type-local order
+    bool quad = !(d_max > 0.0) && group_sensitizers(n, S->type.data(), S->s[0], dist_array, positions, cell,
+                                                    S->local_of_rank_S);
+    if (quad) {
+        int r = 0;
+        for (int q = 0; q < n; ++q)
+            if (S->type[q] == 0) S->local_idx[q] = S->local_of_rank_S[r++];
+    }
+    for (int T = 0; T < 2; ++T) S->gs_of_local[T].assign(S->n[T], 0);
+    for (int q = 0; q < n; ++q) S->gs_of_local[S->type[q]][S->local_idx[q]] = S->gs_ref[q];
     if (S->N == 0) { fail(STB_EINVAL, "No states: the number of energy states is zero."); delete S; return nullptr; }
     DevLattice& L = S->hL;
     memset(&L, 0, sizeof(L));
@@ -585,6 +685,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     L.off[0] = 0;
     L.off[1] = S->s[0] * S->n[0];
     L.n_proc = n_proc;
+    L.quad = quad ? 1 : 0;
     S->plane_of_ref.resize(S->N);
     S->ref_of_plane.resize(S->N);
     for (int q = 0; q < n; ++q) {
@@ -599,6 +700,8 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
 
     CKP(upload(S->stream, &S->d_type, S->type));
     CKP(upload(S->stream, &S->d_local_idx, S->local_idx));
+    if (quad) CKP(upload(S->stream, &S->d_local_of_rank_S, S->local_of_rank_S));
+    if (n_proc > 0) CKP(upload(S->stream, &S->d_procs, S->procs));
     CKP(upload(S->stream, &S->d_gs_ref, S->gs_ref));
     CKP(upload(S->stream, &S->d_plane_of_ref, S->plane_of_ref));
     CKP(upload(S->stream, &S->d_ref_of_plane, S->ref_of_plane));
@@ -892,6 +995,8 @@ extern "C" int stb_export_interactions(const stb_system* S, int32_t system, uint
     EA.gs_ref = S->d_gs_ref;
     EA.gs_of_local[0] = S->d_gs_of_local[0];
     EA.gs_of_local[1] = S->d_gs_of_local[1];
+    EA.local_of_rank[0] = S->d_local_of_rank_S;      // null unless the sensitizers are stored in quads
+    EA.local_of_rank[1] = nullptr;
     EA.len = S->d_len;
     EA.offset = d_off;
     EA.procs = d_pr;
@@ -1245,8 +1350,10 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
         forced = atoi(env);
         if (forced != 1 && forced != 2 && forced != 4 && forced != 8) return false;
     }
-    bool allow_v2 = true;
-    if (const char* env = getenv("STB_CL_V")) allow_v2 = atoi(env) != 1;
+    // the ion-major variant (stb_integrate_cl2.cuh) is opt-in: measured slower than the element-major
+    // kernel on the Yb-Tm sweeps (profiles/r02_integrator_notes.md)
+    bool allow_v2 = false;
+    if (const char* env = getenv("STB_CL_V")) allow_v2 = atoi(env) == 2;
     int want_res = 1;
     if (const char* env = getenv("STB_RESIDENT")) want_res = atoi(env) != 0;
     ClPlan best;
@@ -1288,7 +1395,7 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
             ClLayout Z;
             // the difference array is touched in every step, basis vectors beyond the first few
             // only by long linear solves: D first (with at least 4 vectors), then more vectors
-            for (int c = 8; c >= 4 && !d_smem; --c) {
+            for (int c = 8; c >= 3 && !d_smem; --c) {
                 cl_layout(L, G, mask, c, 1, Z, v2);
                 if ((size_t)Z.total * 8 <= cap) { v_smem = c; d_smem = 1; }
             }
@@ -1296,7 +1403,7 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
                 cl_layout(L, G, mask, c, 0, Z, v2);
                 if ((size_t)Z.total * 8 <= cap) v_smem = c;
             }
-            for (int c = STB_KRYLOV + 1; c > v_smem; --c) {
+            for (int c = CL_KRYLOV + 1; c > v_smem; --c) {
                 cl_layout(L, G, mask, c, d_smem, Z, v2);
                 if ((size_t)Z.total * 8 <= cap) { v_smem = c; break; }
             }
@@ -1343,7 +1450,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     HostTimer tm;
     ClLayout Y;
     cl_layout(L, plan.G, plan.resmask, plan.v_smem, plan.d_smem, Y, plan.v2);
-    const int64_t work_stride = (int64_t)(STB_KRYLOV + 1 + 8) * Y.PO;
+    const int64_t work_stride = (int64_t)(CL_KRYLOV + 1 + 8) * Y.PO;
     double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_tmp = nullptr,
            *d_avg = nullptr;
     int* d_next = nullptr;
@@ -1396,7 +1503,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.first = first; A.n_sys = n; A.pulse = pulse; A.G = plan.G;
     A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
     A.compact = plan.v2 ? 1 : 0;
-    A.opts = CL_OPT_GUESS | CL_OPT_LAGPC;
+    A.procs = S->d_procs;
+    A.opts = CL_OPT_GUESS | CL_OPT_LAGPC | CL_OPT_QUAD;
     if (const char* env = getenv("STB_CL_OPTS")) A.opts = atoi(env);
     A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;
     A.nsteps = nsteps > 0 ? nsteps : 1000;
@@ -1405,9 +1513,17 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.prof = d_prof;
     S->last_G = plan.G; S->last_groups = plan.n_clusters;
     if (getenv("STB_VERBOSE"))
+    {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, cl_kernel(S, plan.v2));
+        ClLayout Z;
+        cl_layout(L, plan.G, plan.resmask, 4, 1, Z, plan.v2);
         fprintf(stderr, "[stb] cluster integrator v%d: n=%d G=%d clusters=%d resmask=%x (%.0f%% of pair rows "
-                "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d\n", plan.v2 ? 2 : 1, n, plan.G, plan.n_clusters,
-                plan.resmask, 100.0 * plan.resident_frac, plan.v_smem, plan.d_smem, plan.dyn_bytes, Y.PO);
+                "in smem) V_smem=%d D_smem=%d dyn_smem=%zu B own_pitch=%d static_smem=%zu B; with V=4 + D: %lld B "
+                "of %zu B\n", plan.v2 ? 2 : 1, n, plan.G, plan.n_clusters,
+                plan.resmask, 100.0 * plan.resident_frac, plan.v_smem, plan.d_smem, plan.dyn_bytes, Y.PO,
+                (size_t)fa.sharedSizeBytes, (long long)Z.total * 8, (size_t)(232448 - fa.sharedSizeBytes - 256));
+    }
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
     CKC(cudaEventRecord(e0, S->stream));
     {

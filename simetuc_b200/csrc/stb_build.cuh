@@ -152,6 +152,8 @@ struct ExportArgs {
     const int* local_idx;
     const int* gs_ref;          // [n] ground-state index of each ion, reference layout
     const int* gs_of_local[2];  // [n_T] the same, by type-local index
+    const int* local_of_rank[2]; // [n_T] type-local index of the r-th ion of the type in lattice
+                                //       order (null: identity) - dense blocks only
     const int* len;             // [2][n]
     const int64_t* offset;      // [n] first interaction of each ion
     const stb_process* procs;   // device copy, strengths already replaced by the system's
@@ -195,9 +197,10 @@ __global__ void k_export(ExportArgs A) {
                     int kl = 0;
                     bool ok;
                     if (L.dense) {
-                        idx = (int64_t)ql * L.ld[U] + e;
+                        // partners in LATTICE order (the r-th ion of type U), wherever it is stored
+                        kl = e < L.n[U] ? (A.local_of_rank[U] ? A.local_of_rank[U][e] : e) : 0;
+                        idx = (int64_t)ql * L.ld[U] + kl;
                         ok = e < L.n[U] && B.g[0][idx] != 0.0;
-                        kl = e;
                         const unsigned m = __ballot_sync(0xffffffffu, ok);
                         e = seen + __popc(m & ((1u << lane) - 1u));
                         seen += __popc(m);

@@ -86,7 +86,29 @@ struct DevLattice {
     int blk_stride;              // doubles per system in the `blocks` array
     int n_coop;                  // 0, or 3 roles: S as first donor, S as second donor, A as acceptor
     CoopList coop[3];
+    int quad;                    // 1: the sensitizers are stored in quads of strongly coupled ions
+                                 // (type-local indices 4m .. 4m+3), see group_sensitizers()
 };
+
+// Rows of type T owned by CTA `rank` of a group of G CTAs.  Quad lattices split the sensitizers in
+// whole quads, so that the block preconditioner of a quad never straddles two CTAs.
+__host__ __device__ inline void stb_own_rows(const DevLattice& L, int T, int rank, int G, int& lo, int& cnt) {
+    if (T == 0 && L.quad) {
+        const int nq = (L.n[0] + 3) / 4;
+        const int q_lo = (int)(((long long)nq * rank) / G), q_hi = (int)(((long long)nq * (rank + 1)) / G);
+        lo = 4 * q_lo;
+        const int hi = 4 * q_hi < L.n[0] ? 4 * q_hi : L.n[0];
+        cnt = hi > lo ? hi - lo : 0;
+    } else {
+        lo = (int)(((long long)L.n[T] * rank) / G);
+        cnt = (int)(((long long)L.n[T] * (rank + 1)) / G) - lo;
+    }
+}
+// the largest such count over the ranks
+__host__ __device__ inline int stb_own_rows_max(const DevLattice& L, int T, int G) {
+    if (T == 0 && L.quad) return 4 * (((L.n[0] + 3) / 4 + G - 1) / G);
+    return (L.n[T] + G - 1) / G;
+}
 
 // per-system parameters as the kernels see them
 struct SysParams {

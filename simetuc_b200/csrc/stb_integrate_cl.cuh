@@ -23,6 +23,12 @@
 #include "stb_integrate.cuh"
 
 #define CL_RG 8            // rows per row group
+// GMRES basis size of the cluster integrators.  Smaller than the grid integrator's STB_KRYLOV: the
+// Hessenberg / rotation arrays live in static shared memory, which the difference array needs more
+// (a linear solve that does not converge in CL_KRYLOV iterations fails the Newton iteration, the
+// step is halved: with the quad preconditioner solves take 1-6 iterations).
+#define CL_KRYLOV 20
+#define CL_KRED (CL_KRYLOV + 4)
 #define CL_MAXRG 256       // row groups per CTA
 #define CL_MAXG 8
 #ifndef CL_PIECE_FIX
@@ -35,7 +41,8 @@ struct ClLayout {          // offsets in doubles into dynamic shared memory
     int cntm[2], cntp[2];  // max own rows per type (over the ranks), rounded up to CL_RG
     int PO;                // pitch of own-compact vectors
     int nkp[2], nst[2];    // partner pairs / warp steps (4 pairs) per partner type
-    int zy, zv, dd, psi, scl, fv, tw, kv, minv, mcur, F, Pp, part, info, V, D, gres;
+    int zy, zv, dd, psi, scl, fv, tw, kv, minv, mcur, qinv, F, Pp, part, info, V, D, gres;
+    int sq, nqm;               // quad lattices: states of a sensitizer quad, quads per CTA (max over ranks)
     int gres_off[2][2];    // resident pair rows of block [T][U], relative to gres (-1: streamed)
     int nfm;               // field slots per row, max over the types
     int nsm;               // field slots of one block, max over the blocks
@@ -61,7 +68,7 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
         Y.ldz[U] = (L.n[U] + 1) & ~1;
         Y.nkp[U] = Y.ldz[U] / 2;
         Y.nst[U] = (Y.nkp[U] + 3) / 4;
-        Y.cntm[U] = (L.n[U] + G - 1) / G;
+        Y.cntm[U] = stb_own_rows_max(L, U, G);
         Y.cntp[U] = (Y.cntm[U] + CL_RG - 1) / CL_RG * CL_RG;
     }
     Y.zoff[0] = 0;
@@ -88,6 +95,10 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.moff[1] = L.s[0] * L.s[0] * Y.cntm[0];
     Y.minv = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);
     Y.mcur = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);     // rows of I - c J_qq of the current iterate
+    // quad lattices: inverse of I - cJ restricted to every sensitizer quad, [entry][quad]
+    Y.sq = L.quad ? 4 * L.s[0] : 0;
+    Y.nqm = L.quad ? Y.cntm[0] / 4 : 0;
+    Y.qinv = take(Y.sq * Y.sq * Y.nqm);
     Y.nfm = L.nf[0] > L.nf[1] ? L.nf[0] : L.nf[1];
     if (Y.nfm < 1) Y.nfm = 1;
     Y.foff[0] = 0;
@@ -98,7 +109,7 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
         for (int U = 0; U < 2; ++U)
             if (L.blk[T][U].n_slots > Y.nsm) Y.nsm = L.blk[T][U].n_slots;
     Y.Pp = take(STB_NW * 2 * Y.nsm * CL_RG);
-    Y.part = take(2 * G * STB_KRED);
+    Y.part = take(2 * G * CL_KRED);
     Y.info = take(compact ? 0 : Y.PO + Y.PO / 2);            // three int tables of PO entries
     Y.V = v_smem > 0 ? take(v_smem * Y.PO) : -1;       // the first v_smem basis vectors
     Y.D = d_smem ? take(8 * Y.PO) : -1;
@@ -122,6 +133,10 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
 // than 30 %, after CL_PC_MAXAGE steps or after a failed Newton iteration, CVODE's rule); the operator
 // is then applied as Minv_old (M v - c k(v)) with the rows of the current M = I - c J_qq.
 #define CL_OPT_LAGPC 2
+// Quad lattices (DevLattice.quad): block preconditioner over quads of strongly coupled sensitizers
+// instead of single ions - energy migration between close Yb ions is what the single-ion blocks
+// miss (Krylov iterations per linear solve fall by half on the Yb-Tm sweeps).
+#define CL_OPT_QUAD 4
 #define CL_PC_MAXAGE 20
 #define CL_PC_DRIFT 0.3
 
@@ -133,6 +148,7 @@ struct ClArgs {
     int G;
     int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
     int opts;                      // CL_OPT_* bits
+    const stb_process* procs;      // [L.n_proc] the process table (quad lattices: couplings inside a quad)
     int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
     int64_t n_t;
     const double* t;
@@ -356,11 +372,10 @@ struct ClShared {
     SysParams P;
     Ctl C;
     ClLayout Y;
-    double H[(STB_KRYLOV + 1) * STB_KRYLOV];
-    double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV], rd[STB_KRYLOV];
+    double H[(CL_KRYLOV + 1) * CL_KRYLOV];
+    double cs[CL_KRYLOV], sn[CL_KRYLOV], gg[CL_KRYLOV + 1], yk_s[CL_KRYLOV], rd[CL_KRYLOV];
     double red[STB_NW * 4];
-    double dred[2][STB_NW][8];                   // k_integrate_cl2_t: per-warp partials of 8 reduced values
-    double rv[STB_KRED];
+    double rv[CL_KRED];
     int wb_g[STB_NW + 1], wb_t[STB_NW + 1];      // work-list boundaries of the warps
     int wpos[STB_NW + 1];                        // the same as linear step positions
     // pieces of segments shared by several warps are summed in warp order:
@@ -424,8 +439,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     double (&ERRC)[6] = K.ERRC;
     if (tid == 0) {
         for (int T = 0; T < 2; ++T) {
-            r_lo[T] = (int)(((int64_t)L.n[T] * rank) / G);
-            cnt[T] = (int)(((int64_t)L.n[T] * (rank + 1)) / G) - r_lo[T];
+            stb_own_rows(L, T, rank, G, r_lo[T], cnt[T]);
             nrg[T] = (cnt[T] + CL_RG - 1) / CL_RG;
         }
         ob[0] = 0;
@@ -474,6 +488,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     double* Mcur = dyn + Y.mcur;
     const bool lagpc = (A.opts & CL_OPT_LAGPC) != 0;
     const bool guess = (A.opts & CL_OPT_GUESS) != 0;
+    // quad lattices: the sensitizers are preconditioned in blocks of four strongly coupled ions
+    // (needs the operator in the form Minv (M v - c k(v)), i.e. the lagged mode)
+    const bool quadpc = L.quad && lagpc && (A.opts & CL_OPT_QUAD) != 0 && A.procs != nullptr;
+    double* Qinv = dyn + Y.qinv;
     double* F = dyn + Y.F;
     double* Pp = dyn + Y.Pp;
     double* part = dyn + Y.part;
@@ -488,7 +506,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     auto Vrow = [&](int i) -> double* {
         return i < nvs ? dyn + Y.V + i * PO : wk + (int64_t)(i - nvs) * PO;
     };
-    double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(STB_KRYLOV + 1) * PO;
+    double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(CL_KRYLOV + 1) * PO;
 
 #ifndef STB_CL_NO_ZEROFILL
     // start from a defined state: nothing below may depend on what an earlier kernel left in the
@@ -666,12 +684,12 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
         if (tid < K) {
 #pragma unroll
             for (int r = 0; r < CL_MAXG; ++r)
-                if (r < G) cl_st_f64(rb_part[r] + (uint32_t)(((pbuf * G + rank) * STB_KRED + tid) * 8), mine);
+                if (r < G) cl_st_f64(rb_part[r] + (uint32_t)(((pbuf * G + rank) * CL_KRED + tid) * 8), mine);
         }
         cl_barrier();
         if (tid < K) {
             double acc = 0.0;
-            for (int r = 0; r < G; ++r) acc += part[(pbuf * G + r) * STB_KRED + tid];
+            for (int r = 0; r < G; ++r) acc += part[(pbuf * G + r) * CL_KRED + tid];
             S.rv[tid] = acc;
         }
         pbuf ^= 1;
@@ -776,6 +794,18 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     // x_a = sum_b Minv[a][b] r_b for own element (T, a, i), r = own-compact vector
     auto minv_apply = [&](int T, int a, int i, const double* r) -> double {
         const int s = L.s[T];
+        if (quadpc && T == 0) {
+            // row (i % 4) * s + a of the inverse of the quad's block
+            const int Q = i >> 2, sq = Y.sq;
+            const double* Bp = Qinv + (((i & 3) * s + a) * sq) * Y.nqm + Q;
+            const double* rq = r + ob[0] + 4 * Q;
+            double acc = 0.0;
+            for (int m = 0; m < 4; ++m) {
+                if (4 * Q + m >= cnt[0]) break;
+                for (int b = 0; b < s; ++b) acc = fma(Bp[(m * s + b) * Y.nqm], rq[b * cnt[0] + m], acc);
+            }
+            return acc;
+        }
         const double* Mp = Minv + Y.moff[T] + (a * s) * Y.cntm[T] + i;
         const double* rq = r + ob[T] + i;
         double acc = 0.0;
@@ -809,7 +839,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             const TermTable& tt = L.terms[T];
             const double* lin = P.lin[T];
             const double* Fq = F + Y.foff[T] + i;
-            if (s <= 2) {
+            if (s <= 2 && !(quadpc && T == 0)) {
                 if (a != 0) continue;
                 double m00 = 1.0 - c * lin[0], m01 = 0.0, m10 = 0.0, m11 = 1.0;
                 if (s == 2) { m01 = -c * lin[1]; m10 = -c * lin[2]; m11 = 1.0 - c * lin[3]; }
@@ -840,19 +870,58 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 const double kq = c * P.C[tt.proc[t]] * Fq[tt.fslot[t] * Y.cntp[T]];
                 Mp[tt.a[t] * cm] += (e & 0x4000) ? -kq : kq;     // row b_t: -, row a_t: +
             }
-            if (lagpc && refresh) {
+            if (lagpc && refresh && !(quadpc && T == 0)) {
                 double* Mi = Minv + Y.moff[T] + (a * s) * cm + i;
                 for (int b = 0; b < s; ++b) Mi[b * cm] = Mp[b * cm];
             }
         }
         __syncthreads();
         if (!refresh) return;
-        // 2. in-place Gauss-Jordan of the larger blocks, 64 threads per ion (<= 3 entries each), no
+        if (quadpc && cnt[0] > 0) {
+            // blocks of I - cJ over the quads: ion blocks from Mcur, couplings between the ions of a
+            // quad from the pair rates, the state at the current iterate and the S-S processes:
+            // interaction (donor q, partner k): rate = C g_qk y_q[ii] y_k[fi] moves q: ii -> if, k: fi -> ff
+            const int s0 = L.s[0], sq = Y.sq, cm0 = Y.cntm[0];
+            const int nq = (cnt[0] + 3) >> 2;
+            const double* g00 = L.blk[0][0].g[0];
+            const double* yS = zy + Y.zoff[0] + r_lo[0];
+            for (int e = tid; e < nq * sq * sq; e += STB_NT) {
+                const int Q = e / (sq * sq), rc = e - Q * sq * sq;
+                const int rho = rc / sq, gam = rc - rho * sq;
+                const int mq = rho / s0, aq = rho - mq * s0, mk = gam / s0, ak = gam - mk * s0;
+                const int iq = 4 * Q + mq, ik = 4 * Q + mk;
+                double v;
+                if (iq >= cnt[0] || ik >= cnt[0]) {
+                    v = rho == gam ? 1.0 : 0.0;               // padding of the last quad
+                } else if (mq == mk) {
+                    v = Mcur[Y.moff[0] + (aq * s0 + ak) * cm0 + iq];
+                } else {
+                    v = 0.0;
+                    const double g = g00 ? g00[(int64_t)(r_lo[0] + iq) * L.ld[0] + r_lo[0] + ik] : 0.0;
+                    for (int p = 0; p < L.n_proc; ++p) {
+                        const stb_process pr = A.procs[p];
+                        if (pr.donor_type != 0 || pr.partner_type != 0 || P.C[p] == 0.0) continue;
+                        const double cg = c * P.C[p] * g;
+                        if (ak == pr.fi) {            // q donor, k partner: d rate / d y_k[fi]
+                            const double w = cg * yS[pr.ii * Y.ldz[0] + iq];
+                            if (aq == pr.ii) v += w;
+                            if (aq == pr.if_) v -= w;
+                        }
+                        if (ak == pr.ii) {            // k donor, q partner: d rate / d y_k[ii]
+                            const double w = cg * yS[pr.fi * Y.ldz[0] + iq];
+                            if (aq == pr.fi) v += w;
+                            if (aq == pr.ff) v -= w;
+                        }
+                    }
+                }
+                Qinv[(rho * sq + gam) * Y.nqm + Q] = v;
+            }
+            __syncthreads();
+        }
+        // 2. in-place Gauss-Jordan of the larger blocks, 64 threads per block (<= 3 entries each), no
         //    pivoting (column-diagonally-dominant M-matrix); compact rolled code: a lane-per-row
         //    shuffle version costs 4-10k cycles per call (tools/ubench.cu), mostly instruction fetch
-        for (int T = 0; T < 2; ++T) {
-            const int s = L.s[T], cm = Y.cntm[T];
-            if (s <= 2 || cnt[T] <= 0) continue;
+        auto gauss_jordan = [&](double* base, int s, int cm, int count) {
             const int ss = s * s, tl = tid & 63;
             int ei[3], ej[3];
 #pragma unroll
@@ -861,10 +930,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 ei[u] = e / s;
                 ej[u] = e - ei[u] * s;
             }
-            for (int ion0 = 0; ion0 < cnt[T]; ion0 += STB_NT / 64) {
-                const int ion = ion0 + (tid >> 6);
-                const bool act = ion < cnt[T];
-                double* Mq = Minv + Y.moff[T] + (act ? ion : 0);
+            for (int blk0 = 0; blk0 < count; blk0 += STB_NT / 64) {
+                const int blk = blk0 + (tid >> 6);
+                const bool act = blk < count;
+                double* Mq = base + (act ? blk : 0);
                 for (int p = 0; p < s; ++p) {
                     double nv[3];
                     if (act) {
@@ -890,7 +959,12 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     __syncthreads();
                 }
             }
+        };
+        for (int T = 0; T < 2; ++T) {
+            if (L.s[T] <= 2 || cnt[T] <= 0 || (quadpc && T == 0)) continue;
+            gauss_jordan(Minv + Y.moff[T], L.s[T], Y.cntm[T], cnt[T]);
         }
+        if (quadpc && cnt[0] > 0) gauss_jordan(Qinv, Y.sq, Y.nqm, (cnt[0] + 3) >> 2);
     };
 
     auto apply_change_D = [&](int order) {
@@ -1118,7 +1192,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         const int inf = own_inf[k];
                         const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
                         double kq = term_sum(T, a, i, zy);
-                        if (lagpc && L.s[T] > 2) {
+                        if (lagpc && (L.s[T] > 2 || (quadpc && T == 0))) {
                             // lagged inverse: Minv_old (M v - c k(v)), rows of the current M in Mcur
                             const int s = L.s[T], cm = Y.cntm[T];
                             const double* Mp = Mcur + Y.moff[T] + (a * s) * cm + i;
@@ -1136,7 +1210,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                             const int inf = own_inf[k];
                             const int T = (inf >> 30) & 1, a = (inf >> 24) & 63, i = inf & 0xffffff;
                             const double mk = minv_apply(T, a, i, kv);
-                            tw[k] = lagpc && L.s[T] > 2 ? mk / scl[k] : Vj[k] - c * mk / scl[k];
+                            tw[k] = lagpc && (L.s[T] > 2 || (quadpc && T == 0)) ? mk / scl[k]
+                                                                                : Vj[k] - c * mk / scl[k];
                         }
                     }
                     __syncthreads();
@@ -1175,14 +1250,14 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     const bool reorth = !(hn2 > 1e-8 * ww);
                     if (reorth) {
                         // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
-                        if (tid <= j) S.H[tid * STB_KRYLOV + j] = S.rv[tid];
+                        if (tid <= j) S.H[tid * CL_KRYLOV + j] = S.rv[tid];
                         __syncthreads();
                         dots();
                         reduce_post(K, tid < K ? S.rv[tid] : 0.0);
                         const double w2 = S.rv[j + 1];
                         hn2 = w2;
                         for (int i = 0; i <= j; ++i) hn2 = fma(-S.rv[i], S.rv[i], hn2);
-                        if (tid <= j) S.H[tid * STB_KRYLOV + j] += S.rv[tid];
+                        if (tid <= j) S.H[tid * CL_KRYLOV + j] += S.rv[tid];
                         orth();
                         if (!(hn2 > 1e-8 * w2)) {
                             double v1[1] = {0.0};
@@ -1199,11 +1274,11 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     // the path of the threads that orthogonalise and exchange the next direction
                     if (tid == STB_NT - 32) {
                         C.st.n_jv += 1;
-                        double* Hc = S.H + j;   // column j, stride STB_KRYLOV
+                        double* Hc = S.H + j;   // column j, stride CL_KRYLOV
                         double prev = reorth ? Hc[0] : S.rv[0];
                         for (int i = 0; i < j; ++i) {
-                            const double b = reorth ? Hc[(i + 1) * STB_KRYLOV] : S.rv[i + 1];
-                            Hc[i * STB_KRYLOV] = S.cs[i] * prev + S.sn[i] * b;
+                            const double b = reorth ? Hc[(i + 1) * CL_KRYLOV] : S.rv[i + 1];
+                            Hc[i * CL_KRYLOV] = S.cs[i] * prev + S.sn[i] * b;
                             prev = -S.sn[i] * prev + S.cs[i] * b;
                         }
                         const double a = prev;
@@ -1212,7 +1287,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         const double csj = dnm > 0.0 ? a * idn : 1.0, snj = hn * idn;
                         S.cs[j] = csj;
                         S.sn[j] = snj;
-                        Hc[j * STB_KRYLOV] = dnm;
+                        Hc[j * CL_KRYLOV] = dnm;
                         S.rd[j] = idn;
                         S.gg[j + 1] = -snj * S.gg[j];
                         S.gg[j] = csj * S.gg[j];
@@ -1220,13 +1295,13 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         double beta = fabs(S.gg[j + 1]);
                         if (!(hn > 0.0) || !isfinite(hn)) beta = 0.0;
                         C.beta = beta;
-                        if (!(beta > C.tol_lin) || j + 1 >= STB_KRYLOV) {
+                        if (!(beta > C.tol_lin) || j + 1 >= CL_KRYLOV) {
                             // x = V y with R y = g; ||x|| = ||y|| (orthonormal basis)
                             const int nk = j + 1;
                             double y2 = 0.0;
                             for (int i = nk - 1; i >= 0; --i) {
                                 double acc = S.gg[i];
-                                for (int k = i + 1; k < nk; ++k) acc -= S.H[i * STB_KRYLOV + k] * S.yk_s[k];
+                                for (int k = i + 1; k < nk; ++k) acc -= S.H[i * CL_KRYLOV + k] * S.yk_s[k];
                                 const double yi = acc * S.rd[i];
                                 S.yk_s[i] = yi;
                                 y2 = fma(yi, yi, y2);
@@ -1250,7 +1325,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     sync_all();
                     CLPROF(12)
                     ++j;
-                    lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
+                    lin_done = !(C.beta > C.tol_lin) || j >= CL_KRYLOV;
                 }
                 const int nk = C.kk;
                 const int flag = C.flag;

@@ -134,6 +134,7 @@ template <bool COOP>
 __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     STB_DYN_SMEM(dyn);
     __shared__ ClShared S;
+    __shared__ double s_dred[2][STB_NW][CL2_CH];     // per-warp partials of the 8 reduced values
     DevLattice& L = S.L;
     SysParams& P = S.P;
     Ctl& C = S.C;
@@ -179,8 +180,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     double (&ERRC)[6] = K.ERRC;
     if (tid == 0) {
         for (int T = 0; T < 2; ++T) {
-            r_lo[T] = (int)(((int64_t)L.n[T] * rank) / G);
-            cnt[T] = (int)(((int64_t)L.n[T] * (rank + 1)) / G) - r_lo[T];
+            stb_own_rows(L, T, rank, G, r_lo[T], cnt[T]);
             nrg[T] = (cnt[T] + CL_RG - 1) / CL_RG;
         }
         ob[0] = 0;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     auto Vrow = [&](int i) -> double* {
         return i < nvs ? dyn + Y.V + i * PO : wk + (int64_t)(i - nvs) * PO;
     };
-    double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(STB_KRYLOV + 1) * PO;
+    double* D = A.d_smem ? dyn + Y.D : wk + (int64_t)(CL_KRYLOV + 1) * PO;
 
 #ifndef STB_CL_NO_ZEROFILL
     // start from a defined state: nothing below may depend on what an earlier kernel left in the
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     // Gauss-Jordan teams and every barrier): the owner phases are bound by issue slots
     const bool wown = (warp * 32 < R0) ? (warp * 32 < cnt[0] * Wt[0]) : (warp * 32 - R0 < cnt[1] * Wt[1]);
     const int GIV = STB_NT - 32;                           // the thread that keeps the Hessenberg / Givens state
-    for (int i = tid; i < 2 * STB_NW * CL2_CH; i += STB_NT) (&S.dred[0][0][0])[i] = 0.0;
+    for (int i = tid; i < 2 * STB_NW * CL2_CH; i += STB_NT) (&s_dred[0][0][0])[i] = 0.0;
     __syncthreads();
 
     // every CTA of the cluster must be running before its shared memory is written remotely
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     };
     // CTA partial `mine` of value idx (one thread per value) -> slot of this rank in every CTA
     auto push_part = [&](int idx, double mine) {
-        const int slot = (pbuf * G + rank) * STB_KRED + idx;
+        const int slot = (pbuf * G + rank) * CL_KRED + idx;
         if (G > 1) {
 #pragma unroll
             for (int r = 0; r < CL_MAXG; ++r)
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
     auto cta_partials = [&](const double (&v)[8], int nb, int c0) {
         if (wown) {
             const double r = cl2_warp_reduce8(v, lane);
-            if ((lane & 3) == 0) S.dred[qbuf][warp][vi_lane] = r;
+            if ((lane & 3) == 0) s_dred[qbuf][warp][vi_lane] = r;
         }
         CLPROF(21)
         __syncthreads();
@@ -451,16 +451,16 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
         if (tid < nb) {
             double mine = 0.0;
 #pragma unroll
-            for (int w = 0; w < STB_NW; ++w) mine += S.dred[qbuf][w][tid];
+            for (int w = 0; w < STB_NW; ++w) mine += s_dred[qbuf][w][tid];
             push_part(c0 + tid, mine);
         }
         qbuf ^= 1;
     };
     // cluster total of exchanged value idx, summed in rank order (identical in every thread)
     auto total_of = [&](int idx) -> double {
-        const double* pp = part + pbuf * G * STB_KRED + idx;
+        const double* pp = part + pbuf * G * CL_KRED + idx;
         double acc = 0.0;
-        for (int r = 0; r < G; ++r) acc += pp[r * STB_KRED];
+        for (int r = 0; r < G; ++r) acc += pp[r * CL_KRED];
         return acc;
     };
     // all-reduce of K <= 8 per-thread values: totals in tot[] of every thread, no trailing barrier
@@ -884,10 +884,10 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                     if (reorth) {
                         // cancellation: explicit norm and one re-orthogonalisation pass (DGKS)
                         if (tid == GIV)
-                            for (int i = 0; i <= j; ++i) S.H[i * STB_KRYLOV + j] = S.rv[i];
+                            for (int i = 0; i <= j; ++i) S.H[i * CL_KRYLOV + j] = S.rv[i];
                         hn2 = dots_orth();
                         if (tid == GIV)
-                            for (int i = 0; i <= j; ++i) S.H[i * STB_KRYLOV + j] += S.rv[i];
+                            for (int i = 0; i <= j; ++i) S.H[i * CL_KRYLOV + j] += S.rv[i];
                         if (!(hn2 > 1e-8 * ww)) {
                             double v8[8] = {w * w, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, tot[8];
                             allreduce8(1, v8, tot);
@@ -901,11 +901,11 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                     // the threads that normalise and exchange the next direction
                     if (tid == GIV) {
                         C.st.n_jv += 1;
-                        double* Hc = S.H + j;   // column j, stride STB_KRYLOV
+                        double* Hc = S.H + j;   // column j, stride CL_KRYLOV
                         double prev = reorth ? Hc[0] : S.rv[0];
                         for (int i = 0; i < j; ++i) {
-                            const double b = reorth ? Hc[(i + 1) * STB_KRYLOV] : S.rv[i + 1];
-                            Hc[i * STB_KRYLOV] = S.cs[i] * prev + S.sn[i] * b;
+                            const double b = reorth ? Hc[(i + 1) * CL_KRYLOV] : S.rv[i + 1];
+                            Hc[i * CL_KRYLOV] = S.cs[i] * prev + S.sn[i] * b;
                             prev = -S.sn[i] * prev + S.cs[i] * b;
                         }
                         const double a = prev;
@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                         const double csj = dnm > 0.0 ? a * idn : 1.0, snj = hn * idn;
                         S.cs[j] = csj;
                         S.sn[j] = snj;
-                        Hc[j * STB_KRYLOV] = dnm;
+                        Hc[j * CL_KRYLOV] = dnm;
                         S.rd[j] = idn;
                         S.gg[j + 1] = -snj * S.gg[j];
                         S.gg[j] = csj * S.gg[j];
@@ -922,13 +922,13 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                         double beta = fabs(S.gg[j + 1]);
                         if (!(hn > 0.0) || !isfinite(hn)) beta = 0.0;
                         C.beta = beta;
-                        if (!(beta > C.tol_lin) || j + 1 >= STB_KRYLOV) {
+                        if (!(beta > C.tol_lin) || j + 1 >= CL_KRYLOV) {
                             // x = V y with R y = g; ||x|| = ||y|| (orthonormal basis)
                             const int nk = j + 1;
                             double y2 = 0.0;
                             for (int i = nk - 1; i >= 0; --i) {
                                 double acc = S.gg[i];
-                                for (int kk2 = i + 1; kk2 < nk; ++kk2) acc -= S.H[i * STB_KRYLOV + kk2] * S.yk_s[kk2];
+                                for (int kk2 = i + 1; kk2 < nk; ++kk2) acc -= S.H[i * CL_KRYLOV + kk2] * S.yk_s[kk2];
                                 const double yi = acc * S.rd[i];
                                 S.yk_s[i] = yi;
                                 y2 = fma(yi, yi, y2);
@@ -949,7 +949,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                     sync_all();
                     CLPROF(12)
                     ++j;
-                    lin_done = !(C.beta > C.tol_lin) || j >= STB_KRYLOV;
+                    lin_done = !(C.beta > C.tol_lin) || j >= CL_KRYLOV;
                 }
                 const int nk = C.kk;
                 const int flag = C.flag;

@@ -230,3 +230,28 @@ def test_c4_large_lattice_rows_and_tolerance_tightening():
     ref = curves[1e-10]
     big = ref > 1e-9
     assert np.all(np.abs(curves[1e-8] - ref)[big] <= 1e-4 * ref[big])
+
+
+def test_quad_preconditioner_same_solution_fewer_iterations(monkeypatch):
+    """Quad lattices (the library stores strongly coupled sensitizers next to each other and
+    preconditions them in blocks of four): same interaction lists in the reference's order, same
+    trajectory within the integration tolerance, about half the Krylov iterations."""
+    import bench
+    cte = bench.make_cte()
+    res = {}
+    for quads in ('1', '0'):
+        monkeypatch.setenv('STB_QUADS', quads)
+        lat = lattice.generate(cte, seed=2000)
+        system = precalculate.build_system(cte, lat, n_sys=1)
+        _, _, pop = system.ground_states()
+        t_pulse, t_sol = bench.t_grids(cte)
+        _, y, avg, st_p, st = system.integrate_dynamics(t_pulse, t_sol[::5], pop.astype(float), rtol=RTOL,
+                                                        atol=ATOL, want_y=True)
+        assert st_p[0]['status'] == 0 and st[0]['status'] == 0
+        res[quads] = (system.export_interactions(), y[0], st[0]['n_jv'], st[0]['n_steps'])
+        system.close()
+    for a, b in zip(res['1'][0], res['0'][0]):
+        assert np.array_equal(a, b)                      # reference order, whatever the storage order
+    assert parity_metric(res['1'][1], res['0'][1]) <= 1.0
+    assert res['1'][2] < 0.75 * res['0'][2]              # Krylov iterations
+    assert abs(res['1'][3] - res['0'][3]) <= 0.05 * res['0'][3]
