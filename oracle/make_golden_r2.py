@@ -14,6 +14,8 @@ Cases:
            pulse + 1000-point relaxation
   c3a/c3b  two corners of the C3 concentration grid (10 % / 0.1 % and 50 % / 2 %), N_uc=10, dynamics
   c2all    all 32 powers of the C2 sweep on the bench lattice (seed 2000): emission curves only
+  coop     cooperative (S-S-A) energy transfer on a 277-ion lattice, d_max_coop 8 A: pulse + 100-point
+           relaxation, and row 40 of the same relaxation without the cooperative process
 
 Stored per case: the lattice arrays fed to the oracle (ion types, positions; the test regenerates the
 lattice with the same seed and checks they agree), the state after the pulse, the full state at 12
@@ -85,6 +87,41 @@ def case_c3b():
     return _ybtm(10, 50.0, 2.0, 3002, 1000)
 
 
+def coop_case():
+    """Settings + lattice of the cooperative-ET trajectory case (shared with the test)."""
+    from simetuc_b200 import configs, lattice
+    cte = configs.test_cte()
+    cte['lattice'] = dict(cte['lattice'])
+    lat = lattice.generate_arrays(configs.yb_tm_cte(N_uc=10, S_conc=15.0, A_conc=3.0), seed=4343)
+    g = {'ion_type': lat['ion_type'], 'dist_array': lat['dist_array'], 'info': np.array([2, 7]),
+         'doped_lattice': lat['doped_lattice']}
+    cte['lattice']['d_max_coop'] = 8.0
+    cte['energy_transfer']['coop1'].strength = 5e11
+    for exc in cte['excitations']['Vis_473']:
+        exc.active = False
+    for exc in cte['excitations']['NIR_980']:
+        exc.active = True
+        exc.power_dens = 1e9
+    return cte, g
+
+
+def case_coop():
+    from oracle import oracle_np as onp
+    from tests.helpers import oracle_operands
+    cte, g = coop_case()
+    op = oracle_operands(g, cte, coop=True)
+    t_pulse, t_sol = onp.time_grids(1e-8, onp.t_simulation(cte['decay']), 100)
+    y0 = op['initial_population'].astype(float)
+    kw = dict(rtol=RTOL, atol=ATOL, nsteps=100000)
+    yp = onp.solve_pulse(t_pulse, y0, op['abs'], op['decay'], op['ET'], op['N_indices'], op['jac_indices'],
+                         coop=op['coop'], **kw)
+    ys = onp.solve_relax(t_sol, yp[-1], op['decay'], op['ET'], op['N_indices'], op['jac_indices'],
+                         coop=op['coop'], **kw)
+    y_nc = onp.solve_relax(t_sol, yp[-1], op['decay'], op['ET'], op['N_indices'], op['jac_indices'], **kw)
+    return dict(t_sol=t_sol, y_pulse_end=yp[-1], y=ys, y_no_coop_row40=y_nc[40], ion_type=np.asarray(g['ion_type']),
+                n_coop=np.int64(op['coop'][1].shape[0]))
+
+
 def _c2_one(k):
     import warnings
     warnings.simplefilter('ignore')
@@ -123,7 +160,7 @@ def _run_case(name):
 
 
 def main():
-    cases = sys.argv[1:] or ['fix240', 'c1p', 'c3a', 'c3b', 'c2all']
+    cases = sys.argv[1:] or ['fix240', 'c1p', 'c3a', 'c3b', 'coop', 'c2all']
     single = [c for c in cases if c != 'c2all']
     with Pool(8) as pool:
         pending = [pool.apply_async(_run_case, (c,)) for c in single]

@@ -625,6 +625,22 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     if (n_ions > 2000000) { fail(STB_EINVAL, "too many ions"); return nullptr; }
     CKP(cudaSetDevice(device));
     stb_system* S = new stb_system();
+    // every failure below releases what the handle already owns (stream, pooled device blocks)
+    double* d_geo = nullptr;
+    auto die = [&]() -> stb_system* {
+        if (d_geo) pool_free(d_geo);
+        stb_system_destroy(S);
+        return nullptr;
+    };
+#define CKS(call)                                                                     \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) {                                                      \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);               \
+            return die();                                                             \
+        }                                                                             \
+    } while (0)
+
     S->device = device;
     S->n_ions = n_ions;
     S->s[0] = n_S_states;
@@ -641,14 +657,13 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             bad = p.ii >= sd || p.if_ >= sd || p.fi >= sp || p.ff >= sp;
         if (bad) {
             fail(STB_EINVAL, "The number of A or S states is lower than required by a process.");
-            delete S;
-            return nullptr;
+            return die();
         }
     }
     cudaDeviceProp prop;
-    CKP(cudaGetDeviceProperties(&prop, device));
+    CKS(cudaGetDeviceProperties(&prop, device));
     S->sm_count = prop.multiProcessorCount;
-    CKP(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
+    CKS(cudaStreamCreateWithFlags(&S->stream, cudaStreamNonBlocking));
 
     // ---- ion table: type-local indices, ground states, layout maps (lattice.py:259-298) -------
     const int n = (int)n_ions;
@@ -676,7 +691,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     }
     for (int T = 0; T < 2; ++T) S->gs_of_local[T].assign(S->n[T], 0);
     for (int q = 0; q < n; ++q) S->gs_of_local[S->type[q]][S->local_idx[q]] = S->gs_ref[q];
-    if (S->N == 0) { fail(STB_EINVAL, "No states: the number of energy states is zero."); delete S; return nullptr; }
+    if (S->N == 0) { fail(STB_EINVAL, "No states: the number of energy states is zero."); return die(); }
     DevLattice& L = S->hL;
     memset(&L, 0, sizeof(L));
     L.n_ions = n;
@@ -696,16 +711,16 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             S->ref_of_plane[pl] = S->gs_ref[q] + a;
         }
     }
-    if (build_tables(S, L) != STB_OK) { delete S; return nullptr; }
+    if (build_tables(S, L) != STB_OK) { return die(); }
 
-    CKP(upload(S->stream, &S->d_type, S->type));
-    CKP(upload(S->stream, &S->d_local_idx, S->local_idx));
-    if (quad) CKP(upload(S->stream, &S->d_local_of_rank_S, S->local_of_rank_S));
-    if (n_proc > 0) CKP(upload(S->stream, &S->d_procs, S->procs));
-    CKP(upload(S->stream, &S->d_gs_ref, S->gs_ref));
-    CKP(upload(S->stream, &S->d_plane_of_ref, S->plane_of_ref));
-    CKP(upload(S->stream, &S->d_ref_of_plane, S->ref_of_plane));
-    for (int T = 0; T < 2; ++T) CKP(upload(S->stream, &S->d_gs_of_local[T], S->gs_of_local[T]));
+    CKS(upload(S->stream, &S->d_type, S->type));
+    CKS(upload(S->stream, &S->d_local_idx, S->local_idx));
+    if (quad) CKS(upload(S->stream, &S->d_local_of_rank_S, S->local_of_rank_S));
+    if (n_proc > 0) CKS(upload(S->stream, &S->d_procs, S->procs));
+    CKS(upload(S->stream, &S->d_gs_ref, S->gs_ref));
+    CKS(upload(S->stream, &S->d_plane_of_ref, S->plane_of_ref));
+    CKS(upload(S->stream, &S->d_ref_of_plane, S->ref_of_plane));
+    for (int T = 0; T < 2; ++T) CKS(upload(S->stream, &S->d_gs_of_local[T], S->gs_of_local[T]));
     L.plane_of_ref = S->d_plane_of_ref;
     L.ref_of_plane = S->d_ref_of_plane;
 
@@ -714,30 +729,29 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     memset(&G, 0, sizeof(G));
     G.n = n;
     G.d_max = d_max;
-    double* d_geo = nullptr;
     if (dist_array) {
-        CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
-        CKP(copy_on(S->stream, d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+        CKS(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * n));
+        CKS(copy_on(S->stream, d_geo, dist_array, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
         G.dist = d_geo;
     } else {
-        CKP(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
-        CKP(copy_on(S->stream, d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
+        CKS(pool_malloc((void**)&d_geo, sizeof(double) * (size_t)n * 3));
+        CKS(copy_on(S->stream, d_geo, positions, sizeof(double) * (size_t)n * 3, cudaMemcpyHostToDevice));
         G.pos = d_geo;
         if (cell) {
             G.periodic = 1;
             memcpy(G.cell, cell, sizeof(double) * 9);
-            if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); pool_free(d_geo); delete S; return nullptr; }
+            if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); return die(); }
         }
     }
     // ---- pass 1: row lengths ---------------------------------------------------------------------
-    CKP(pool_malloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
+    CKS(pool_malloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
     g_launches++;
     k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
-    CKP(cudaGetLastError());
+    CKS(cudaGetLastError());
     S->len.resize(2 * (size_t)n);
-    CKP(cudaMemcpyAsync(S->len.data(), S->d_len, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, S->stream));
-    CKP(cudaStreamSynchronize(S->stream));
+    CKS(cudaMemcpyAsync(S->len.data(), S->d_len, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, S->stream));
+    CKS(cudaStreamSynchronize(S->stream));
     // lanes per row from the mean row length (about 16 entries per lane)
     double mean_len = 0;
     for (int q = 0; q < n; ++q) mean_len += S->len[q] + S->len[n + q];
@@ -770,8 +784,8 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
                 if (L.blk[T][U].n_slots == 0 || S->n[T] == 0 || S->n[U] == 0) continue;
                 const size_t cells = (size_t)S->n[T] * L.ld[U];
                 for (int m = 0; m < L.n_mult; ++m) {
-                    CKP(pool_malloc((void**)&S->d_g[T][U][m], cells * sizeof(double)));
-                    CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, cells * sizeof(double), S->stream));
+                    CKS(pool_malloc((void**)&S->d_g[T][U][m], cells * sizeof(double)));
+                    CKS(cudaMemsetAsync(S->d_g[T][U][m], 0, cells * sizeof(double), S->stream));
                     L.blk[T][U].g[m] = S->d_g[T][U][m];
                     FD.g[T][U][m] = S->d_g[T][U][m];
                 }
@@ -783,8 +797,8 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
         S->stream_bytes = S->slots * 8 * (int64_t)L.n_mult;
         g_launches++;
         k_fill_dense<<<blocks, 256, 0, S->stream>>>(FD);
-        CKP(cudaGetLastError());
-        CKP(cudaStreamSynchronize(S->stream));
+        CKS(cudaGetLastError());
+        CKS(cudaStreamSynchronize(S->stream));
     } else {
     // ---- slice line pointers ---------------------------------------------------------------------
     std::vector<int> ion_of_local[2];
@@ -809,13 +823,13 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             }
             int64_t lines = lp.back();
             S->h_line_ptr[T][U] = lp;
-            CKP(upload(S->stream, &S->d_line_ptr[T][U], lp));
+            CKS(upload(S->stream, &S->d_line_ptr[T][U], lp));
             size_t slots = std::max<int64_t>(lines * 32, 1);
-            CKP(pool_malloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
-            CKP(cudaMemsetAsync(S->d_col[T][U], 0, slots * sizeof(uint32_t), S->stream));
+            CKS(pool_malloc((void**)&S->d_col[T][U], slots * sizeof(uint32_t)));
+            CKS(cudaMemsetAsync(S->d_col[T][U], 0, slots * sizeof(uint32_t), S->stream));
             for (int m = 0; m < L.n_mult; ++m) {
-                CKP(pool_malloc((void**)&S->d_g[T][U][m], slots * sizeof(double)));
-                CKP(cudaMemsetAsync(S->d_g[T][U][m], 0, slots * sizeof(double), S->stream));
+                CKS(pool_malloc((void**)&S->d_g[T][U][m], slots * sizeof(double)));
+                CKS(cudaMemsetAsync(S->d_g[T][U][m], 0, slots * sizeof(double), S->stream));
             }
             S->slots += lines * 32;
             L.blk[T][U].col = S->d_col[T][U];
@@ -847,16 +861,18 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             if (L.blk[T][U].n_slots == 0) FA.col[T][U] = nullptr;
     g_launches++;
     k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
-    CKP(cudaGetLastError());
-    CKP(cudaStreamSynchronize(S->stream));
+    CKS(cudaGetLastError());
+    CKS(cudaStreamSynchronize(S->stream));
     }
     pool_free(d_geo);
+    d_geo = nullptr;
     L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
-    CKP(pool_malloc((void**)&S->dL, sizeof(DevLattice)));
-    CKP(copy_on(S->stream, S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
+    CKS(pool_malloc((void**)&S->dL, sizeof(DevLattice)));
+    CKS(copy_on(S->stream, S->dL, &L, sizeof(DevLattice), cudaMemcpyHostToDevice));
     if (stb_set_batch(S, 1) != STB_OK) { stb_system_destroy(S); return nullptr; }
     return S;
 }
+#undef CKS
 
 extern "C" int stb_system_info(const stb_system* S, int64_t out[8]) {
     if (!S) return fail(STB_EINVAL, "null system");
@@ -1636,25 +1652,25 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
         ClPlan plan;
         HostTimer tm;
         bool use_cl = cl_choose(S, n, plan);
-        if (use_cl && !S->hL.n_coop && n <= plan.n_clusters) {
+        if (use_cl && (!S->hL.n_coop || L.lpr >= 32) && n <= plan.n_clusters) {
             // the whole batch runs at once: the latency of one solve decides
             const int groups = std::max(1, std::min(max_ctas / G, n));
             const double grid_us = std::ceil((double)n / groups) * est_grid_pass_us(G, (double)S->stream_bytes);
             if (grid_us < plan.est_us) use_cl = false;
         }
         if (const char* env = getenv("STB_CLUSTER")) {
-            if (atoi(env) == 0) use_cl = false;
-            else if (plan.G > 0) use_cl = true;
+            if (atoi(env) == 0 && (!S->hL.n_coop || L.lpr >= 32)) use_cl = false;
+            else if (atoi(env) != 0 && plan.G > 0) use_cl = true;
         }
         tm.mark("cl_choose");
         if (use_cl)
             return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
                                      avg_out, stats, dev);
     }
-    if (S->hL.n_coop)
-        return fail(STB_EINVAL, "cooperative energy transfer is integrated by the cluster integrator only, "
-                                "and this lattice does not fit it (all-to-all pairs, one multipolarity, "
-                                "state vector within the shared memory of 8 SMs)");
+    if (S->hL.n_coop && L.lpr < 32)
+        return fail(STB_EINVAL, "cooperative energy transfer in the grid integrator needs rows handled by whole "
+                                "warps (lattices with >= 256 partners per ion); smaller lattices are integrated "
+                                "by the cluster integrator (all-to-all pairs, one multipolarity)");
     // small systems: the gathered vector is staged in shared memory and barriers leave L1 warm;
     // if, with a few more CTAs per group, every CTA's own pair rows also fit in shared memory,
     // they are made resident there (the Krylov loop then runs out of shared memory)

@@ -380,6 +380,22 @@ __device__ __forceinline__ void load_sys_params(const DevLattice& L, const doubl
     if (threadIdx.x == 0 && L.n_coop) P.C[L.n_proc] = 1.0;     // cooperative terms: w carries the strength
 }
 
+// the same with the gathered vectors read through L2 (grid integrator: other CTAs of the group wrote
+// them; its group barrier is release-only, so L1 may hold stale lines)
+__device__ __forceinline__ double coop_list_field_cg(const CoopList& C, int q, const double* y1, const double* y2,
+                                                     const double* v1, const double* v2, int lane) {
+    const int64_t e0 = C.row_ptr[q], e1 = C.row_ptr[q + 1];
+    double acc = 0.0;
+    for (int64_t e = e0 + lane; e < e1; e += 32) {
+        const uint32_t a = C.p1[e], b = C.p2[e];
+        const double w = C.w[e];
+        if (v1) acc = fma(w, fma(__ldcg(v1 + a), __ldcg(y2 + b), __ldcg(y1 + a) * __ldcg(v2 + b)), acc);
+        else acc = fma(w * __ldcg(y1 + a), __ldcg(y2 + b), acc);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
 // cooperative field of one ion (see CoopList in stb_common.cuh)
 __device__ __forceinline__ double coop_list_field(const CoopList& C, int q, const double* y1, const double* y2,
                                                   const double* v1, const double* v2, int lane) {

@@ -372,6 +372,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         // per-ion epilogue of a row handled by W >= 16 lanes: lane j <-> state j of the ion
         auto rhs_row = [&](int T, int q, bool valid, int W, int gl, double fl) {
             const int s = L.s[T], nT = L.n[T];
+            // cooperative (three-ion) process: one more field of the ion, summed over its triple list
+            // by the whole warp (rows of such lattices are handled by W = 32 lanes, one row per warp)
+            for (int r = 0; r < L.n_coop; ++r) {
+                const CoopList& Cl = L.coop[r];
+                if (Cl.T != T) continue;
+                const double cf = coop_list_field_cg(Cl, valid ? q : nT - 1, z + L.off[Cl.T1] + Cl.col1 * L.n[Cl.T1],
+                                                  z + L.off[Cl.T2] + Cl.col2 * L.n[Cl.T2], nullptr, nullptr, lane);
+                if (gl == Cl.fslot) fl = cf;
+            }
             const bool act = valid && gl < s;
             const int e = L.off[T] + (gl < s ? gl : 0) * nT + (valid ? q : nT - 1);
             const double yj = gl < s ? z[e] : 0.0;
@@ -459,6 +468,14 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             const int s = L.s[T], nT = L.n[T];
             const bool act = valid && gl < s;
             const int qc = valid ? q : nT - 1;
+            // cooperative field linearised at the iterate yk in the direction inrm * gv
+            for (int r = 0; r < L.n_coop; ++r) {
+                const CoopList& Cl = L.coop[r];
+                if (Cl.T != T) continue;
+                const int o1 = L.off[Cl.T1] + Cl.col1 * L.n[Cl.T1], o2 = L.off[Cl.T2] + Cl.col2 * L.n[Cl.T2];
+                const double cf = inrm * coop_list_field_cg(Cl, qc, yk + o1, yk + o2, gv + o1, gv + o2, lane);
+                if (gl == Cl.fslot) fvl = cf;
+            }
             const int e = L.off[T] + (gl < s ? gl : 0) * nT + qc;
             const double yj = gl < s ? yk[e] : 0.0;
             const double kj = coop_coupling(L, P, T, W, gl, yj, fvl);

@@ -255,3 +255,35 @@ def test_quad_preconditioner_same_solution_fewer_iterations(monkeypatch):
     assert parity_metric(res['1'][1], res['0'][1]) <= 1.0
     assert res['1'][2] < 0.75 * res['0'][2]              # Krylov iterations
     assert abs(res['1'][3] - res['0'][3]) <= 0.05 * res['0'][3]
+
+
+@pytest.mark.parametrize('which', ['cluster', 'grid'])
+def test_coop_in_both_integrators(monkeypatch, which):
+    """Cooperative (three-ion, S-S-A) energy transfer (`precalculate.py:427-599`, `odesolver.py:40-41,
+    56-60`) through the cluster integrator and through the grid integrator (what lattices too large for
+    a cluster use: the manual's published dynamics run has 1230 ions and 10 453 cooperative
+    interactions) against the committed scipy-LSODA run on the oracle's operators
+    (`oracle/make_golden_r2.py coop`; 40 s of CPU)."""
+    from oracle.make_golden_r2 import coop_case
+    from tests.test_gpu_parity import make_coop_system
+    gold = _gold('coop')
+    cte, g = coop_case()
+    assert np.array_equal(g['ion_type'], gold['ion_type']) and len(g['ion_type']) > 262
+    system = make_coop_system(g, cte, d_max_coop=8.0)
+    assert system.n_coop == int(gold['n_coop']) > 100
+    _integrators(monkeypatch, which)
+    if which == 'grid':
+        monkeypatch.setenv('STB_GROUP_CTAS', '12')         # a group size only the grid integrator takes
+    t_sol = gold['t_sol']
+    t_pulse = np.linspace(0.0, t_sol[0], 2)
+    _, _, pop = system.ground_states()
+    y_p, _, st_p = system.integrate(t_pulse, pop.astype(float), pulse=True, rtol=RTOL, atol=ATOL)
+    y, _, st = system.integrate(t_sol, y_p[0, -1], pulse=False, rtol=RTOL, atol=ATOL)
+    prof = system.last_profile()
+    system.close()
+    assert st_p[0]['status'] == 0 and st[0]['status'] == 0
+    assert (prof['G'] == 12) == (which == 'grid')          # the integrator that was asked for
+    assert parity_metric(y_p[0, -1], gold['y_pulse_end']) <= 1.0
+    assert parity_metric(y[0], gold['y']) <= 1.0
+    # the cooperative channel matters: without it the state differs far beyond the tolerance
+    assert parity_metric(gold['y_no_coop_row40'], gold['y'][40]) > 100.0
