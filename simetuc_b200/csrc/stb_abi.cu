@@ -1520,6 +1520,10 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
     A.compact = plan.v2 ? 1 : 0;
     A.procs = S->d_procs;
+    A.pc_maxage = CL_PC_MAXAGE;
+    A.pc_drift = CL_PC_DRIFT;
+    if (const char* env = getenv("STB_PC_MAXAGE")) A.pc_maxage = std::max(1, atoi(env));
+    if (const char* env = getenv("STB_PC_DRIFT")) A.pc_drift = std::max(0.0, atof(env));
     A.opts = CL_OPT_GUESS | CL_OPT_LAGPC | CL_OPT_QUAD;
     if (const char* env = getenv("STB_CL_OPTS")) A.opts = atoi(env);
     A.n_t = n_t; A.t = t_p; A.y0 = y0_p; A.rtol = rtol; A.atol = atol;

@@ -149,6 +149,8 @@ struct ClArgs {
     int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
     int opts;                      // CL_OPT_* bits
     const stb_process* procs;      // [L.n_proc] the process table (quad lattices: couplings inside a quad)
+    int pc_maxage;                 // lagged block inverses: refresh after this many steps ...
+    double pc_drift;               // ... or when |c / c_factored - 1| exceeds this (CL_PC_MAXAGE, CL_PC_DRIFT)
     int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
     int64_t n_t;
     const double* t;
@@ -1099,8 +1101,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 if (C.h < eps_t) C.status = 2;
                 if (C.steps_since_out >= A.nsteps) C.status = 1;
                 C.c = C.h / ALPHA[C.order];
-                C.pc_refresh = !lagpc || C.pc_age < 0 || C.pc_age >= CL_PC_MAXAGE ||
-                               fabs(C.c / C.pc_c - 1.0) > CL_PC_DRIFT;
+                C.pc_refresh = !lagpc || C.pc_age < 0 || C.pc_age >= A.pc_maxage ||
+                               fabs(C.c / C.pc_c - 1.0) > A.pc_drift;
             }
             __syncthreads();
             if (C.status != 0) break;

@@ -755,8 +755,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                 }
             }
             const double c = h / ALPHA[order];
-            const bool pc_ref = !lagpc || C.pc_age < 0 || C.pc_age >= CL_PC_MAXAGE ||
-                                fabs(c / C.pc_c - 1.0) > CL_PC_DRIFT;
+            const bool pc_ref = !lagpc || C.pc_age < 0 || C.pc_age >= A.pc_maxage ||
+                                fabs(c / C.pc_c - 1.0) > A.pc_drift;
             const double gf = guess ? C.gfac : 0.0;
             bool first_newton = true;
             // predictor, scale, psi; the Newton start (predictor + the previous correction rescaled

@@ -634,7 +634,12 @@ class Simulations:
             # keep_y=False: the ion average commutes with the time integral, so the area under the
             # device-computed emission curves gives the same steady state without moving the
             # [n_t, N] trajectories to the host; one pass over the curves of all the systems
-            steady_all = cumulative_trapezoid(np.stack([avg for _, _, avg in sols], axis=1), sols[0][0])
+            # time along the contiguous axis: [n, kinds, n_t]
+            curves = np.ascontiguousarray(np.stack([avg for _, _, avg in sols]).transpose(0, 2, 1))
+            t_rel = sols[0][0]
+            steady_all = np.zeros_like(curves)
+            np.cumsum(0.5 * (curves[:, :, 1:] + curves[:, :, :-1]) * np.diff(t_rel), axis=2,
+                      out=steady_all[:, :, 1:])
         ions = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
         for k, (cte, (t_sol, y_sol, avg), st) in enumerate(zip(ctes, sols, stats)):
             cte['ions'] = dict(ions)
@@ -643,10 +648,10 @@ class Simulations:
                 sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
                                        average=average, own_cte=True).calculate_steady_state()
             elif pulsed:
-                avg_steady = steady_all[:, k, :]
+                avg_steady = steady_all[k].T            # [n_t, kinds] view; rows of steady_all[k] = curves
                 sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, average=average,
                                           own_cte=True)
-                sol.set_avg_data(avg_steady)
+                sol.__dict__['list_avg_data'] = list(steady_all[k])
             else:
                 sol = SteadyStateSolution(t_sol, y_sol if y_sol is not None else avg,
                                           index_S_i, index_A_j, cte, average=average, own_cte=True)

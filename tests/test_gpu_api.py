@@ -328,3 +328,91 @@ def test_cooperative_process_through_the_reference_api(lattice_file_2S_2A):
     # operands of another system are refused, not silently solved without the term
     with pytest.raises(TypeError):
         odesolver._rate_eq_pulse(0, y, abs_m, dec_m, ET, N_idx, cET, np.zeros((0, 3), np.uint32))
+
+
+def test_operand_sets_keep_their_own_parameters():
+    """Two `setup_microscopic_eqs` calls on one lattice share a device handle; each operand set must
+    still integrate with the parameters it was created from (`precalculate.ParamSet`)."""
+    from simetuc_b200 import odesolver
+    cte1 = configs.yb_tm_cte(N_uc=5, S_conc=20.0, A_conc=2.0, power_dens=1e6)
+    cte1['lattice_seed'] = 11
+    cte2 = configs.yb_tm_cte(N_uc=5, S_conc=20.0, A_conc=2.0, power_dens=1e9)
+    cte2['lattice_seed'] = 11
+    t = np.linspace(0, 1e-6, 5)
+
+    def pulse(op):
+        return odesolver.solve_pulse(t, op[1].astype(float), *op[4:12], rtol=1e-8, atol=1e-15)
+
+    op1 = precalculate.setup_microscopic_eqs(cte1)
+    y1_alone = pulse(op1)
+    op2 = precalculate.setup_microscopic_eqs(cte2)          # same lattice: same device handle
+    assert op1[6].stb[0] is op2[6].stb[0]
+    y2 = pulse(op2)
+    y1_again = pulse(op1)                                    # must not pick up cte2's power
+    assert np.array_equal(y1_again, y1_alone)
+    assert np.abs(y2 - y1_alone).max() > 1e-6
+
+
+def test_batch_reports_failed_solves(caplog):
+    """A solve that cannot reach the end inside a batched sweep is reported like the reference
+    reports it (`odesolver.py:129-134`), and a relaxation whose pulse failed is not returned as data
+    (ADVICE r1)."""
+    import logging
+    from simetuc_b200.engine import RateSystem
+    cte = configs.yb_tm_cte(N_uc=5, S_conc=20.0, A_conc=2.0, power_dens=1e7)
+    cte['lattice_seed'] = 12
+    sim = Simulations(cte)
+    lat = precalculate.get_lattice(cte)
+    orig = RateSystem.integrate_dynamics
+
+    def starved(self, t_pulse, t_sol, y0, **kw):
+        kw['nsteps'] = 2                                     # far too few steps between two output times
+        return orig(self, t_pulse, t_sol, y0, **kw)
+
+    RateSystem.integrate_dynamics = starved
+    try:
+        with caplog.at_level(logging.WARNING):
+            sols, _, _, stats = sim._solve_batch(lat, [cte], 0, dynamics=True, keep_y=False)
+    finally:
+        RateSystem.integrate_dynamics = orig
+    assert stats[0]['pulse']['status'] == 1 or stats[0]['relax']['status'] == 1
+    assert any('increase "nsteps"' in r.getMessage() for r in caplog.records)
+    if stats[0]['pulse']['status'] != 0:
+        assert np.all(np.isnan(sols[0][2]))
+
+
+def test_batch_rejects_differing_cooperative_strengths():
+    cte = configs.test_cte()
+    cte['lattice'] = dict(cte['lattice'])
+    cte['lattice'].update(N_uc=4, S_conc=20.0, A_conc=5.0)
+    cte['lattice_seed'] = 13
+    import copy
+    other = copy.deepcopy(cte)
+    other['energy_transfer']['coop1'].strength = 1e10
+    sim = Simulations(cte)
+    lat = precalculate.get_lattice(cte)
+    with pytest.raises(ValueError, match='cooperative'):
+        sim._solve_batch(lat, [cte, other], 0, dynamics=True)
+
+
+@pytest.mark.parametrize('env', [{'STB_CL_OPTS': '0'}, {'STB_CL_OPTS': '3'}, {'STB_CL_V': '2'},
+                                 {'STB_QUADS': '0'}, {'STB_CLUSTER': '0'}])
+def test_integrator_variants_agree(monkeypatch, env):
+    """Every option set of the integrators (no Newton start / no lagged inverses, no quad blocks, the
+    ion-major cluster kernel, the grid integrator) is another path to the same solution."""
+    import bench
+    cte = bench.make_cte(1e9)
+    t_pulse, t_sol = bench.t_grids(cte)
+    res = []
+    for variant in ({}, env):
+        for k, v in variant.items():
+            monkeypatch.setenv(k, v)
+        lat = lattice.generate(cte, seed=2000)
+        system = precalculate.build_system(cte, lat, n_sys=1)
+        _, _, pop = system.ground_states()
+        _, y, avg, st_p, st = system.integrate_dynamics(t_pulse, t_sol[::10], pop.astype(float), rtol=1e-8,
+                                                        atol=1e-15, want_y=True)
+        assert st_p[0]['status'] == 0 and st[0]['status'] == 0
+        res.append(y[0])
+        system.close()
+    assert np.max(np.abs(res[1] - res[0]) / (1e-4 * np.abs(res[0]) + 1e-12)) <= 1.0
