@@ -216,6 +216,11 @@ int stb_objective(stb_system* sys, int32_t n, double* errors);
  * (:1412-1417) - give every handle its share, so that the launches are co-resident and the
  * integrator is chosen for throughput of the whole sweep rather than for the latency of one solve. */
 int stb_set_option(stb_system* sys, const char* name, double value);
+/* Read-only properties of a handle: "sm_budget"; "quad" (1: the sensitizers are stored in quads of
+ * strongly coupled ions for the block preconditioner - an internal order, every result is in the
+ * reference's order); "cell_lists" (1: the d_max pair lists were built with cell lists instead of the
+ * O(n^2) scan - the feature settings.py:35 parses and lattice.py:301-374 never applies). */
+int stb_get_option(const stb_system* sys, const char* name, double* value);
 /* Device time (ms, CUDA events) of the pulse and of the relaxation kernel of the last
  * stb_integrate_dynamics[_dev] call. */
 int stb_last_timing_dynamics(const stb_system* sys, float* ms_pulse, float* ms_relax);

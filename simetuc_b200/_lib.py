@@ -33,7 +33,7 @@ EXPORTS = ['stb_last_error', 'stb_device_count', 'stb_describe', 'stb_system_cre
            'stb_system_destroy', 'stb_system_info', 'stb_ground_states', 'stb_set_batch',
            'stb_set_blocks', 'stb_set_strengths', 'stb_num_interactions',
            'stb_export_interactions', 'stb_rhs', 'stb_jv', 'stb_rhs_dev', 'stb_jv_dev',
-           'stb_to_planes', 'stb_from_planes', 'stb_integrate', 'stb_integrate_dev', 'stb_integrate_dynamics', 'stb_integrate_dynamics_dev', 'stb_last_timing_dynamics', 'stb_set_option', 'stb_set_experiment', 'stb_objective', 'stb_stream', 'stb_launch_count', 'stb_release_cached_memory',
+           'stb_to_planes', 'stb_from_planes', 'stb_integrate', 'stb_integrate_dev', 'stb_integrate_dynamics', 'stb_integrate_dynamics_dev', 'stb_last_timing_dynamics', 'stb_set_option', 'stb_get_option', 'stb_set_experiment', 'stb_objective', 'stb_stream', 'stb_launch_count', 'stb_release_cached_memory',
            'stb_set_coop', 'stb_coop_count', 'stb_export_coop',
            'stb_last_timing', 'stb_last_profile']
 
@@ -88,6 +88,7 @@ def load():
                                   C.c_double, C.c_double, C.c_int64, P, P, P]
     lib.stb_integrate_dev.argtypes = lib.stb_integrate.argtypes
     lib.stb_set_option.argtypes = [P, C.c_char_p, C.c_double]
+    lib.stb_get_option.argtypes = [P, C.c_char_p, C.POINTER(C.c_double)]
     lib.stb_set_experiment.argtypes = [P, C.c_int32, C.c_int64, P, P, C.c_double]
     lib.stb_objective.argtypes = [P, C.c_int32, P]
     lib.stb_last_timing_dynamics.argtypes = [P, C.POINTER(C.c_float), C.POINTER(C.c_float)]

@@ -317,6 +317,7 @@ struct stb_system {
     int64_t last_launches = 0;
     int sm_count = 148;
     int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
+    bool built_with_cells = false;   // the cutoff lists came from the cell-list build
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
     enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR,
@@ -528,6 +529,60 @@ static int build_tables(stb_system* S, DevLattice& L) {
 // inside the library changes; every result is reported in the reference's order.
 // Returns false (identity order) for lattices it does not apply to.  out[r] = type-local index of
 // the r-th sensitizer in lattice order.
+// Cell grid for the cell-list pair build: cells no thinner than d_max along every axis (fractional
+// coordinates of the periodic supercell, or the bounding box of an open lattice).  Returns false when
+// the grid would be too coarse to pay off (a periodic axis needs >= 3 cells so that the 27
+// neighbours are distinct).  cell_ions keeps the ions of a cell in ascending order.
+static bool build_cell_grid(int n, const double* pos, const double* cell, const double* inv, double d_max,
+                            int nc[3], std::vector<int>& cell_start, std::vector<int>& cell_ions,
+                            std::vector<int>& ion_cell) {
+    double lo[3] = {1e300, 1e300, 1e300}, ext[3] = {0, 0, 0};
+    if (cell) {
+        for (int c = 0; c < 3; ++c) {
+            // height of the supercell along fractional axis c = 1 / |column c of inv|
+            const double nrm = std::sqrt(inv[c] * inv[c] + inv[3 + c] * inv[3 + c] + inv[6 + c] * inv[6 + c]);
+            nc[c] = (int)std::floor(1.0 / (nrm * d_max * (1.0 + 1e-9)));      // cells a hair wider than d_max
+            if (nc[c] < 3) return false;
+        }
+    } else {
+        double hi[3] = {-1e300, -1e300, -1e300};
+        for (int q = 0; q < n; ++q)
+            for (int c = 0; c < 3; ++c) {
+                lo[c] = std::min(lo[c], pos[3 * q + c]);
+                hi[c] = std::max(hi[c], pos[3 * q + c]);
+            }
+        for (int c = 0; c < 3; ++c) {
+            ext[c] = std::max(hi[c] - lo[c], 1e-9);
+            nc[c] = std::max(1, (int)std::floor(ext[c] / (d_max * (1.0 + 1e-9))));
+        }
+        if ((long long)nc[0] * nc[1] * nc[2] < 27) return false;
+    }
+    for (int c = 0; c < 3; ++c) nc[c] = std::min(nc[c], 256);
+    const int n_cells = nc[0] * nc[1] * nc[2];
+    ion_cell.resize(n);
+    cell_start.assign(n_cells + 1, 0);
+    for (int q = 0; q < n; ++q) {
+        int idx[3];
+        for (int c = 0; c < 3; ++c) {
+            double f;
+            if (cell) {
+                f = pos[3 * q] * inv[c] + pos[3 * q + 1] * inv[3 + c] + pos[3 * q + 2] * inv[6 + c];
+                f -= std::floor(f);
+            } else {
+                f = (pos[3 * q + c] - lo[c]) / ext[c];
+            }
+            idx[c] = std::min(nc[c] - 1, std::max(0, (int)(f * nc[c])));
+        }
+        ion_cell[q] = (idx[0] * nc[1] + idx[1]) * nc[2] + idx[2];
+        cell_start[ion_cell[q] + 1]++;
+    }
+    for (int c = 0; c < n_cells; ++c) cell_start[c + 1] += cell_start[c];
+    cell_ions.resize(n);
+    std::vector<int> fill(cell_start.begin(), cell_start.end() - 1);
+    for (int q = 0; q < n; ++q) cell_ions[fill[ion_cell[q]]++] = q;      // ascending inside a cell
+    return true;
+}
+
 static bool group_sensitizers(int n, const uint8_t* type, int sS, const double* dist, const double* pos,
                               const double* cell, std::vector<int>& out) {
     out.clear();
@@ -743,11 +798,41 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
             if (!invert3(G.cell, G.inv)) { fail(STB_EINVAL, "singular cell"); return die(); }
         }
     }
+    // ---- cutoff lattices given by positions: cell lists (stb_build.cuh) ---------------------------
+    CellGrid CG;
+    memset(&CG, 0, sizeof(CG));
+    bool use_cells = false;
+    int *d_cell_start = nullptr, *d_cell_ions = nullptr, *d_ion_cell = nullptr;
+    {
+        std::vector<int> cell_start, cell_ions, ion_cell;
+        int nc[3] = {1, 1, 1};
+        bool want = d_max > 0.0 && positions != nullptr;
+        if (const char* env = getenv("STB_CELLS")) want = want && atoi(env) != 0;
+        if (want && build_cell_grid(n, positions, cell ? G.cell : nullptr, cell ? G.inv : nullptr, d_max, nc,
+                                    cell_start, cell_ions, ion_cell)) {
+            CKS(upload(S->stream, &d_cell_start, cell_start));
+            CKS(upload(S->stream, &d_cell_ions, cell_ions));
+            CKS(upload(S->stream, &d_ion_cell, ion_cell));
+            CG.cell_start = d_cell_start;
+            CG.cell_ions = d_cell_ions;
+            CG.ion_cell = d_ion_cell;
+            for (int c = 0; c < 3; ++c) CG.nc[c] = nc[c];
+            CG.periodic = G.periodic;
+            use_cells = true;
+        }
+    }
+    auto free_cells = [&]() {
+        pool_free(d_cell_start);
+        pool_free(d_cell_ions);
+        pool_free(d_ion_cell);
+        d_cell_start = d_cell_ions = d_ion_cell = nullptr;
+    };
     // ---- pass 1: row lengths ---------------------------------------------------------------------
     CKS(pool_malloc((void**)&S->d_len, sizeof(int) * 2 * (size_t)n));
     int blocks = std::min((n + 7) / 8, S->sm_count * 8);
     g_launches++;
-    k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
+    if (use_cells) k_count_pairs_cells<<<blocks, 256, 0, S->stream>>>(G, CG, S->d_type, S->d_len);
+    else k_count_pairs<<<blocks, 256, 0, S->stream>>>(G, S->d_type, S->d_len);
     CKS(cudaGetLastError());
     S->len.resize(2 * (size_t)n);
     CKS(cudaMemcpyAsync(S->len.data(), S->d_len, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, S->stream));
@@ -860,10 +945,13 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
         for (int U = 0; U < 2; ++U)
             if (L.blk[T][U].n_slots == 0) FA.col[T][U] = nullptr;
     g_launches++;
-    k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
+    if (use_cells) k_fill_pairs_cells<<<std::min((n + 3) / 4, S->sm_count * 16), 128, 0, S->stream>>>(FA, CG);
+    else k_fill_pairs<<<blocks, 256, 0, S->stream>>>(FA);
     CKS(cudaGetLastError());
     CKS(cudaStreamSynchronize(S->stream));
     }
+    free_cells();
+    S->built_with_cells = use_cells;
     pool_free(d_geo);
     d_geo = nullptr;
     L.blk_stride = 2 * (S->s[0] * S->s[0] + S->s[1] * S->s[1]);
@@ -2008,6 +2096,15 @@ extern "C" int stb_set_option(stb_system* S, const char* name, double value) {
         return STB_OK;
     }
     return fail(STB_EINVAL, std::string("unknown option ") + name);
+}
+
+extern "C" int stb_get_option(const stb_system* S, const char* name, double* value) {
+    if (!S || !name || !value) return fail(STB_EINVAL, "null argument");
+    if (!strcmp(name, "sm_budget")) *value = S->sm_budget;
+    else if (!strcmp(name, "quad")) *value = S->hL.quad;
+    else if (!strcmp(name, "cell_lists")) *value = S->built_with_cells ? 1.0 : 0.0;
+    else return fail(STB_EINVAL, std::string("unknown option ") + name);
+    return STB_OK;
 }
 
 extern "C" int stb_last_timing_dynamics(const stb_system* S, float* ms_pulse, float* ms_relax) {

@@ -116,6 +116,142 @@ __global__ void k_fill_pairs(FillArgs A) {
     }
 }
 
+// ---- cell lists for cutoff lattices (d_max > 0, positions given) -----------------------------------
+// The supercell (or the bounding box of an open lattice) is cut into nc[0] x nc[1] x nc[2] cells
+// no thinner than d_max (in fractional coordinates), so every partner within the cutoff sits in one
+// of the 27 cells around an ion's own cell: the build is O(n * partners) instead of the O(n^2) scan
+// of k_count_pairs / k_fill_pairs.  The distances come from the same geo_dist (bit-identical rates)
+// and the partners of a row are written in ascending lattice order (lattice.py:335-371) like the
+// scan does: candidates are collected in shared memory and placed by rank.
+struct CellGrid {
+    const int* cell_start;   // [n_cells + 1]
+    const int* cell_ions;    // [n] ions of cell c at cell_start[c] .. cell_start[c + 1], ascending
+    const int* ion_cell;     // [n] cell of every ion
+    int nc[3];
+    int periodic;
+};
+
+// calls f(k, valid) for the candidate partners of ion q, 32 at a time (uniform trip count per warp)
+template <class F>
+__device__ __forceinline__ void cells_for_each(const CellGrid& C, int q, int lane, F&& f) {
+    const int c = C.ion_cell[q];
+    const int cz = c % C.nc[2], cy = (c / C.nc[2]) % C.nc[1], cx = c / (C.nc[2] * C.nc[1]);
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dz = -1; dz <= 1; ++dz) {
+                int x = cx + dx, y = cy + dy, z = cz + dz;
+                if (C.periodic) {
+                    x = (x + C.nc[0]) % C.nc[0];
+                    y = (y + C.nc[1]) % C.nc[1];
+                    z = (z + C.nc[2]) % C.nc[2];
+                } else if (x < 0 || y < 0 || z < 0 || x >= C.nc[0] || y >= C.nc[1] || z >= C.nc[2]) {
+                    continue;
+                }
+                const int cc = (x * C.nc[1] + y) * C.nc[2] + z;
+                const int s0 = C.cell_start[cc], s1 = C.cell_start[cc + 1];
+                for (int s = s0; s < s1; s += 32) {
+                    const bool valid = s + lane < s1;
+                    f(valid ? C.cell_ions[s + lane] : 0, valid);
+                }
+            }
+}
+
+__global__ void k_count_pairs_cells(Geo G, CellGrid C, const uint8_t* type, int* len /*[2][n]*/) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int q = warp; q < G.n; q += nwarps) {
+        int c0 = 0, c1 = 0;
+        cells_for_each(C, q, lane, [&](int k, bool valid) {
+            const bool ok = valid && geo_pair(G, geo_dist(G, q, k));
+            const int U = valid ? (type[k] != 0) : 0;
+            c0 += __popc(__ballot_sync(0xffffffffu, ok && U == 0));
+            c1 += __popc(__ballot_sync(0xffffffffu, ok && U == 1));
+        });
+        if (lane == 0) { len[q] = c0; len[G.n + q] = c1; }
+    }
+}
+
+#define STB_CELL_CAP 1024     // accepted partners of one row kept in shared memory (per warp)
+
+__global__ void __launch_bounds__(128) k_fill_pairs_cells(FillArgs A, CellGrid C) {
+    __shared__ unsigned ks[4][STB_CELL_CAP];      // ion index | partner type << 31
+    __shared__ double ds[4][STB_CELL_CAP];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const Geo& G = A.G;
+    for (int q = warp; q < G.n; q += nwarps) {
+        const int T = A.type[q] != 0;
+        const int ql = A.local_idx[q];
+        const int slice = ql / A.R, rl = ql % A.R;
+        int cnt = 0;
+        bool overflow = false;
+        cells_for_each(C, q, lane, [&](int k, bool valid) {
+            double d = 0.0;
+            bool ok = false;
+            if (valid) {
+                d = geo_dist(G, q, k);
+                ok = geo_pair(G, d);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (ok && pos < STB_CELL_CAP) {
+                ks[wib][pos] = (unsigned)k | (A.type[k] != 0 ? 0x80000000u : 0u);
+                ds[wib][pos] = d;
+            }
+            cnt += __popc(m);
+            if (cnt > STB_CELL_CAP) overflow = true;
+        });
+        __syncwarp();
+        if (overflow) {
+            // a row with more partners than the buffer holds: the ordered scan of k_fill_pairs
+            int e[2] = {0, 0};
+            for (int k0 = 0; k0 < G.n; k0 += 32) {
+                const int k = k0 + lane;
+                bool ok = false;
+                int U = 0;
+                double d = 0.0;
+                if (k < G.n) {
+                    d = geo_dist(G, q, k);
+                    ok = geo_pair(G, d);
+                    U = A.type[k] != 0;
+                }
+#pragma unroll
+                for (int UU = 0; UU < 2; ++UU) {
+                    const unsigned m = __ballot_sync(0xffffffffu, ok && U == UU);
+                    if (ok && U == UU && A.col[T][UU] != nullptr) {
+                        const int pos = e[UU] + __popc(m & ((1u << lane) - 1u));
+                        const int64_t line = A.line_ptr[T][UU][slice] + pos / A.lpr;
+                        const int64_t idx = line * 32 + rl * A.lpr + pos % A.lpr;
+                        A.col[T][UU][idx] = (uint32_t)A.local_idx[k];
+                        for (int mm = 0; mm < A.n_mult; ++mm) A.g[T][UU][mm][idx] = pow(d, -(double)A.mults[mm]);
+                    }
+                    e[UU] += __popc(m);
+                }
+            }
+            continue;
+        }
+        // place every accepted partner by its rank among the partners of its type (ascending ion index)
+        for (int e = lane; e < cnt; e += 32) {
+            const unsigned me = ks[wib][e];
+            const int UU = me >> 31;
+            if (A.col[T][UU] == nullptr) continue;
+            int pos = 0;
+            for (int o = 0; o < cnt; ++o) {
+                const unsigned other = ks[wib][o];
+                pos += ((other >> 31) == (unsigned)UU) && other < me;
+            }
+            const int k = (int)(me & 0x7fffffffu);
+            const double d = ds[wib][e];
+            const int64_t line = A.line_ptr[T][UU][slice] + pos / A.lpr;
+            const int64_t idx = line * 32 + rl * A.lpr + pos % A.lpr;
+            A.col[T][UU][idx] = (uint32_t)A.local_idx[k];
+            for (int mm = 0; mm < A.n_mult; ++mm) A.g[T][UU][mm][idx] = pow(d, -(double)A.mults[mm]);
+        }
+        __syncwarp();
+    }
+}
+
 struct FillDenseArgs {
     Geo G;
     const uint8_t* type;

@@ -162,6 +162,12 @@ class RateSystem:
         _lib.check(self.lib.stb_objective(self.handle, int(n), _lib.ptr(out)))
         return out
 
+    def get_option(self, name: str) -> float:
+        """`stb_get_option`: 'sm_budget', 'quad', 'cell_lists'."""
+        out = C.c_double()
+        _lib.check(self.lib.stb_get_option(self.handle, name.encode(), C.byref(out)))
+        return float(out.value)
+
     # ------------------------------------------------------------------ lattice-side outputs
     def ground_states(self):
         """`(index_S_i, index_A_j, initial_population)` as `lattice.create_ground_states`."""

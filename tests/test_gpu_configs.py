@@ -287,3 +287,26 @@ def test_coop_in_both_integrators(monkeypatch, which):
     assert parity_metric(y[0], gold['y']) <= 1.0
     # the cooperative channel matters: without it the state differs far beyond the tolerance
     assert parity_metric(gold['y_no_coop_row40'], gold['y'][40]) > 100.0
+
+
+@pytest.mark.parametrize('periodic', [True, False])
+def test_cell_list_build_equals_the_scan(monkeypatch, periodic):
+    """`d_max` lattices given by positions are built with cell lists (O(n x partners)); the pair lists,
+    their order and the rates must be bit-identical to the O(n^2) scan (`STB_CELLS=0`), for the
+    periodic hexagonal supercell and for an open (nanoparticle-like) lattice."""
+    cte = configs.yb_tm_cte(N_uc=14, S_conc=20.0, A_conc=2.0, power_dens=1e7)
+    lat = lattice.generate(cte, seed=14)
+    if not periodic:
+        lat.cell = None
+    d_max = 9.0
+    et = dict(pair_processes(cte))
+    res = {}
+    for cells in ('1', '0'):
+        monkeypatch.setenv('STB_CELLS', cells)
+        system = RateSystem(lat, et, d_max=d_max, geometry='positions')
+        assert system.get_option('cell_lists') == float(cells)
+        res[cells] = system.export_interactions() + (system.n_pairs,)
+        system.close()
+    assert res['1'][4] == res['0'][4] > 1000
+    for a, b in zip(res['1'][:4], res['0'][:4]):
+        assert np.array_equal(a, b)
