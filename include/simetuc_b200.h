@@ -215,6 +215,10 @@ int stb_objective(stb_system* sys, int32_t n, double* errors);
  * Simulations.simulate_concentration_dependence (simulations.py:1356-1372) and sample_simulation
  * (:1412-1417) - give every handle its share, so that the launches are co-resident and the
  * integrator is chosen for throughput of the whole sweep rather than for the latency of one solve. */
+/* "avg_cumulative" (0/1): stb_integrate_dynamics returns in avg_out the running trapezoid of the emission
+ * curves over t_sol - t_sol[0] instead of the curves: the pulsed steady state of
+ * DynamicsSolution.calculate_steady_state (simulations.py:579-591) for sweeps that do not keep the
+ * trajectories (the ion average commutes with the time integral). */
 int stb_set_option(stb_system* sys, const char* name, double value);
 /* Read-only properties of a handle: "sm_budget"; "quad" (1: the sensitizers are stored in quads of
  * strongly coupled ions for the block preconditioner - an internal order, every result is in the

@@ -318,6 +318,7 @@ struct stb_system {
     int sm_count = 148;
     int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
     bool built_with_cells = false;   // the cutoff lists came from the cell-list build
+    bool avg_cumulative = false;     // stb_integrate_dynamics returns the running time integral of the curves
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
     enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR,
@@ -1985,6 +1986,13 @@ static int integrate_dynamics_core(stb_system* S, int32_t first, int32_t n, int6
     CK(cudaGetLastError());
     rc = integrate_core(S, first, n, 0, n_t, ts_p, d_y0, rtol, atol, nsteps, d_ys, d_avg, stats_relax, true);
     if (rc) return rc;
+    if (S->avg_cumulative && d_avg) {
+        if (!S->exp_t.empty())
+            return fail(STB_ESTATE, "avg_cumulative and the device objective (stb_set_experiment) exclude each other");
+        g_launches++;
+        k_cumtrapz<<<(unsigned)((n * kinds + 127) / 128), 128, 0, S->stream>>>(d_avg, ts_p, n_t, kinds, n);
+        CK(cudaGetLastError());
+    }
     tm.mark("relax");
     S->last_avg = d_avg;
     S->last_ts = ts_p;
@@ -2093,6 +2101,10 @@ extern "C" int stb_set_option(stb_system* S, const char* name, double value) {
     if (!S || !name) return fail(STB_EINVAL, "null argument");
     if (!strcmp(name, "sm_budget")) {
         S->sm_budget = (int)std::max(1.0, std::min((double)S->sm_count, value));
+        return STB_OK;
+    }
+    if (!strcmp(name, "avg_cumulative")) {
+        S->avg_cumulative = value != 0.0;
         return STB_OK;
     }
     return fail(STB_EINVAL, std::string("unknown option ") + name);

@@ -31,6 +31,10 @@
 #define CL_KRED (CL_KRYLOV + 4)
 #define CL_MAXRG 256       // row groups per CTA
 #define CL_MAXG 8
+#ifndef CL_STREAM_UNROLL
+#define CL_STREAM_UNROLL 4     // loads in flight per lane when the pair rows are streamed from L2
+#endif
+constexpr int kClStreamUnroll = CL_STREAM_UNROLL;
 #ifndef CL_PIECE_FIX
 #define CL_PIECE_FIX 6     // fixed cost of a pair-pass piece, in steps
 #endif
@@ -243,7 +247,7 @@ __device__ __forceinline__ void cl_piece(int g_off, const double* gb, int64_t pi
     } else {
         const int kmax = nkp - 1;
         const double* gr = gb + (int64_t)row * pitch;
-#pragma unroll 4
+#pragma unroll (kClStreamUnroll)
         for (int st = s0; st < s1; ++st) {
             const int kp = st * 4 + kk;
             const double2 g = cl_ld_nc2(gr + 2 * kp);

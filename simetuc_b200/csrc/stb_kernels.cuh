@@ -225,6 +225,25 @@ __global__ void __launch_bounds__(256) k_coop_add(const DevLattice* Lp, const do
 }
 
 
+// Pulsed steady state of a batch: running trapezoid of every emission curve over the solution times,
+// in place (DynamicsSolution.calculate_steady_state applied to the averages, simulations.py:579-591;
+// the ion average commutes with the time integral).  One thread per (system, state kind).
+__global__ void k_cumtrapz(double* avg /*[n][n_t][kinds]*/, const double* t_sol, int64_t n_t, int kinds, int n) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n * kinds) return;
+    const int sys = (int)(i / kinds), kind = (int)(i % kinds);
+    double* a = avg + (int64_t)sys * n_t * kinds + kind;
+    double prev = a[0], run = 0.0;
+    a[0] = 0.0;
+    for (int64_t k = 1; k < n_t; ++k) {
+        const double cur = a[k * kinds];
+        // same operation order as the host mirror: cumsum(0.5 * (y[k] + y[k-1]) * (t[k] - t[k-1]))
+        run += 0.5 * (cur + prev) * ((t_sol[k] - t_sol[0]) - (t_sol[k - 1] - t_sol[0]));
+        a[k * kinds] = run;
+        prev = cur;
+    }
+}
+
 // Optimisation objective on the device: deviation of every emission curve from its experimental
 // decay curve, exactly as DynamicsSolution._get_background / _interpolate_sim_data / _calc_errors
 // compute it on the host (simulations.py:425-527):

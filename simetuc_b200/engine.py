@@ -292,7 +292,7 @@ class RateSystem:
 
     def integrate_dynamics(self, t_pulse, t_sol, y0, rtol: float = 1e-3, atol: float = 1e-15,
                            nsteps: int = 1000, first: int = 0, want_y: bool = True,
-                           want_avg: bool = True, want_pulse: bool = False):
+                           want_avg: bool = True, want_pulse: bool = False, cumulative: bool = False):
         """Pulse then relaxation of systems `first..first+n` in one C-ABI call
         (`stb_integrate_dynamics`): the relaxation starts on the device from the last pulse row.
         Returns `(y_pulse [n, n_tp, N] | None, y [n, n_t, N] | None, avg [n, n_t, sS+sA] | None,
@@ -305,6 +305,8 @@ class RateSystem:
         avg = np.empty((n, len(t_sol), self.sS + self.sA)) if want_avg else None
         st_p = (_lib.StbStats * n)()
         st_r = (_lib.StbStats * n)()
+        # cumulative: `avg` is the running time integral of the emission curves (pulsed steady state)
+        self.set_option('avg_cumulative', 1.0 if cumulative else 0.0)
         _lib.check(self.lib.stb_integrate_dynamics(
             self.handle, first, n, len(t_pulse), _lib.ptr(t_pulse), len(t_sol), _lib.ptr(t_sol),
             _lib.ptr(y0), float(rtol), float(atol), int(nsteps), int(nsteps), _lib.ptr(y_p),

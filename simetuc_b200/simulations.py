@@ -108,7 +108,16 @@ class Solution:
     @cached_property
     def list_avg_data(self) -> List[np.array]:
         '''List of average populations for each state in the solution'''
+        matrix = getattr(self, '_avg_matrix', None)
+        if matrix is not None:
+            return [np.ascontiguousarray(col) for col in matrix.T]
         return self._calculate_avg_populations()
+
+    def set_avg_matrix(self, avg: np.ndarray) -> None:
+        '''Like `set_avg_data`, but the per-state curves are only split out of the `[n_t, sS+sA]`
+        matrix when `list_avg_data` is read (a sweep over many systems mostly needs the last row).'''
+        self._avg_matrix = avg
+        self.__dict__.pop('list_avg_data', None)
 
     def set_avg_data(self, avg: np.ndarray) -> None:
         '''Use the per-state averages computed on the device ([n_t, sS+sA]) instead of the host
@@ -160,7 +169,9 @@ class SteadyStateSolution(Solution):
         st, lat = self.cte['states'], self.cte['lattice']
         conc = np.array([lat['S_conc']] * st['sensitizer_states'] +
                         [lat['A_conc']] * st['activator_states'], dtype=np.float64)
-        return np.array([curve[-1] for curve in self.list_avg_data]) * conc
+        matrix = getattr(self, '_avg_matrix', None)
+        last = matrix[-1] if matrix is not None else np.array([curve[-1] for curve in self.list_avg_data])
+        return last * conc
 
     @cached_property
     def steady_state_populations(self) -> np.ndarray:
@@ -482,7 +493,8 @@ class Simulations:
     def _solve_batch(self, lat, ctes: List[Any], device: int, dynamics: bool,
                      strengths: Optional[np.ndarray] = None, keep_y: bool = True,
                      average: bool = False, gpu_busy: Optional[threading.Event] = None,
-                     sm_budget: Optional[int] = None, experiments: Optional[list] = None):
+                     sm_budget: Optional[int] = None, experiments: Optional[list] = None,
+                     steady: bool = False):
         """Integrate `len(ctes)` systems that share `lat` in one batch on `device`.
         Each cte supplies its own absorption / decay blocks (and optionally ET strengths).
         Returns a list of `(t_sol, y_sol | None, avg)` per system plus the solver statistics.
@@ -491,7 +503,9 @@ class Simulations:
         device buffers are reused by the next sweep on this lattice); pulse and relaxation run
         in one C-ABI call.  `experiments` (dynamics only): one experimental curve or None per
         state kind; the per-state deviations are then evaluated on the device and returned as
-        `stats[k]['errors']`, and the curves are not copied back (`avg` is None).
+        `stats[k]['errors']`, and the curves are not copied back (`avg` is None).  `steady`
+        (dynamics only): `avg` is the running time integral of the emission curves, computed on the
+        device (the pulsed steady state of `DynamicsSolution.calculate_steady_state`).
         Systems whose solve did not reach the end are reported with the
         reference's warnings (`odesolver.py:129-134`); a relaxation that would start from an
         unreached pulse row is blanked (NaN) instead of returned as data."""
@@ -540,7 +554,7 @@ class Simulations:
                         system.set_experiment(kind, exp)
                 _, y, avg, st_p, st = system.integrate_dynamics(
                     t_pulse, t_sol, y0, rtol=rtol, atol=atol, want_y=keep_y,
-                    want_avg=experiments is None)
+                    want_avg=experiments is None, cumulative=steady and experiments is None)
                 if experiments is not None:
                     errors = system.objective(n)
                 t_out = t_sol - t_sol[0]
@@ -574,7 +588,7 @@ class Simulations:
     def _sweep_same_lattice(self, ctes: List[Any], dynamics: bool, keep_y: bool = True,
                             strengths: Optional[np.ndarray] = None, average: bool = False,
                             gpu_busy: Optional[threading.Event] = None,
-                            experiments: Optional[list] = None):
+                            experiments: Optional[list] = None, steady: bool = False):
         """Systems sharing one lattice, dealt round-robin over `self.devices`."""
         gen_lattice = self.cte.get('gen_lattice', False)
         if average:
@@ -585,7 +599,7 @@ class Simulations:
         shards = [list(range(d, len(ctes), n_dev)) for d in range(n_dev)]
         jobs = [(lambda d=d, ids=ids: self._solve_batch(
             lat, [ctes[i] for i in ids], self.devices[d], dynamics, keep_y=keep_y, average=average,
-            gpu_busy=gpu_busy, experiments=experiments,
+            gpu_busy=gpu_busy, experiments=experiments, steady=steady,
             strengths=None if strengths is None else strengths[ids])) for d, ids in enumerate(shards)]
         results = _run_on_devices(jobs, n_dev)
         out = [None] * len(ctes)
@@ -618,8 +632,12 @@ class Simulations:
                 for exc in exc_list:
                     exc.power_dens = power_dens
             light.append(cte)
+        # keep_y=False on a pulsed source: the ion average commutes with the time integral, so the area
+        # under the emission curves (running trapezoid, computed on the device) is the steady state
+        # without moving the [n_t, N] trajectories to the host
+        on_device_steady = pulsed and not keep_y
         sols, index_S_i, index_A_j, lat, stats = self._sweep_same_lattice(
-            light, dynamics=pulsed, keep_y=keep_y, average=average)
+            light, dynamics=pulsed, keep_y=keep_y, average=average, steady=on_device_steady)
         # per-solution settings (the reference deep-copies everything, `simulations.py:1290`): only
         # what differs between the solutions or is written per solution is private - the
         # excitations (made for the batch above), the state and ion counts; the other sections are
@@ -629,17 +647,6 @@ class Simulations:
             cte['states'] = copy.copy(self.cte['states'])
             ctes.append(cte)
         solutions = []
-        steady_all = None
-        if pulsed and not keep_y:
-            # keep_y=False: the ion average commutes with the time integral, so the area under the
-            # device-computed emission curves gives the same steady state without moving the
-            # [n_t, N] trajectories to the host; one pass over the curves of all the systems
-            # time along the contiguous axis: [n, kinds, n_t]
-            curves = np.ascontiguousarray(np.stack([avg for _, _, avg in sols]).transpose(0, 2, 1))
-            t_rel = sols[0][0]
-            steady_all = np.zeros_like(curves)
-            np.cumsum(0.5 * (curves[:, :, 1:] + curves[:, :, :-1]) * np.diff(t_rel), axis=2,
-                      out=steady_all[:, :, 1:])
         ions = {'total': lat.n_ions, 'sensitizers': lat.n_S, 'activators': lat.n_A}
         for k, (cte, (t_sol, y_sol, avg), st) in enumerate(zip(ctes, sols, stats)):
             cte['ions'] = dict(ions)
@@ -648,10 +655,9 @@ class Simulations:
                 sol = DynamicsSolution(t_sol, y_sol, index_S_i, index_A_j, cte,
                                        average=average, own_cte=True).calculate_steady_state()
             elif pulsed:
-                avg_steady = steady_all[k].T            # [n_t, kinds] view; rows of steady_all[k] = curves
-                sol = SteadyStateSolution(t_sol, avg_steady, index_S_i, index_A_j, cte, average=average,
+                sol = SteadyStateSolution(t_sol, avg, index_S_i, index_A_j, cte, average=average,
                                           own_cte=True)
-                sol.__dict__['list_avg_data'] = list(steady_all[k])
+                sol.set_avg_matrix(avg)                 # `avg` is the steady-state (integrated) curves
             else:
                 sol = SteadyStateSolution(t_sol, y_sol if y_sol is not None else avg,
                                           index_S_i, index_A_j, cte, average=average, own_cte=True)
