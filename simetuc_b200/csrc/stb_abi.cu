@@ -1709,7 +1709,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
             const double den = unit[k] == 'p' ? nrhs + njv : unit[k] == 'n' ? nrhs : unit[k] == 'k' ? njv : steps;
             fprintf(stderr, " %s=%.0f/%c(%.0f%%)", names[k], pr[k] / den, unit[k], 100.0 * pr[k] / std::max(tot, 1.0));
         }
-        fprintf(stderr, " | extra probes [20..23] per Krylov it: %.0f %.0f %.0f %.0f", pr[20] / njv, pr[21] / njv, pr[22] / njv, pr[23] / njv);
+        if (plan.v2)
+            fprintf(stderr, " | ion-major kernel, per Krylov it: products=%.0f butterfly=%.0f wait=%.0f orth_sums=%.0f", pr[20] / njv, pr[21] / njv, pr[22] / njv, pr[23] / njv);
         fprintf(stderr, "\n");
     }
     return STB_OK;

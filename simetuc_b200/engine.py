@@ -6,7 +6,7 @@ solve_relax` drive; the reference has no such object because it rebuilds every m
 every call (`simulations.py:1118,1214`).
 """
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import scipy.sparse as sp

@@ -13,7 +13,6 @@ index_S_i, index_A_j, cte, list_avg_data, steady_state_populations, power_dens,
 concentration, errors`); plotting and HDF5 persistence are outside this path (results are
 saved as `.npz`).
 """
-import concurrent.futures
 import copy
 import csv
 import functools
@@ -26,7 +25,6 @@ from typing import Any, Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import lattice as lattice_mod
 from . import odesolver, precalculate
 from .util import Conc, disable_loggers
 
