@@ -323,7 +323,7 @@ struct ClConst {           // per-CTA constants that are indexed dynamically: sh
     int gres_on[2][2];
     int goff[2][2];            // resident blocks: offset into the dynamic shared array
     int rgpos[2];              // work-list position (steps) of the first row group of a type
-    double GAMMA[6], ALPHA[6], ERRC[6];
+    double GAMMA[6], ALPHA[6], ERRC[6], RALPHA[6];
     double Rs[36], Us[36];
 };
 
@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
         for (int k = 0; k <= 5; ++k) {
             ALPHA[k] = (1.0 - KAPPA[k]) * GAMMA[k];
             ERRC[k] = KAPPA[k] * GAMMA[k] + 1.0 / (k + 1);
+            K.RALPHA[k] = k ? 1.0 / ALPHA[k] : 0.0;
         }
     }
     __syncthreads();
@@ -987,6 +988,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     };
 
     const double sqrtN = sqrt((double)N);
+    const double inv_N = 1.0 / (double)N;
+    const double tol_lin = STB_LIN_RMS * sqrtN;
     const double rtol = A.rtol, atol = A.atol;
 
     // =================================== systems ============================================
@@ -1088,32 +1091,44 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             __syncthreads();
             CLPROF(14)
             if (C.status != 0 || k_out_l >= A.n_t) break;
-            if (tid == 0) {
-                C.flag = 0;
-                const double t_new = C.t + C.h;
-                if (t_new > C.t_end && (t_new - C.t_end) > 1e-14 * fabs(C.t_end)) {
-                    const double factor = (C.t_end - C.t) / C.h;
-                    cl_compute_RU(C.order, factor, C.RU, K.Rs, K.Us);
-                    C.h = C.t_end - C.t;
-                    C.n_equal = 0;
-                    C.flag = 1;
-                    C.gfac *= cl_ipow(factor, C.order + 1);
-                } else if (t_new > C.t_end) {
-                    C.h = C.t_end - C.t;
-                }
-                const double eps_t = 10.0 * fabs(nextafter(C.t, 1e300) - C.t);
-                if (C.h < eps_t) C.status = 2;
-                if (C.steps_since_out >= A.nsteps) C.status = 1;
-                C.c = C.h / ALPHA[C.order];
-                C.pc_refresh = !lagpc || C.pc_age < 0 || C.pc_age >= A.pc_maxage ||
-                               fabs(C.c / C.pc_c - 1.0) > A.pc_drift;
-            }
-            __syncthreads();
-            if (C.status != 0) break;
-            if (C.flag) apply_change_D(C.order);
+            // scalar prologue, evaluated by every thread from the same shared values (no serial section,
+            // no second barrier on the common path)
+            double h = C.h;
+            const double t_cur = C.t, t_end = C.t_end;
             const int order = C.order;
-            const double c = C.c;
-            const bool pc_ref = C.pc_refresh != 0;
+            {
+                const double t_try = t_cur + h;
+                if (t_try > t_end && (t_try - t_end) > 1e-14 * fabs(t_end)) {
+                    // the last step is shortened to land on t_end (rare)
+                    __syncthreads();
+                    if (tid == 0) {
+                        const double factor = (t_end - t_cur) / h;
+                        cl_compute_RU(order, factor, C.RU, K.Rs, K.Us);
+                        C.h = t_end - t_cur;
+                        C.n_equal = 0;
+                        C.gfac *= cl_ipow(factor, order + 1);
+                    }
+                    __syncthreads();
+                    apply_change_D(order);
+                    h = t_end - t_cur;
+                } else if (t_try > t_end) {
+                    h = t_end - t_cur;      // round-off sized overshoot: land exactly on t_end
+                }
+            }
+            {
+                int st_now = 0;
+                if (h < 10.0 * 2.220446049250313e-16 * fabs(t_cur)) st_now = 2;
+                if (C.steps_since_out >= A.nsteps) st_now = 1;
+                if (st_now) {
+                    __syncthreads();
+                    if (tid == 0) C.status = st_now;
+                    break;
+                }
+            }
+            const double ralpha = K.RALPHA[order];
+            const double c = h * ralpha;
+            const bool pc_ref = !lagpc || C.pc_age < 0 || C.pc_age >= A.pc_maxage ||
+                                fabs(c - C.pc_c) > A.pc_drift * fabs(C.pc_c);
             const double gf = guess ? C.gfac : 0.0;
             bool first_newton = true;
             // predictor, scale, psi; d = 0; the predicted state goes to every CTA of the cluster
@@ -1125,7 +1140,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     if (j >= 1) ps = fma(GAMMA[j], dj, ps);
                 }
                 scl[k] = atol + rtol * fabs(yp);
-                psi[k] = ps / ALPHA[order];
+                psi[k] = ps * ralpha;
                 // Newton start: predictor + the previous correction (D[order + 1]) rescaled to this step
                 const double d0 = gf != 0.0 ? gf * D[(order + 1) * PO + k] : 0.0;
                 dd[k] = d0;
@@ -1163,29 +1178,34 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     reduce_vals(2, v2);
                     CLPROF(7)
                 }
+                // beta and the start of the linear solve are evaluated by every thread from the reduced
+                // values; only the rare closures (non-finite residual, residual already below the linear
+                // tolerance) go through thread 0 and a barrier
+                const double beta0 = sqrt(S.rv[0]);
+                const bool bad0 = S.rv[1] != 0.0 || !isfinite(beta0);
+                const bool small0 = !bad0 && !(beta0 > tol_lin);
                 if (tid == 0) {
                     if (lagpc && pc_now) { C.pc_c = c; C.pc_age = 0; }
                     C.st.n_rhs += 1;
                     C.st.n_lin += 1;
-                    C.beta = sqrt(S.rv[0]);
+                    C.beta = beta0;
                     C.kk = 0;
-                    if (S.rv[1] != 0.0 || !isfinite(C.beta)) C.flag = 2;
-                    S.gg[0] = C.beta;
-                    C.inrm = C.beta > 0.0 ? 1.0 / C.beta : 0.0;
-                    if (C.flag != 2 && !(C.beta > C.tol_lin)) {
+                    S.gg[0] = beta0;
+                    if (bad0) C.flag = 2;
+                    if (small0) {
                         // residual already below the linear tolerance: dy = 0
                         int fl = newton_decide(C, 0.0);
                         if (fl == 0 && C.newton_it >= STB_NEWTON_MAXIT) fl = 2;
                         C.flag = fl;
                     }
                 }
-                __syncthreads();
+                if (bad0 || small0) __syncthreads();
                 // ---- GMRES: V_0 = tw / beta; zv holds the direction, scaled by `zmul` ----------
                 // (C.flag: 0 while the solve runs; the thread that closes the solve leaves the Newton
                 // decision there: 1 converged, 2 failed, 0 iterate again)
-                bool lin_done = !(C.beta > C.tol_lin) || C.flag == 2;
+                bool lin_done = bad0 || small0;
                 int j = 0;
-                double zmul = C.inrm;
+                double zmul = beta0 > 0.0 ? 1.0 / beta0 : 0.0;
                 if (!lin_done) {
                     double* V0 = Vrow(0);
                     for (int k = tid; k < n_own; k += STB_NT) V0[k] = tw[k] * zmul;
@@ -1355,8 +1375,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 // Newton / Krylov failure: halve the step (scipy: factor 0.5 with current Jacobian)
                 if (tid == 0) {
                     C.st.n_newton_fail += 1;
-                    cl_compute_RU(C.order, 0.5, C.RU, K.Rs, K.Us);
-                    C.h *= 0.5;
+                    cl_compute_RU(order, 0.5, C.RU, K.Rs, K.Us);
+                    C.h = h * 0.5;
                     C.n_equal = 0;
                     C.steps_since_out += 1;
                     C.gfac = 0.0;
@@ -1367,7 +1387,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 continue;
             }
             CLPROF(13)
-            const double h = C.h, t_new = C.t + C.h;     // read before the control warp may change them
+            const double t_new = t_cur + h;
             // ---- error test and order selection share one reduction -------------------------------
             {
                 double v3[3] = {0.0, 0.0, 0.0};
@@ -1388,30 +1408,27 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     }
                 }
                 reduce_vals(3, v3);
+            }
+            // accept / reject evaluated by every thread from the reduced values (no serial section)
+            const double err_norm = sqrt(S.rv[0] * inv_N);
+            const double err_m2 = S.rv[1], err_p2 = S.rv[2];
+            const double safety = 0.9 * (2 * STB_NEWTON_MAXIT + 1) / (2.0 * STB_NEWTON_MAXIT + C.n_iter);
+            if (err_norm > 1.0 || !isfinite(err_norm)) {
                 if (tid == 0) {
-                    C.err_norm = sqrt(S.rv[0] / N);
-                    C.safety = 0.9 * (2 * STB_NEWTON_MAXIT + 1) / (2.0 * STB_NEWTON_MAXIT + C.n_iter);
-                    C.flag = 0;
-                    if (C.err_norm > 1.0 || !isfinite(C.err_norm)) {
-                        const double factor = isfinite(C.err_norm)
-                            ? fmax(STB_MIN_FACTOR, C.safety * pow(C.err_norm, -1.0 / (order + 1)))
-                            : STB_MIN_FACTOR;
-                        cl_compute_RU(order, factor, C.RU, K.Rs, K.Us);
-                        C.h *= factor;
-                        C.n_equal = 0;
-                        C.st.n_rejected += 1;
-                        C.steps_since_out += 1;
-                        C.flag = 1;
-                        C.gfac *= cl_ipow(factor, order + 1);
-                    }
+                    const double factor = isfinite(err_norm)
+                        ? fmax(STB_MIN_FACTOR, safety * pow(err_norm, -1.0 / (order + 1)))
+                        : STB_MIN_FACTOR;
+                    cl_compute_RU(order, factor, C.RU, K.Rs, K.Us);
+                    C.h = h * factor;
+                    C.n_equal = 0;
+                    C.st.n_rejected += 1;
+                    C.steps_since_out += 1;
+                    C.gfac *= cl_ipow(factor, order + 1);
                 }
                 __syncthreads();
-                if (C.flag == 1) {
-                    apply_change_D(order);
-                    continue;
-                }
+                apply_change_D(order);
+                continue;
             }
-            const double err_m2 = S.rv[1], err_p2 = S.rv[2];
             // ---- accepted: update differences, dense output, order / step selection -------------
             // Every thread updates and interpolates its own elements with no barrier in between
             // (the output cursor k_out_l / tq_l is kept identically by all threads); the scalar
@@ -1465,7 +1482,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     if (lane < 3) {
                         // candidate orders order-1, order, order+1 on lanes 0, 1, 2
                         const bool avail = lane == 1 || (lane == 0 ? order > 1 : order < STB_MAXORD);
-                        const double en = lane == 1 ? C.err_norm : sqrt((lane == 0 ? err_m2 : err_p2) / N);
+                        const double en = lane == 1 ? err_norm : sqrt((lane == 0 ? err_m2 : err_p2) * inv_N);
                         f = !avail ? 0.0 : (en > 0.0 ? pow(en, -1.0 / (order + lane)) : INFINITY);
                     }
                     const double fm = __shfl_sync(0xffffffffu, f, 0);
@@ -1478,7 +1495,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     else if (f0 >= fp) { best = f0; delta = 0; }
                     else { best = fp; delta = 1; }
                     new_order = order + delta;
-                    factor = fmin(STB_MAX_FACTOR, C.safety * best);
+                    factor = fmin(STB_MAX_FACTOR, safety * best);
                     cl_compute_RU_warp(new_order, factor, C.RU, K.Rs, K.Us, lane);
                 }
                 if (lane == 0) {
@@ -1496,6 +1513,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         C.flag2 = 1;
                         C.gfac = new_order == order ? cl_ipow(factor, order + 1) : 0.0;
                     } else {
+                        C.h = h;
                         C.n_equal += 1;
                         C.gfac = 1.0;
                     }
