@@ -1583,9 +1583,9 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     if (own_yout) WSC(WS_YOUT, d_yout, out_bytes);
     WSC(WS_NEXT, d_next, sizeof(int));
     WSC(WS_STATS, d_stats, sizeof(stb_stats) * n);
-    WSC(WS_PROF, d_prof, sizeof(long long) * 24);
+    WSC(WS_PROF, d_prof, sizeof(long long) * 64);
     CKC(ws_events(S));
-    CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 24, S->stream));
+    CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 64, S->stream));
     CKC(cudaMemsetAsync(d_next, 0, sizeof(int), S->stream));
     CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     double* yout_p = own_yout ? d_yout : y_out;
@@ -1609,6 +1609,10 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.resmask = plan.resmask; A.v_smem = plan.v_smem; A.d_smem = plan.d_smem;
     A.compact = plan.v2 ? 1 : 0;
     A.procs = S->d_procs;
+    A.cst_base = 2;
+    A.cst_slot = 3;
+    if (const char* env = getenv("STB_CST_BASE")) A.cst_base = std::max(0, atoi(env));
+    if (const char* env = getenv("STB_CST_SLOT")) A.cst_slot = std::max(1, atoi(env));
     A.pc_maxage = CL_PC_MAXAGE;
     A.pc_drift = CL_PC_DRIFT;
     if (const char* env = getenv("STB_PC_MAXAGE")) A.pc_maxage = std::max(1, atoi(env));
@@ -1690,7 +1694,7 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         tm.log += buf;
     }
     if (getenv("STB_VERBOSE")) {
-        long long pr[24];
+        long long pr[64];
         CKC(copy_on(S->stream, pr, d_prof, sizeof(pr), cudaMemcpyDeviceToHost));
         static const char* names[16] = {"stream", "stream_sync", "combine", "yk_barrier", "rhs_epilogue",
                                         "block_inv", "residual", "beta_reduce", "arnoldi_epi", "dots",
@@ -1712,6 +1716,12 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         if (plan.v2)
             fprintf(stderr, " | ion-major kernel, per Krylov it: products=%.0f butterfly=%.0f wait=%.0f orth_sums=%.0f", pr[20] / njv, pr[21] / njv, pr[22] / njv, pr[23] / njv);
         fprintf(stderr, "\n");
+        if (!plan.v2) {
+            fprintf(stderr, "[stb] pair pass per warp (cycles per pass | work-list steps):");
+            for (int w = 0; w < STB_NW; ++w)
+                fprintf(stderr, " %.0f|%lld", pr[24 + w] / (nrhs + njv), pr[24 + STB_NW + w + 1] - pr[24 + STB_NW + w]);
+            fprintf(stderr, "\n");
+        }
     }
     return STB_OK;
 }

@@ -153,6 +153,7 @@ struct ClArgs {
     int resmask, v_smem, d_smem;   // bit 2T+U: rows of block [T][U] resident in shared memory
     int opts;                      // CL_OPT_* bits
     const stb_process* procs;      // [L.n_proc] the process table (quad lattices: couplings inside a quad)
+    int cst_base, cst_slot;        // cost model of a pair-pass step: cst_base + cst_slot * field slots
     int pc_maxage;                 // lagged block inverses: refresh after this many steps ...
     double pc_drift;               // ... or when |c / c_factored - 1| exceeds this (CL_PC_MAXAGE, CL_PC_DRIFT)
     int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
@@ -166,7 +167,7 @@ struct ClArgs {
     double* work;              // [n_clusters][G][work_stride]: spilled V / D
     int64_t work_stride;
     int* next_sys;             // work counter (dynamic assignment of systems to clusters)
-    long long* prof;           // [24] clock64 cycles per phase (cluster 0, rank 0, thread 0) + counters; may be null
+    long long* prof;           // [64] clock64 cycles per phase (cluster 0, rank 0, thread 0) + counters, per-warp pair-pass cycles and work-list positions; may be null
 };
 
 __device__ __forceinline__ double cl_ipow(double x, int n) {
@@ -392,6 +393,7 @@ struct ClShared {
     short tl_ent[2][2 * STB_MAXT];               // term index | sign bit (0x4000: +, i.e. b == a)
     int cur_sys;
     long long prof[24];
+    long long wprof[STB_NW];                     // development aid: cycles of every warp's share of the pair passes
 };
 
 // COOP: the instance for systems with a cooperative (three-ion) process; the plain instance
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
 
     long long tick = clock64();
     if (tid == 0) for (int k = 0; k < 24; ++k) S.prof[k] = 0;
+    if (tid < STB_NW) S.wprof[tid] = 0;
 #define CLPROF(k)                                            \
     if (tid == 0) {                                          \
         const long long now_ = clock64();                    \
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             for (int U = 0; U < 2; ++U) {
                 const bool used = L.blk[T][U].n_slots > 0 && L.n[U] > 0;
                 stp[T][U] = used ? Y.nst[U] : 0;
-                cst[T][U] = 2 + 3 * L.blk[T][U].n_slots;
+                cst[T][U] = A.cst_base + A.cst_slot * L.blk[T][U].n_slots;
                 gsrc[T][U] = L.blk[T][U].g[0] ? L.blk[T][U].g[0] + (int64_t)r_lo[T] * L.ld[U] : nullptr;
                 gpitch[T][U] = L.ld[U];
                 gres_on[T][U] = Y.gres_off[T][U] >= 0 && used && cnt[T] > 0;
@@ -723,6 +726,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     // zb: offset of the gathered vector (Y.zy or Y.zv) in the dynamic shared array
     // lin_at >= 0: cooperative fields are linearised at the vector at offset lin_at (Krylov operator)
     auto fields_pass = [&](int zb, double mult, int lin_at) {
+        const long long w_t0 = clock64();
         int g = my_ga, t0 = my_ta, piece = 0;
         while (g < NRG && (g < my_gb || (g == my_gb && t0 < my_tb))) {
             const int T = g >= nrg[0];
@@ -754,6 +758,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             ++g;
             t0 = 0;
         }
+        if (lane == 0) S.wprof[warp] += clock64() - w_t0;
         CLPROF(0)
         __syncthreads();
         CLPROF(1)
@@ -1532,6 +1537,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             S.prof[18] += C.st.n_rhs;
             S.prof[19] += C.st.n_jv;
             for (int k = 0; k < 24; ++k) A.prof[k] = S.prof[k];
+            for (int k = 0; k < STB_NW; ++k) A.prof[24 + k] = S.wprof[k];
+            for (int k = 0; k <= STB_NW; ++k) A.prof[24 + STB_NW + k] = S.wpos[k];
         }
         if (tid == 0 && rank == 0) {
             C.st.status = C.status;

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
             for (int U = 0; U < 2; ++U) {
                 const bool used = L.blk[T][U].n_slots > 0 && L.n[U] > 0;
                 stp[T][U] = used ? Y.nst[U] : 0;
-                cst[T][U] = 2 + 3 * L.blk[T][U].n_slots;
+                cst[T][U] = A.cst_base + A.cst_slot * L.blk[T][U].n_slots;
                 gsrc[T][U] = L.blk[T][U].g[0] ? L.blk[T][U].g[0] + (int64_t)r_lo[T] * L.ld[U] : nullptr;
                 gpitch[T][U] = L.ld[U];
                 gres_on[T][U] = Y.gres_off[T][U] >= 0 && used && cnt[T] > 0;
