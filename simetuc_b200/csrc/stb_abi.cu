@@ -1611,6 +1611,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.procs = S->d_procs;
     A.cst_base = 2;
     A.cst_slot = 3;
+    A.piece_fix = CL_PIECE_FIX;
+    if (const char* env = getenv("STB_PIECE_FIX")) A.piece_fix = std::max(0, atoi(env));
     if (const char* env = getenv("STB_CST_BASE")) A.cst_base = std::max(0, atoi(env));
     if (const char* env = getenv("STB_CST_SLOT")) A.cst_slot = std::max(1, atoi(env));
     A.pc_maxage = CL_PC_MAXAGE;

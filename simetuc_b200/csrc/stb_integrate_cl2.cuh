@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
             // every piece also pays a fixed price (addresses, cross-lane reduction, store): CL_PIECE_FIX
             // pseudo-steps in front of each segment keep warps with three short pieces from
             // finishing long after warps with one long piece
-            WT[T] = (stp[T][0] ? (stp[T][0] + CL_PIECE_FIX) * cst[T][0] : 0) +
-                    (stp[T][1] ? (stp[T][1] + CL_PIECE_FIX) * cst[T][1] : 0);
+            WT[T] = (stp[T][0] ? (stp[T][0] + A.piece_fix) * cst[T][0] : 0) +
+                    (stp[T][1] ? (stp[T][1] + A.piece_fix) * cst[T][1] : 0);
             Wt[T] = cl_pow2ceil(max(L.s[T], 1));
         }
         const double KAPPA[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
                 x -= (int64_t)gi * WT[1];
                 g = nrg[0] + gi;
             }
-            const int64_t c0 = stp[T][0] ? (int64_t)(stp[T][0] + CL_PIECE_FIX) * cst[T][0] : 0;
-            if (x < c0) t = max(0, (int)(x / cst[T][0]) - CL_PIECE_FIX);
-            else t = stp[T][0] + (stp[T][1] ? min(stp[T][1], max(0, (int)((x - c0) / cst[T][1]) - CL_PIECE_FIX)) : 0);
+            const int64_t c0 = stp[T][0] ? (int64_t)(stp[T][0] + A.piece_fix) * cst[T][0] : 0;
+            if (x < c0) t = max(0, (int)(x / cst[T][0]) - A.piece_fix);
+            else t = stp[T][0] + (stp[T][1] ? min(stp[T][1], max(0, (int)((x - c0) / cst[T][1]) - A.piece_fix)) : 0);
         }
         S.wb_g[tid] = g;
         S.wb_t[tid] = t;
