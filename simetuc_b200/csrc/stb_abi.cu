@@ -318,6 +318,7 @@ struct stb_system {
     int sm_count = 148;
     int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
     bool built_with_cells = false;   // the cutoff lists came from the cell-list build
+    bool avg_raw = false;            // the relaxation of a cumulative run: unclipped means (see k_cumtrapz)
     bool avg_cumulative = false;     // stb_integrate_dynamics returns the running time integral of the curves
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
@@ -1612,6 +1613,10 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.cst_base = 2;
     A.cst_slot = 3;
     A.piece_fix = CL_PIECE_FIX;
+    A.lin_rms = CL_LIN_RMS;
+    A.lin_tight_steps = CL_LIN_TIGHT_STEPS;
+    if (const char* env = getenv("STB_LIN_TIGHT_STEPS")) A.lin_tight_steps = std::max(0, atoi(env));
+    if (const char* env = getenv("STB_LIN_RMS")) A.lin_rms = std::max(1e-6, atof(env));
     if (const char* env = getenv("STB_PIECE_FIX")) A.piece_fix = std::max(0, atoi(env));
     if (const char* env = getenv("STB_CST_BASE")) A.cst_base = std::max(0, atoi(env));
     if (const char* env = getenv("STB_CST_SLOT")) A.cst_slot = std::max(1, atoi(env));
@@ -1670,7 +1675,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
             avg_p = d_avg;
         }
         g_launches++;
-        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
+        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p,
+                                                                             S->avg_raw ? 0 : 1);
         CKC(cudaGetLastError());
         S->last_launches += 1;
     }
@@ -1889,6 +1895,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
     A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     A.guess = 1;
+    A.lin_rms = STB_LIN_RMS;
+    if (const char* env = getenv("STB_LIN_RMS_GRID")) A.lin_rms = std::max(1e-6, atof(env));
     if (const char* env = getenv("STB_CL_OPTS")) A.guess = atoi(env) & CL_OPT_GUESS;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;
@@ -1905,7 +1913,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
             avg_p = d_avg;
         }
         g_launches++;
-        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p);
+        k_avg_populations<<<dim3((unsigned)n_t, n), 256, 0, S->stream>>>(S->dL, yout_p, n_t, avg_p,
+                                                                             S->avg_raw ? 0 : 1);
         CKI(cudaGetLastError());
         S->last_launches += 1;
     }
@@ -1997,7 +2006,9 @@ static int integrate_dynamics_core(stb_system* S, int32_t first, int32_t n, int6
     k_row_to_planes<<<(unsigned)((tot + 255) / 256), 256, 0, S->stream>>>(
         S->d_plane_of_ref, N, n, d_yp + (n_tp - 1) * (int64_t)N, n_tp * (int64_t)N, d_y0);
     CK(cudaGetLastError());
+    S->avg_raw = S->avg_cumulative && d_avg;     // k_cumtrapz clips after integrating
     rc = integrate_core(S, first, n, 0, n_t, ts_p, d_y0, rtol, atol, nsteps, d_ys, d_avg, stats_relax, true);
+    S->avg_raw = false;
     if (rc) return rc;
     if (S->avg_cumulative && d_avg) {
         if (!S->exp_t.empty())

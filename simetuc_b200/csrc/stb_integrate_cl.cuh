@@ -155,6 +155,8 @@ struct ClArgs {
     const stb_process* procs;      // [L.n_proc] the process table (quad lattices: couplings inside a quad)
     int cst_base, cst_slot;        // cost model of a pair-pass step: cst_base + cst_slot * field slots
     int piece_fix;                 // ... and the fixed cost of a piece, in steps (CL_PIECE_FIX)
+    double lin_rms;                // GMRES tolerance in units of the error test (CL_LIN_RMS) ...
+    int lin_tight_steps;           // ... tightened to STB_LIN_RMS for this many steps after a rejection
     int pc_maxage;                 // lagged block inverses: refresh after this many steps ...
     double pc_drift;               // ... or when |c / c_factored - 1| exceeds this (CL_PC_MAXAGE, CL_PC_DRIFT)
     int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
@@ -995,7 +997,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
 
     const double sqrtN = sqrt((double)N);
     const double inv_N = 1.0 / (double)N;
-    const double tol_lin = STB_LIN_RMS * sqrtN;
+    const double tol_loose = A.lin_rms * sqrtN, tol_tight = fmin(A.lin_rms, STB_LIN_RMS) * sqrtN;
     const double rtol = A.rtol, atol = A.atol;
 
     // =================================== systems ============================================
@@ -1026,7 +1028,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             C.k_out = 1;
             C.steps_since_out = 0;
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
-            C.tol_lin = STB_LIN_RMS * sqrtN;
+            C.tol_lin = tol_loose;
+            C.lin_tight = 0;
             C.crate = 1.0;
             C.since_verify = 0;
             C.gfac = 0.0;
@@ -1131,6 +1134,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     break;
                 }
             }
+            const double tol_lin = C.tol_lin;      // loose, or tight for a while after a rejection
             const double ralpha = K.RALPHA[order];
             const double c = h * ralpha;
             const bool pc_ref = !lagpc || C.pc_age < 0 || C.pc_age >= A.pc_maxage ||
@@ -1387,6 +1391,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.steps_since_out += 1;
                     C.gfac = 0.0;
                     C.pc_age = -1;       // factor the block inverses afresh
+                    C.lin_tight = A.lin_tight_steps;
+                    C.tol_lin = tol_tight;
                 }
                 __syncthreads();
                 apply_change_D(order);
@@ -1430,6 +1436,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.st.n_rejected += 1;
                     C.steps_since_out += 1;
                     C.gfac *= cl_ipow(factor, order + 1);
+                    C.lin_tight = A.lin_tight_steps;
+                    C.tol_lin = tol_tight;
                 }
                 __syncthreads();
                 apply_change_D(order);
@@ -1512,6 +1520,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     C.t = t_new;
                     C.flag2 = 0;      // (not C.flag: slow threads may still be reading the rejection test)
                     if (C.pc_age >= 0) C.pc_age += 1;
+                    if (C.lin_tight > 0 && --C.lin_tight == 0) C.tol_lin = tol_loose;
                     if (need_order) {
                         C.order = new_order;
                         C.h = h * factor;

@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl2_t(ClArgs A) {
             C.k_out = 1;
             C.steps_since_out = 0;
             C.newton_tol = fmax(10.0 * EPS / rtol, fmin(0.03, sqrt(rtol)));
-            C.tol_lin = STB_LIN_RMS * sqrtN;
+            C.tol_lin = A.lin_rms * sqrtN;
             C.crate = 1.0;
             C.since_verify = 0;
             C.gfac = 0.0;

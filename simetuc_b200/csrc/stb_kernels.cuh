@@ -147,8 +147,9 @@ __global__ void k_planes_to_ref(const int* plane_of_ref, int N, int n, const dou
 // per-state ion averages clipped at zero: Solution._calculate_avg_populations
 // (simulations.py:100-128).  y_out is [n_t][N] in reference layout for one system; one block per
 // (time row, system); out [n_t][sS+sA].
+// clip = 0 (avg_cumulative): the raw means, for k_cumtrapz to integrate and clip afterwards.
 __global__ void k_avg_populations(const DevLattice* Lg, const double* y_out, int64_t n_t,
-                                  double* avg) {
+                                  double* avg, int clip) {
     const DevLattice& L = *Lg;
     int64_t row = blockIdx.x;
     int b = blockIdx.y;
@@ -169,7 +170,7 @@ __global__ void k_avg_populations(const DevLattice* Lg, const double* y_out, int
             double t = 0.0;
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
             t = L.n[T] ? t / L.n[T] : 0.0;
-            o[k] = t > 0.0 ? t : 0.0;
+            o[k] = (t > 0.0 || !clip) ? t : 0.0;
         }
         __syncthreads();
     }
@@ -227,7 +228,9 @@ __global__ void __launch_bounds__(256) k_coop_add(const DevLattice* Lp, const do
 
 // Pulsed steady state of a batch: running trapezoid of every emission curve over the solution times,
 // in place (DynamicsSolution.calculate_steady_state applied to the averages, simulations.py:579-591;
-// the ion average commutes with the time integral).  One thread per (system, state kind).
+// the ion average commutes with the time integral; the clip at zero does not - states whose
+// population sits below atol have means of either sign - so the means come in unclipped and the
+// integral is clipped, as the host does).  One thread per (system, state kind).
 __global__ void k_cumtrapz(double* avg /*[n][n_t][kinds]*/, const double* t_sol, int64_t n_t, int kinds, int n) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)n * kinds) return;
@@ -239,7 +242,7 @@ __global__ void k_cumtrapz(double* avg /*[n][n_t][kinds]*/, const double* t_sol,
         const double cur = a[k * kinds];
         // same operation order as the host mirror: cumsum(0.5 * (y[k] + y[k-1]) * (t[k] - t[k-1]))
         run += 0.5 * (cur + prev) * ((t_sol[k] - t_sol[0]) - (t_sol[k - 1] - t_sol[0]));
-        a[k * kinds] = run;
+        a[k * kinds] = run > 0.0 ? run : 0.0;
         prev = cur;
     }
 }

@@ -238,17 +238,27 @@ def test_group_sizes_agree(monkeypatch):
     _, _, pop = system.ground_states()
     t = np.array([0.0, 1e-8])
     res = {}
-    for G in (1, 4, 16):
-        monkeypatch.setenv('STB_GROUP_CTAS', str(G))
-        y, _, st = system.integrate(t, pop.astype(float), pulse=True, rtol=1e-8, atol=1e-15)
-        assert st[0]['status'] == 0
-        res[G] = y[0, -1]
+    # STB_LIN_RMS: the GMRES tolerance of the cluster integrator.  At the tight 2e-3 a different reduction
+    # order moves the result by round-off only; at the shipped default (5e-2 of the error test) the last
+    # Krylov iteration may or may not run, so two group sizes agree within the integration tolerance.
+    for lin in ('2e-3', None):
+        if lin:
+            monkeypatch.setenv('STB_LIN_RMS', lin)
+        else:
+            monkeypatch.delenv('STB_LIN_RMS')
+        for G in (1, 4, 16):
+            monkeypatch.setenv('STB_GROUP_CTAS', str(G))
+            y, _, st = system.integrate(t, pop.astype(float), pulse=True, rtol=1e-8, atol=1e-15)
+            assert st[0]['status'] == 0
+            res[lin, G] = y[0, -1]
     monkeypatch.delenv('STB_GROUP_CTAS')
     # G = 1, 4: the cluster integrator with 1 and 4 CTAs per system (same arithmetic, different
     # reduction order); G = 16: the grid integrator (no lagged block inverses: another path to the
     # same solution, equal within the integration tolerance rtol 1e-8, atol 1e-15)
-    assert np.all(np.abs(res[4] - res[1]) <= 1e-9 * np.abs(res[1]) + 1e-18)
-    assert np.all(np.abs(res[16] - res[1]) <= 1e-6 * np.abs(res[1]) + 1e-15)
+    ref = res['2e-3', 1]
+    assert np.all(np.abs(res['2e-3', 4] - ref) <= 1e-9 * np.abs(ref) + 1e-18)
+    for key in (('2e-3', 16), (None, 1), (None, 4), (None, 16)):
+        assert np.all(np.abs(res[key] - ref) <= 1e-6 * np.abs(ref) + 1e-15), key
     system.close()
 
 
