@@ -222,7 +222,8 @@ int stb_objective(stb_system* sys, int32_t n, double* errors);
 int stb_set_option(stb_system* sys, const char* name, double value);
 /* Read-only properties of a handle: "sm_budget"; "quad" (1: the sensitizers are stored in quads of
  * strongly coupled ions for the block preconditioner - an internal order, every result is in the
- * reference's order); "cell_lists" (1: the d_max pair lists were built with cell lists instead of the
+ * reference's order); "pc_group" (ions per preconditioner block of the cluster integrator: 4 or 16,
+ * 1 without grouping); "cell_lists" (1: the d_max pair lists were built with cell lists instead of the
  * O(n^2) scan - the feature settings.py:35 parses and lattice.py:301-374 never applies). */
 int stb_get_option(const stb_system* sys, const char* name, double* value);
 /* Device time (ms, CUDA events) of the pulse and of the relaxation kernel of the last

@@ -585,67 +585,28 @@ static bool build_cell_grid(int n, const double* pos, const double* cell, const 
     return true;
 }
 
-static bool group_sensitizers(int n, const uint8_t* type, int sS, const double* dist, const double* pos,
-                              const double* cell, std::vector<int>& out) {
-    out.clear();
-    if (const char* env = getenv("STB_QUADS")) if (atoi(env) == 0) return false;
-    if (sS < 1 || 4 * sS > 12) return false;      // a quad block has at most 12 x 12 entries (Gauss-Jordan teams)
-    std::vector<int> ions;
-    for (int q = 0; q < n; ++q) if (type[q] == 0) ions.push_back(q);
-    const int nS = (int)ions.size();
-    if (nS < 2 || nS > 2048) return false;
-    double inv[9];
-    bool periodic = pos && cell && invert3(cell, inv);
-    auto d2 = [&](int a, int b) -> double {
-        if (dist) { const double d = dist[(size_t)ions[a] * n + ions[b]]; return d * d; }
-        double v[3] = {pos[3 * ions[b]] - pos[3 * ions[a]], pos[3 * ions[b] + 1] - pos[3 * ions[a] + 1],
-                       pos[3 * ions[b] + 2] - pos[3 * ions[a] + 2]};
-        if (periodic) {      // nearest image by fractional rounding (good enough to find neighbours)
-            double f[3];
-            for (int c = 0; c < 3; ++c) f[c] = v[0] * inv[c] + v[1] * inv[3 + c] + v[2] * inv[6 + c];
-            for (int c = 0; c < 3; ++c) f[c] -= std::nearbyint(f[c]);
-            for (int c = 0; c < 3; ++c) v[c] = f[0] * cell[c] + f[1] * cell[3 + c] + f[2] * cell[6 + c];
-        }
-        return v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-    };
-    struct Cand { double d2; int a, b; };
-    std::vector<Cand> cand;
-    cand.reserve((size_t)nS * 3);
-    for (int a = 0; a < nS; ++a) {
-        double best[3] = {1e300, 1e300, 1e300};
-        int who[3] = {-1, -1, -1};
-        for (int b = 0; b < nS; ++b) {
-            if (b == a) continue;
-            const double d = d2(a, b);
-            if (!(d > 0.0)) continue;
-            for (int k = 0; k < 3; ++k)
-                if (d < best[k]) {
-                    for (int m = 2; m > k; --m) { best[m] = best[m - 1]; who[m] = who[m - 1]; }
-                    best[k] = d; who[k] = b;
-                    break;
-                }
-        }
-        for (int k = 0; k < 3; ++k)
-            if (who[k] >= 0 && a < who[k]) cand.push_back({best[k], a, who[k]});
-            else if (who[k] >= 0) cand.push_back({best[k], who[k], a});
-    }
-    std::sort(cand.begin(), cand.end(), [](const Cand& x, const Cand& y) {
+// Greedy packing of n items into groups of <= 4 strongly coupled items: the candidate pairs (a < b,
+// d2 = squared distance; every item proposes its nearest items) are merged closest first while a group
+// holds at most four items, and the groups are emitted as 4, 3+1, 2+2, 2+1+1, 1+1+1+1.
+struct PairCand { double d2; int a, b; };
+static std::vector<int> greedy_fours(int n, std::vector<PairCand>& cand) {
+    std::sort(cand.begin(), cand.end(), [](const PairCand& x, const PairCand& y) {
         return x.d2 != y.d2 ? x.d2 < y.d2 : (x.a != y.a ? x.a < y.a : x.b < y.b);
     });
-    std::vector<int> grp(nS);
-    std::vector<std::vector<int>> members(nS);
-    for (int a = 0; a < nS; ++a) { grp[a] = a; members[a] = {a}; }
-    for (const Cand& c : cand) {
+    std::vector<int> grp(n);
+    std::vector<std::vector<int>> members(n);
+    for (int a = 0; a < n; ++a) { grp[a] = a; members[a] = {a}; }
+    for (const PairCand& c : cand) {
         const int ga = grp[c.a], gb = grp[c.b];
         if (ga == gb || members[ga].size() + members[gb].size() > 4) continue;
         for (int m : members[gb]) { grp[m] = ga; members[ga].push_back(m); }
         members[gb].clear();
     }
     std::vector<std::vector<int>> by_size[5];
-    for (int a = 0; a < nS; ++a)
+    for (int a = 0; a < n; ++a)
         if (!members[a].empty()) by_size[members[a].size()].push_back(members[a]);
-    std::vector<int> order;          // sensitizer ranks in storage order
-    order.reserve(nS);
+    std::vector<int> order;          // items in storage order
+    order.reserve(n);
     auto take = [&](int sz) {
         std::vector<int> g = by_size[sz].back();
         by_size[sz].pop_back();
@@ -658,6 +619,156 @@ static bool group_sensitizers(int n, const uint8_t* type, int sS, const double* 
     while (by_size[3].empty() && !by_size[2].empty() && by_size[1].size() >= 2) { take(2); take(1); take(1); }
     for (int sz = 3; sz >= 1; --sz)
         while (!by_size[sz].empty()) take(sz);
+    return order;
+}
+
+// Order of the sensitizers for the block preconditioners: strongly coupled ions (the closest pairs:
+// energy migration goes with d^-6) are put next to each other, in quads of type-local indices
+// 4m .. 4m+3, and neighbouring quads in groups of four, 16m .. 16m+15.  What counts is that no strong
+// pair is cut by a group boundary (compact boxes of a k-d bisection cut too many: 3.97 Krylov iterations
+// per solve against 2.02 on a 25 % Yb lattice, single-ion blocks 4.71), so both levels are greedy: every
+// ion proposes its three nearest sensitizers, the pairs are merged closest first into quads; then every
+// quad proposes its three nearest quads (distance = the closest pair of ions) and the quads are merged
+// into groups the same way.  Neighbours: brute force up to 2048 sensitizers, through a uniform grid
+// (positions required) above.  Only the ORDER of the ions inside the library changes; every result is
+// reported in the reference's order.  Returns false (identity order) for lattices it does not apply to.
+// out[r] = type-local index of the r-th sensitizer in lattice order.
+static bool group_sensitizers(int n, const uint8_t* type, int sS, const double* dist, const double* pos,
+                              const double* cell, std::vector<int>& out) {
+    out.clear();
+    if (const char* env = getenv("STB_QUADS")) if (atoi(env) == 0) return false;
+    if (sS < 1 || 4 * sS > 12) return false;      // a quad block has at most 12 x 12 entries (Gauss-Jordan teams)
+    std::vector<int> ions;
+    for (int q = 0; q < n; ++q) if (type[q] == 0) ions.push_back(q);
+    const int nS = (int)ions.size();
+    if (nS < 2) return false;
+    if (nS > 2048 && !pos) return false;
+    double inv[9];
+    const bool periodic = pos && cell && invert3(cell, inv);
+    auto d2 = [&](int a, int b) -> double {
+        if (dist) { const double d = dist[(size_t)ions[a] * n + ions[b]]; return d * d; }
+        double v[3] = {pos[3 * ions[b]] - pos[3 * ions[a]], pos[3 * ions[b] + 1] - pos[3 * ions[a] + 1],
+                       pos[3 * ions[b] + 2] - pos[3 * ions[a] + 2]};
+        if (periodic) {      // nearest image by fractional rounding (good enough to find neighbours)
+            double f[3];
+            for (int c = 0; c < 3; ++c) f[c] = v[0] * inv[c] + v[1] * inv[3 + c] + v[2] * inv[6 + c];
+            for (int c = 0; c < 3; ++c) f[c] -= std::nearbyint(f[c]);
+            for (int c = 0; c < 3; ++c) v[c] = f[0] * cell[c] + f[1] * cell[3 + c] + f[2] * cell[6 + c];
+        }
+        return v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    };
+    // ---- the K nearest sensitizers of every sensitizer ----------------------------------------------
+    const int K = 8;
+    std::vector<int> nbr((size_t)nS * K, -1);
+    std::vector<double> nbd((size_t)nS * K, 1e300);
+    auto offer = [&](int a, int b) {
+        const double d = d2(a, b);
+        if (!(d > 0.0)) return;
+        double* bd = &nbd[(size_t)a * K];
+        int* bn = &nbr[(size_t)a * K];
+        if (!(d < bd[K - 1])) return;
+        int k = K - 1;
+        while (k > 0 && d < bd[k - 1]) { bd[k] = bd[k - 1]; bn[k] = bn[k - 1]; --k; }
+        bd[k] = d; bn[k] = b;
+    };
+    if (nS <= 2048) {
+        for (int a = 0; a < nS; ++a)
+            for (int b = 0; b < nS; ++b) if (b != a) offer(a, b);
+    } else {
+        // uniform grid with ~4 sensitizers per cell, in fractional (periodic, wrapped) or bounding-box
+        // coordinates; the 27 cells around an ion hold its nearest neighbours
+        const int nc = std::max(3, (int)std::cbrt(nS / 4.0));
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        if (!periodic)
+            for (int a = 0; a < nS; ++a)
+                for (int c = 0; c < 3; ++c) {
+                    lo[c] = std::min(lo[c], pos[3 * ions[a] + c]);
+                    hi[c] = std::max(hi[c], pos[3 * ions[a] + c]);
+                }
+        std::vector<int> cidx((size_t)nS * 3), cell_of(nS), start((size_t)nc * nc * nc + 1, 0), items(nS);
+        for (int a = 0; a < nS; ++a) {
+            const double* p = pos + 3 * ions[a];
+            for (int c = 0; c < 3; ++c) {
+                double f;
+                if (periodic) { f = p[0] * inv[c] + p[1] * inv[3 + c] + p[2] * inv[6 + c]; f -= std::floor(f); }
+                else f = (p[c] - lo[c]) / std::max(hi[c] - lo[c], 1e-9);
+                cidx[3 * a + c] = std::min(nc - 1, std::max(0, (int)(f * nc)));
+            }
+            cell_of[a] = (cidx[3 * a] * nc + cidx[3 * a + 1]) * nc + cidx[3 * a + 2];
+            start[cell_of[a] + 1]++;
+        }
+        for (size_t c = 0; c + 1 < start.size(); ++c) start[c + 1] += start[c];
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int a = 0; a < nS; ++a) items[fill[cell_of[a]]++] = a;
+        for (int a = 0; a < nS; ++a)
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dz = -1; dz <= 1; ++dz) {
+                        int c3[3] = {cidx[3 * a] + dx, cidx[3 * a + 1] + dy, cidx[3 * a + 2] + dz};
+                        bool in = true;
+                        for (int c = 0; c < 3; ++c) {
+                            if (periodic) c3[c] = (c3[c] + nc) % nc;
+                            else if (c3[c] < 0 || c3[c] >= nc) in = false;
+                        }
+                        if (!in) continue;
+                        const int cc = (c3[0] * nc + c3[1]) * nc + c3[2];
+                        for (int i = start[cc]; i < start[cc + 1]; ++i) if (items[i] != a) offer(a, items[i]);
+                    }
+    }
+    // ---- ions -> quads -----------------------------------------------------------------------------------
+    std::vector<PairCand> cand;
+    cand.reserve((size_t)nS * 3);
+    for (int a = 0; a < nS; ++a)
+        for (int k = 0; k < 3; ++k) {
+            const int b = nbr[(size_t)a * K + k];
+            if (b >= 0) cand.push_back({nbd[(size_t)a * K + k], std::min(a, b), std::max(a, b)});
+        }
+    const std::vector<int> ion_order = greedy_fours(nS, cand);
+    // ---- quads -> groups of four quads: the last (possibly partial) quad stays last so that every other
+    //      quad keeps its alignment -------------------------------------------------------------------------
+    const int nq = (nS + 3) / 4;
+    std::vector<int> quad_of(nS);
+    for (int p = 0; p < nS; ++p) quad_of[ion_order[p]] = p / 4;
+    std::vector<int> quad_order(nq);
+    for (int q = 0; q < nq; ++q) quad_order[q] = q;
+    bool group16 = nq > 1;
+    if (const char* env = getenv("STB_GROUP16")) group16 = group16 && atoi(env) != 0;
+    if (group16) {
+        cand.clear();
+        for (int q = 0; q + 1 < nq; ++q) {
+            double best[3] = {1e300, 1e300, 1e300};
+            int who[3] = {-1, -1, -1};
+            for (int p = 4 * q; p < 4 * q + 4; ++p) {
+                const int a = ion_order[p];
+                for (int k = 0; k < K; ++k) {
+                    const int b = nbr[(size_t)a * K + k];
+                    if (b < 0) continue;
+                    const int qb = quad_of[b];
+                    if (qb == q || qb == nq - 1) continue;
+                    const double d = nbd[(size_t)a * K + k];
+                    int have = -1;
+                    for (int m = 0; m < 3; ++m) if (who[m] == qb) have = m;
+                    if (have >= 0) {
+                        if (d < best[have]) best[have] = d;
+                    } else if (d < best[2]) {
+                        best[2] = d; who[2] = qb;
+                    } else continue;
+                    for (int m = 2; m > 0; --m)          // keep the three sorted
+                        if (best[m] < best[m - 1]) { std::swap(best[m], best[m - 1]); std::swap(who[m], who[m - 1]); }
+                    for (int m = 2; m > 0; --m)
+                        if (best[m] < best[m - 1]) { std::swap(best[m], best[m - 1]); std::swap(who[m], who[m - 1]); }
+                }
+            }
+            for (int m = 0; m < 3; ++m)
+                if (who[m] >= 0) cand.push_back({best[m], std::min(q, who[m]), std::max(q, who[m])});
+        }
+        std::vector<int> go = greedy_fours(nq - 1, cand);
+        for (int q = 0; q + 1 < nq; ++q) quad_order[q] = go[q];
+    }
+    std::vector<int> order;          // sensitizer ranks in storage order
+    order.reserve(nS);
+    for (int q : quad_order)
+        for (int i = 4 * q; i < std::min(nS, 4 * q + 4); ++i) order.push_back(ion_order[i]);
     out.assign(nS, 0);
     for (int p = 0; p < nS; ++p) out[order[p]] = p;
     return true;
@@ -758,6 +869,18 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     L.off[1] = S->s[0] * S->n[0];
     L.n_proc = n_proc;
     L.quad = quad ? 1 : 0;
+    // ions per preconditioner block of the cluster integrator: the 16-ion groups (blocks of <= 32 unknowns:
+    // 2-state sensitizers) from 192 sensitizers upwards, else the quads.  Measured (profiles/r02_groups.txt):
+    // the reference's 240S/108A benchmark lattice 507 -> 42 ms (quads leave ~18 Krylov iterations per
+    // solve, groups 2.6); Yb-Tm lattices with 600-1100 sensitizers: -15..-22 % Krylov iterations at the same
+    // time (the 32-pivot Gauss-Jordan costs what the iterations save); below, whole groups per CTA unbalance
+    // the cluster (74 sensitizers on 4 CTAs: 32 rows on one of them, pair rows no longer resident: 722 ->
+    // 499 solves/s on the C2 sweep).  STB_PCG=4 / 16 forces the choice.
+    L.grp16 = quad && S->n[0] > 4;
+    if (const char* env = getenv("STB_GROUP16")) if (atoi(env) == 0) L.grp16 = 0;
+    const bool can16 = L.grp16 && 16 * S->s[0] <= 32;
+    L.pcg = (can16 && S->n[0] >= 192) ? 16 : 4;
+    if (const char* env = getenv("STB_PCG")) L.pcg = (atoi(env) == 16 && can16) ? 16 : 4;
     S->plane_of_ref.resize(S->N);
     S->ref_of_plane.resize(S->N);
     for (int q = 0; q < n; ++q) {
@@ -1837,7 +1960,15 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_integrate, STB_NT, dyn_bytes));
     if (occ < 1) return fail(STB_ECUDA, "integrator kernel does not fit on an SM");
 
-    const int64_t work_stride = stb_work_doubles(N, L.NF, NMinv);
+    // group block preconditioner (stb_integrate.cuh): sensitizers stored in compact groups, dense S-S
+    // block (the couplings inside a group are read from it), rows handled by >= 16 lanes
+    int grp = 0;
+    if (L.quad && L.grp16 && L.dense && L.n_mult == 1 && L.lpr >= 16 && !resident && L.s[0] >= 1 && STB_GDIM % L.s[0] == 0 &&
+        (STB_GDIM / L.s[0]) % 4 == 0 && (STB_GDIM / L.s[0]) % L.R == 0 && S->d_procs && L.n_proc > 0)
+        grp = STB_GDIM / L.s[0];
+    if (const char* env = getenv("STB_GRID_GROUPS")) if (atoi(env) == 0) grp = 0;
+    const int NGinv = grp ? ((L.n[0] + grp - 1) / grp + G + 1) * STB_GDIM * STB_GDIM : 0;     // group slots: see ch_slot
+    const int64_t work_stride = stb_work_doubles(N, L.NF, NMinv + NGinv);
     double *d_work = nullptr, *d_y0 = nullptr, *d_yout = nullptr, *d_t = nullptr, *d_part = nullptr,
            *d_tmp = nullptr, *d_avg = nullptr;
     unsigned long long* d_bar = nullptr;
@@ -1895,6 +2026,7 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.bar = d_bar; A.partials = d_part; A.NMinv = NMinv; A.prof = d_prof; A.staged = staged; A.resident = resident;
     A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     A.guess = 1;
+    A.grp = grp; A.NGinv = NGinv; A.procs = S->d_procs;
     A.lin_rms = STB_LIN_RMS;
     if (const char* env = getenv("STB_LIN_RMS_GRID")) A.lin_rms = std::max(1e-6, atof(env));
     if (const char* env = getenv("STB_CL_OPTS")) A.guess = atoi(env) & CL_OPT_GUESS;
@@ -2138,6 +2270,7 @@ extern "C" int stb_get_option(const stb_system* S, const char* name, double* val
     if (!S || !name || !value) return fail(STB_EINVAL, "null argument");
     if (!strcmp(name, "sm_budget")) *value = S->sm_budget;
     else if (!strcmp(name, "quad")) *value = S->hL.quad;
+    else if (!strcmp(name, "pc_group")) *value = S->hL.quad ? S->hL.pcg : 1;
     else if (!strcmp(name, "cell_lists")) *value = S->built_with_cells ? 1.0 : 0.0;
     else return fail(STB_EINVAL, std::string("unknown option ") + name);
     return STB_OK;

@@ -88,16 +88,19 @@ struct DevLattice {
     CoopList coop[3];
     int quad;                    // 1: the sensitizers are stored in quads of strongly coupled ions
                                  // (type-local indices 4m .. 4m+3), see group_sensitizers()
+    int grp16;                   // 1: ... and the quads in groups of four neighbouring quads (16m .. 16m+15)
+    int pcg;                     // ions per block of the cluster integrator's group preconditioner (4 or 16)
 };
 
 // Rows of type T owned by CTA `rank` of a group of G CTAs.  Quad lattices split the sensitizers in
-// whole quads, so that the block preconditioner of a quad never straddles two CTAs.
+// whole preconditioner groups (L.pcg ions), so that a block never straddles two CTAs.
 __host__ __device__ inline void stb_own_rows(const DevLattice& L, int T, int rank, int G, int& lo, int& cnt) {
     if (T == 0 && L.quad) {
-        const int nq = (L.n[0] + 3) / 4;
+        const int pg = L.pcg;
+        const int nq = (L.n[0] + pg - 1) / pg;
         const int q_lo = (int)(((long long)nq * rank) / G), q_hi = (int)(((long long)nq * (rank + 1)) / G);
-        lo = 4 * q_lo;
-        const int hi = 4 * q_hi < L.n[0] ? 4 * q_hi : L.n[0];
+        lo = pg * q_lo;
+        const int hi = pg * q_hi < L.n[0] ? pg * q_hi : L.n[0];
         cnt = hi > lo ? hi - lo : 0;
     } else {
         lo = (int)(((long long)L.n[T] * rank) / G);
@@ -106,7 +109,7 @@ __host__ __device__ inline void stb_own_rows(const DevLattice& L, int T, int ran
 }
 // the largest such count over the ranks
 __host__ __device__ inline int stb_own_rows_max(const DevLattice& L, int T, int G) {
-    if (T == 0 && L.quad) return 4 * (((L.n[0] + 3) / 4 + G - 1) / G);
+    if (T == 0 && L.quad) return L.pcg * (((L.n[0] + L.pcg - 1) / L.pcg + G - 1) / G);
     return (L.n[T] + G - 1) / G;
 }
 

@@ -80,22 +80,17 @@ __device__ __forceinline__ double coop_coupling(const DevLattice& L, const SysPa
     });
 }
 
-// Row j of Minv = (I - c (Lin_T + sum_t C_t Fy[slot_t] (e_b - e_a) e_a^T))^-1 in lane j.
-// Gauss-Jordan without pivoting: the matrix is a column-diagonally-dominant M-matrix (columns of
-// every rate operator sum to zero, so columns of I - cJ sum to one with non-positive
-// off-diagonals).  Rows live in registers (static indices), pivot rows travel by shuffle.
-__device__ __forceinline__ void coop_block_inverse(const DevLattice& L, const SysParams& P, int T,
-                                                   int W, int gl, double fyl, double c,
-                                                   double (&ai)[STB_MAXS]) {
+// Row j of M = I - c (Lin_T + sum_t C_t Fy[slot_t] (e_b - e_a) e_a^T) in lane j (a[k], k < s).
+__device__ __forceinline__ void coop_block_row(const DevLattice& L, const SysParams& P, int T,
+                                               int W, int gl, double fyl, double c,
+                                               double (&a)[STB_MAXS]) {
     const int s = L.s[T];
     const double* lin = P.lin[T];
     const TermTable& tt = L.terms[T];
-    double a[STB_MAXS];
     const int row = gl < s ? gl : 0;
 #pragma unroll
     for (int k = 0; k < STB_MAXS; ++k) {
         a[k] = k < s ? -c * lin[row * s + k] : 0.0;
-        ai[k] = k == gl ? 1.0 : 0.0;
         if (k == gl) a[k] += 1.0;
     }
     for (int t = 0; t < tt.n_terms; ++t) {
@@ -106,6 +101,20 @@ __device__ __forceinline__ void coop_block_inverse(const DevLattice& L, const Sy
             if (k == ta) a[k] += (gl == ta ? kk : 0.0) - (gl == tb ? kk : 0.0);
         }
     }
+}
+
+// Row j of Minv = M^-1 in lane j.
+// Gauss-Jordan without pivoting: the matrix is a column-diagonally-dominant M-matrix (columns of
+// every rate operator sum to zero, so columns of I - cJ sum to one with non-positive
+// off-diagonals).  Rows live in registers (static indices), pivot rows travel by shuffle.
+__device__ __forceinline__ void coop_block_inverse(const DevLattice& L, const SysParams& P, int T,
+                                                   int W, int gl, double fyl, double c,
+                                                   double (&ai)[STB_MAXS]) {
+    const int s = L.s[T];
+    double a[STB_MAXS];
+    coop_block_row(L, P, T, W, gl, fyl, c, a);
+#pragma unroll
+    for (int k = 0; k < STB_MAXS; ++k) ai[k] = k == gl ? 1.0 : 0.0;
     for (int col = 0; col < s; ++col) {
         double acol = 0.0;
 #pragma unroll

@@ -61,7 +61,13 @@ struct IntArgs {
     int tma_kc, tma_stages;
     int guess;                // Newton starts from the previous step's correction (see CL_OPT_GUESS)
     double lin_rms;           // GMRES tolerance in units of the error test (STB_LIN_RMS)
+    // group block preconditioner: the sensitizers are stored in compact groups of `grp` ions
+    // (grp * s_S = STB_GDIM unknowns) and the block of I - cJ over a whole group is inverted instead
+    // of the single-ion blocks (0: off).  NGinv doubles per system hold the inverses.
+    int grp, NGinv;
+    const stb_process* procs;
 };
+#define STB_GDIM 32           // unknowns of a group block: one warp applies it, lane = row
 
 __device__ __forceinline__ double stb_ipow(double x, int n) {
     double r = 1.0;
@@ -245,6 +251,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     __shared__ double cs[STB_KRYLOV], sn[STB_KRYLOV], gg[STB_KRYLOV + 1], yk_s[STB_KRYLOV];
     __shared__ double red[STB_NW * 4];
     __shared__ double rv[STB_KRED];
+    __shared__ double Gs[STB_GDIM * (STB_GDIM + 1)];    // group block being assembled / inverted
     STB_DYN_SMEM(zs);                // staged gather vector (N doubles) when A.staged, or the TMA ring
 
     const int gid = blockIdx.x / A.G;
@@ -271,6 +278,24 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         r_lo[T] = min(sl_lo[T] * L.R, L.n[T]);
         r_hi[T] = min(sl_hi[T] * L.R, L.n[T]);
     }
+    // group preconditioner: a CTA owns whole groups of sensitizers (type-local rows grp*m .. grp*m + grp-1,
+    // see group_sensitizers: what counts is that no strongly coupled pair is cut by a group boundary)
+    const int grp = A.grp;
+    int n_ch = 0, ch_slot = 0;
+    if (grp) {
+        const int ng = (L.n[0] + grp - 1) / grp;
+        ch_slot = (int)(((int64_t)ng * g.cta) / g.G);
+        n_ch = (int)(((int64_t)ng * (g.cta + 1)) / g.G) - ch_slot;
+        r_lo[0] = min(ch_slot * grp, L.n[0]);
+        r_hi[0] = min((ch_slot + n_ch) * grp, L.n[0]);
+        sl_lo[0] = r_lo[0] / L.R;
+        sl_hi[0] = (r_hi[0] + L.R - 1) / L.R;
+    }
+    // first row (type-local) and ion count of the CTA's group j
+    auto chunk_rows = [&](int j, int& row0, int& m) {
+        row0 = r_lo[0] + j * grp;
+        m = min(grp, r_hi[0] - row0);
+    };
     const int n_own_slices = (sl_hi[0] - sl_lo[0]) + (sl_hi[1] - sl_lo[1]);
 
     // ---- small lattices: make the CTA's own pair rows resident in shared memory ------------
@@ -339,6 +364,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     double* V = wbuf + N;                // [KRYLOV+1][N]
     double* F = V + (int64_t)(STB_KRYLOV + 1) * N;
     double* Minv = F + L.NF;
+    double* Ginv = Minv + A.NMinv;       // [groups][col][row] inverses of the group blocks
 
     const double KAPPA[6] = {0.0, -0.1850, -1.0 / 9.0, -0.0823, -0.0415, 0.0};
     double GAMMA[6], ALPHA[6], ERRC[6];
@@ -399,7 +425,20 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             const double fj = coop_rhs(L, P, T, W, gl, yj, fl);
             if (act) fout[e] = fj;
             if (valid && gl < L.nf[T]) F[L.foff[T] + gl * nT + q] = fl;
-            if (mode == 1) {
+            if (mode == 1 && grp && T == 0) {
+                // group block: keep the ROW of M = I - cJ_qq and the raw residual; the block over the
+                // whole group is assembled, inverted and applied once the CTA's rows are done
+                double am[STB_MAXS];
+                coop_block_row(L, P, T, W, gl, fl, c, am);
+                double* Mp = Minv + q;
+                if (act) {
+#pragma unroll
+                    for (int b = 0; b < STB_MAXS; ++b)
+                        if (b < s) Mp[(int64_t)(gl * s + b) * nT] = am[b];
+                    gv[e] = c * fj - psi[e] - dd[e];
+                    if (!isfinite(fj)) part[1] = 1.0;
+                }
+            } else if (mode == 1) {
                 double ai[STB_MAXS];
                 coop_block_inverse(L, P, T, W, gl, fl, c, ai);
                 double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + q;
@@ -419,8 +458,98 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 }
             }
         };
+        // ---- group blocks (mode 1): B = I - cJ over the grp ions of a group = ion blocks (rows kept
+        //      in Minv) + the S-S pair couplings inside the group at the iterate z (interaction donor
+        //      q, partner k: rate = C g_qk y_q[ii] y_k[fi] moves q: ii -> if, k: fi -> ff), inverted in
+        //      shared memory by the whole CTA (Gauss-Jordan without pivoting: column-diagonally-
+        //      dominant M-matrix), stored and applied to the residual of the group
+        auto group_blocks = [&]() {
+            const int s0 = L.s[0], n0 = L.n[0], GD = STB_GDIM, LD = STB_GDIM + 1;
+            const double* g00 = L.blk[0][0].g[0];
+            const double* yS = z + L.off[0];
+            for (int gq = 0; gq < n_ch; ++gq) {
+                int row0, mg;
+                chunk_rows(gq, row0, mg);
+                __syncthreads();
+                for (int e = threadIdx.x; e < GD * GD; e += STB_NT) {
+                    const int rho = e / GD, gam = e - rho * GD;
+                    const int mq = rho / s0, aq = rho - mq * s0, mk = gam / s0, ak = gam - mk * s0;
+                    const int iq = row0 + mq, ik = row0 + mk;
+                    double v;
+                    if (mq >= mg || mk >= mg) {
+                        v = rho == gam ? 1.0 : 0.0;               // padding of a short group
+                    } else if (mq == mk) {
+                        v = Minv[(int64_t)(aq * s0 + ak) * n0 + iq];
+                    } else {
+                        v = 0.0;
+                        const double gw = g00[(int64_t)iq * L.ld[0] + ik];
+                        for (int p = 0; p < L.n_proc; ++p) {
+                            const stb_process pr = A.procs[p];
+                            if (pr.donor_type != 0 || pr.partner_type != 0 || P.C[p] == 0.0) continue;
+                            const double cg = c * P.C[p] * gw;
+                            if (ak == pr.fi) {            // q donor, k partner: d rate / d y_k[fi]
+                                const double w = cg * yS[pr.ii * n0 + iq];
+                                if (aq == pr.ii) v += w;
+                                if (aq == pr.if_) v -= w;
+                            }
+                            if (ak == pr.ii) {            // k donor, q partner: d rate / d y_k[ii]
+                                const double w = cg * yS[pr.fi * n0 + iq];
+                                if (aq == pr.fi) v += w;
+                                if (aq == pr.ff) v -= w;
+                            }
+                        }
+                    }
+                    Gs[rho * LD + gam] = v;
+                }
+                __syncthreads();
+                for (int p = 0; p < GD; ++p) {
+                    double nv[(GD * GD + STB_NT - 1) / STB_NT];
+                    const double piv = Gs[p * LD + p];
+                    const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+#pragma unroll
+                    for (int u = 0; u < (GD * GD + STB_NT - 1) / STB_NT; ++u) {
+                        const int e = threadIdx.x + u * STB_NT;
+                        if (e < GD * GD) {
+                            const int i = e / GD, j = e - i * GD;
+                            const double aip = Gs[i * LD + p] * inv, apj = Gs[p * LD + j];
+                            nv[u] = i == p ? (j == p ? inv : apj * inv)
+                                           : (j == p ? -aip : fma(-aip, apj, Gs[i * LD + j]));
+                        }
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int u = 0; u < (GD * GD + STB_NT - 1) / STB_NT; ++u) {
+                        const int e = threadIdx.x + u * STB_NT;
+                        if (e < GD * GD) Gs[(e / GD) * LD + (e % GD)] = nv[u];
+                    }
+                    __syncthreads();
+                }
+                double* Gp = Ginv + (int64_t)(ch_slot + gq) * GD * GD;
+                for (int e = threadIdx.x; e < GD * GD; e += STB_NT) {
+                    const int col = e / GD, row = e - col * GD;
+                    Gp[e] = Gs[row * LD + col];
+                }
+                if (warp == 0) {       // x = B^-1 r for the rows of the group, lane = row
+                    const int m = lane / s0, a = lane - m * s0, iq = row0 + m;
+                    const bool ok = m < mg;
+                    const int e = L.off[0] + a * n0 + (ok ? iq : n0 - 1);
+                    const double r = ok ? gv[e] : 0.0;
+                    double acc = 0.0;
+                    for (int col = 0; col < GD; ++col)
+                        acc = fma(Gs[lane * LD + col], __shfl_sync(FULL, r, col), acc);
+                    if (ok) {
+                        const double x = acc / scale[e];
+                        wv[e] = x;
+                        gv[e] = acc;
+                        part[0] = fma(x, x, part[0]);
+                    }
+                }
+            }
+            __syncthreads();
+        };
         if (A.tma) {
             tma_rows(zg, 1.0, rhs_row);
+            if (mode == 1 && grp) group_blocks();
             return;
         }
         for (int task = warp; task < n_own_slices; task += STB_NW) {
@@ -470,6 +599,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 }
             }
         }
+        if (mode == 1 && grp) group_blocks();
     };
 
     // ---- Arnoldi phase: wbuf = Minv (v - c J v) / scale with v = inrm * gv ------------------
@@ -493,15 +623,45 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             const double kj = coop_coupling(L, P, T, W, gl, yj, fvl);
             const double* Mp = Minv + (T ? L.s[0] * L.s[0] * L.n[0] : 0) + qc;
             const int row = gl < s ? gl : 0;
+            if (grp && T == 0) {
+                // group block: B^-1 (I - cJ) v = B^-1 (M v - c k(v)) with the rows of the ion's own
+                // M = I - cJ_qq (kept in Minv); B^-1 is applied when the CTA's rows are done
+                const double vj = gl < s ? inrm * gv[e] : 0.0;
+                double mv = 0.0;
+                for (int b = 0; b < s; ++b)
+                    mv = fma(Mp[(int64_t)(row * s + b) * nT], __shfl_sync(FULL, vj, b, W), mv);
+                if (act) wbuf[e] = mv - c * kj;
+                return;
+            }
             double mk = 0.0;
             for (int b = 0; b < s; ++b)
                 mk = fma(Mp[(int64_t)(row * s + b) * nT], __shfl_sync(FULL, kj, b, W), mk);
             if (act) wbuf[e] = (inrm * gv[e] - c * mk) / scale[e];
         };
+        // wbuf <- B^-1 wbuf / scale over the CTA's own groups, one warp per group, lane = row
+        auto group_apply = [&]() {
+            __syncthreads();
+            const int s0 = L.s[0], n0 = L.n[0], GD = STB_GDIM;
+            for (int gq = warp; gq < n_ch; gq += STB_NW) {
+                int row0, mg;
+                chunk_rows(gq, row0, mg);
+                const int m = lane / s0, a = lane - m * s0, iq = row0 + m;
+                const bool ok = m < mg;
+                const int e = L.off[0] + a * n0 + (ok ? iq : n0 - 1);
+                const double r = ok ? wbuf[e] : 0.0;
+                const double* Gp = Ginv + (int64_t)(ch_slot + gq) * GD * GD + lane;
+                double acc = 0.0;
+#pragma unroll 8
+                for (int col = 0; col < GD; ++col)
+                    acc = fma(__ldcg(Gp + col * GD), __shfl_sync(FULL, r, col), acc);
+                if (ok) wbuf[e] = acc / scale[e];
+            }
+        };
         if (A.tma) {
             long long t0_ = clock64();
             tma_rows(zg, inrm, arn_row);
             if (threadIdx.x == 0) C.prof[6] += clock64() - t0_;
+            if (grp) group_apply();
             return;
         }
         for (int task = warp; task < n_own_slices; task += STB_NW) {
@@ -541,6 +701,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 }
             }
         }
+        if (grp) group_apply();
     };
 
     // dots of `vec` (own elements) against V[0..nv) and itself: rv[i] (i<nv), rv[nv] = <vec,vec>

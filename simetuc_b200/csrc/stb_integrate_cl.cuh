@@ -100,8 +100,8 @@ __host__ __device__ inline void cl_layout(const DevLattice& L, int G, int resmas
     Y.minv = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);
     Y.mcur = take(Y.moff[1] + L.s[1] * L.s[1] * Y.cntm[1]);     // rows of I - c J_qq of the current iterate
     // quad lattices: inverse of I - cJ restricted to every sensitizer quad, [entry][quad]
-    Y.sq = L.quad ? 4 * L.s[0] : 0;
-    Y.nqm = L.quad ? Y.cntm[0] / 4 : 0;
+    Y.sq = L.quad ? L.pcg * L.s[0] : 0;
+    Y.nqm = L.quad ? Y.cntm[0] / L.pcg : 0;
     Y.qinv = take(Y.sq * Y.sq * Y.nqm);
     Y.nfm = L.nf[0] > L.nf[1] ? L.nf[0] : L.nf[1];
     if (Y.nfm < 1) Y.nfm = 1;
@@ -810,14 +810,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     auto minv_apply = [&](int T, int a, int i, const double* r) -> double {
         const int s = L.s[T];
         if (quadpc && T == 0) {
-            // row (i % 4) * s + a of the inverse of the quad's block
-            const int Q = i >> 2, sq = Y.sq;
-            const double* Bp = Qinv + (((i & 3) * s + a) * sq) * Y.nqm + Q;
-            const double* rq = r + ob[0] + 4 * Q;
+            // row (i % pcg) * s + a of the inverse of the group's block; the blocks are stored TRANSPOSED
+            // ([column][row][group]): the threads of a warp own different rows and read consecutive words
+            const int pg = L.pcg, Q = i / pg, sq = Y.sq;
+            const double* Bp = Qinv + ((i - Q * pg) * s + a) * Y.nqm + Q;
+            const double* rq = r + ob[0] + pg * Q;
             double acc = 0.0;
-            for (int m = 0; m < 4; ++m) {
-                if (4 * Q + m >= cnt[0]) break;
-                for (int b = 0; b < s; ++b) acc = fma(Bp[(m * s + b) * Y.nqm], rq[b * cnt[0] + m], acc);
+            for (int m = 0; m < pg; ++m) {
+                if (pg * Q + m >= cnt[0]) break;
+                for (int b = 0; b < s; ++b) acc = fma(Bp[(m * s + b) * sq * Y.nqm], rq[b * cnt[0] + m], acc);
             }
             return acc;
         }
@@ -896,15 +897,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             // blocks of I - cJ over the quads: ion blocks from Mcur, couplings between the ions of a
             // quad from the pair rates, the state at the current iterate and the S-S processes:
             // interaction (donor q, partner k): rate = C g_qk y_q[ii] y_k[fi] moves q: ii -> if, k: fi -> ff
-            const int s0 = L.s[0], sq = Y.sq, cm0 = Y.cntm[0];
-            const int nq = (cnt[0] + 3) >> 2;
+            const int s0 = L.s[0], sq = Y.sq, cm0 = Y.cntm[0], pg = L.pcg;
+            const int nq = (cnt[0] + pg - 1) / pg;
             const double* g00 = L.blk[0][0].g[0];
             const double* yS = zy + Y.zoff[0] + r_lo[0];
             for (int e = tid; e < nq * sq * sq; e += STB_NT) {
                 const int Q = e / (sq * sq), rc = e - Q * sq * sq;
                 const int rho = rc / sq, gam = rc - rho * sq;
                 const int mq = rho / s0, aq = rho - mq * s0, mk = gam / s0, ak = gam - mk * s0;
-                const int iq = 4 * Q + mq, ik = 4 * Q + mk;
+                const int iq = pg * Q + mq, ik = pg * Q + mk;
                 double v;
                 if (iq >= cnt[0] || ik >= cnt[0]) {
                     v = rho == gam ? 1.0 : 0.0;               // padding of the last quad
@@ -929,24 +930,25 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         }
                     }
                 }
-                Qinv[(rho * sq + gam) * Y.nqm + Q] = v;
+                Qinv[(gam * sq + rho) * Y.nqm + Q] = v;       // transposed: (B^T)^-1 = (B^-1)^T
             }
             __syncthreads();
         }
         // 2. in-place Gauss-Jordan of the larger blocks, 64 threads per block (<= 3 entries each), no
         //    pivoting (column-diagonally-dominant M-matrix); compact rolled code: a lane-per-row
         //    shuffle version costs 4-10k cycles per call (tools/ubench.cu), mostly instruction fetch
+        //    (blocks of more than 192 entries, the 32 x 32 group blocks: the whole CTA per block)
         auto gauss_jordan = [&](double* base, int s, int cm, int count) {
-            const int ss = s * s, tl = tid & 63;
+            const int ss = s * s, tpb = ss <= 192 ? 64 : STB_NT, tl = tid % tpb;
             int ei[3], ej[3];
 #pragma unroll
             for (int u = 0; u < 3; ++u) {
-                const int e = tl + 64 * u;
+                const int e = tl + tpb * u;
                 ei[u] = e / s;
                 ej[u] = e - ei[u] * s;
             }
-            for (int blk0 = 0; blk0 < count; blk0 += STB_NT / 64) {
-                const int blk = blk0 + (tid >> 6);
+            for (int blk0 = 0; blk0 < count; blk0 += STB_NT / tpb) {
+                const int blk = blk0 + tid / tpb;
                 const bool act = blk < count;
                 double* Mq = base + (act ? blk : 0);
                 for (int p = 0; p < s; ++p) {
@@ -956,7 +958,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                         const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
 #pragma unroll
                         for (int u = 0; u < 3; ++u) {
-                            const int e = tl + 64 * u;
+                            const int e = tl + tpb * u;
                             if (e < ss) {
                                 const int i = ei[u], j = ej[u];
                                 const double aip = Mq[(i * s + p) * cm] * inv, apj = Mq[(p * s + j) * cm];
@@ -969,7 +971,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                     if (act) {
 #pragma unroll
                         for (int u = 0; u < 3; ++u)
-                            if (tl + 64 * u < ss) Mq[(tl + 64 * u) * cm] = nv[u];
+                            if (tl + tpb * u < ss) Mq[(tl + tpb * u) * cm] = nv[u];
                     }
                     __syncthreads();
                 }
@@ -979,7 +981,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             if (L.s[T] <= 2 || cnt[T] <= 0 || (quadpc && T == 0)) continue;
             gauss_jordan(Minv + Y.moff[T], L.s[T], Y.cntm[T], cnt[T]);
         }
-        if (quadpc && cnt[0] > 0) gauss_jordan(Qinv, Y.sq, Y.nqm, (cnt[0] + 3) >> 2);
+        if (quadpc && cnt[0] > 0) gauss_jordan(Qinv, Y.sq, Y.nqm, (cnt[0] + L.pcg - 1) / L.pcg);
     };
 
     auto apply_change_D = [&](int order) {

@@ -90,7 +90,7 @@ def gmres(A, b, Minv, tol, maxit, stats):
 
 def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=None,
           max_steps=200000, krylov_max=30, eps_lin=0.05, verbose=False, carry_rate=False,
-          verify_every=0):
+          verify_every=0, guess=False):
     """Integrate y' = fun(y) and return y at t_arr (dense output by BDF interpolation).
     jv_factory(y) -> (v -> J(y) v); precond_factory(y, c) -> (r -> M^-1 r), M ~ I - c J."""
     st = Stats()
@@ -123,6 +123,9 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
     n_equal = 0
     newton_tol = max(10 * np.finfo(float).eps / rtol, min(0.03, rtol ** 0.5))
     k_out = 1
+    gfac = 0.0
+    gfac2 = False
+    n_same = 0
     crate = 1.0              # Newton convergence rate carried across steps (LSODA / CVODE practice)
     since_verify = 0
     st.krylov_by_it = [[] for _ in range(NEWTON_MAXITER)]
@@ -135,6 +138,7 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
             if t_new > t_end * (1 + 1e-14) and (t_new - t_end) > 1e-14 * abs(t_end):
                 t_new = t_end
                 change_D(D, order, (t_new - t) / h)
+                gfac *= ((t_new - t) / h) ** (order + 1)
                 n_equal = 0
             h = t_new - t
             y_pred = D[:order + 1].sum(0)
@@ -142,8 +146,8 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
             psi = (D[1:order + 1].T @ GAMMA[1:order + 1]) / ALPHA[order]
             c = h / ALPHA[order]
             # Newton-Krylov
-            d = np.zeros(n)
-            yk = y_pred.copy()
+            d = (gfac * (D[order + 1] + (D[order + 2] if (guess == 2 and gfac2) else 0.0))) if (guess and gfac != 0.0) else np.zeros(n)
+            yk = y_pred + d
             converged = False
             dy_norm_old = None
             Minv = None
@@ -191,6 +195,7 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
                 st.nnewt_fail += 1
                 h *= 0.5
                 change_D(D, order, 0.5)
+                gfac *= 0.5 ** (order + 1)
                 n_equal = 0
                 continue
             n_iter = it + 1
@@ -203,11 +208,14 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
                 factor = max(MIN_FACTOR, safety * err_norm ** (-1 / (order + 1)))
                 h *= factor
                 change_D(D, order, factor)
+                gfac *= factor ** (order + 1)
                 n_equal = 0
             else:
                 step_accepted = True
         st.nsteps += 1
         n_equal += 1
+        gfac2 = (gfac == 1.0)
+        gfac = 1.0
         t_old = t
         t = t_new
         y = yk
@@ -238,6 +246,7 @@ def solve(fun, jv_factory, precond_factory, t_arr, y0, rtol, atol, first_step=No
         factor = min(MAX_FACTOR, safety * np.max(factors))
         h *= factor
         change_D(D, order, factor)
+        gfac = factor ** (order + 1) if delta == 0 else 0.0
         n_equal = 0
         if verbose and st.nsteps % 200 == 0:
             print('step', st.nsteps, 't', t, 'h', h, 'order', order)
