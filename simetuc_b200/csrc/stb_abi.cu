@@ -318,6 +318,7 @@ struct stb_system {
     int sm_count = 148;
     int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
     bool built_with_cells = false;   // the cutoff lists came from the cell-list build
+    bool can16 = false, pcg_auto = true;   // 16-ion preconditioner groups possible / chosen by the restart rule
     bool avg_raw = false;            // the relaxation of a cumulative run: unclipped means (see k_cumtrapz)
     bool avg_cumulative = false;     // stb_integrate_dynamics returns the running time integral of the curves
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
@@ -869,18 +870,24 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     L.off[1] = S->s[0] * S->n[0];
     L.n_proc = n_proc;
     L.quad = quad ? 1 : 0;
-    // ions per preconditioner block of the cluster integrator: the 16-ion groups (blocks of <= 32 unknowns:
-    // 2-state sensitizers) from 192 sensitizers upwards, else the quads.  Measured (profiles/r02_groups.txt):
-    // the reference's 240S/108A benchmark lattice 507 -> 42 ms (quads leave ~18 Krylov iterations per
-    // solve, groups 2.6); Yb-Tm lattices with 600-1100 sensitizers: -15..-22 % Krylov iterations at the same
-    // time (the 32-pivot Gauss-Jordan costs what the iterations save); below, whole groups per CTA unbalance
-    // the cluster (74 sensitizers on 4 CTAs: 32 rows on one of them, pair rows no longer resident: 722 ->
-    // 499 solves/s on the C2 sweep).  STB_PCG=4 / 16 forces the choice.
+    // ions per preconditioner block of the cluster integrator: quads, or the 16-ion groups (blocks of <= 32
+    // unknowns: 2-state sensitizers).  Measured (profiles/r02_groups.txt): on the reference's 240S/108A
+    // benchmark lattice quads leave ~18 Krylov iterations per solve, groups 2.6: 507 -> 42 ms; on Yb-Tm
+    // lattices (1.4-3.6 iterations with quads) groups save 15-22 % of the iterations and cost as much in
+    // 32-pivot Gauss-Jordan sweeps, and whole groups per CTA unbalance small clusters (C2: 334 sensitizers
+    // on 4 CTAs, 96 instead of 84 rows, pair rows no longer all resident: 722 -> 499 solves/s).  So a handle
+    // starts with quads and a launch that needs more than CL_RESTART_ITS iterations per solve after
+    // CL_RESTART_STEPS steps is repeated - and the handle continues - with groups (integrate_cluster).
+    // STB_PCG=4 / 16 fixes the choice.
     L.grp16 = quad && S->n[0] > 4;
     if (const char* env = getenv("STB_GROUP16")) if (atoi(env) == 0) L.grp16 = 0;
-    const bool can16 = L.grp16 && 16 * S->s[0] <= 32;
-    L.pcg = (can16 && S->n[0] >= 192) ? 16 : 4;
-    if (const char* env = getenv("STB_PCG")) L.pcg = (atoi(env) == 16 && can16) ? 16 : 4;
+    S->can16 = L.grp16 && 16 * S->s[0] <= 32;
+    L.pcg = 4;
+    S->pcg_auto = true;
+    if (const char* env = getenv("STB_PCG")) {
+        L.pcg = (atoi(env) == 16 && S->can16) ? 16 : 4;
+        S->pcg_auto = false;
+    }
     S->plane_of_ref.resize(S->N);
     S->ref_of_plane.resize(S->N);
     for (int q = 0; q < n; ++q) {
@@ -1705,12 +1712,12 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         WSC(WS_T, d_t, sizeof(double) * n_t);
     }
     if (own_yout) WSC(WS_YOUT, d_yout, out_bytes);
-    WSC(WS_NEXT, d_next, sizeof(int));
+    WSC(WS_NEXT, d_next, 2 * sizeof(int));        // work queue head, restart request
     WSC(WS_STATS, d_stats, sizeof(stb_stats) * n);
     WSC(WS_PROF, d_prof, sizeof(long long) * 64);
     CKC(ws_events(S));
     CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 64, S->stream));
-    CKC(cudaMemsetAsync(d_next, 0, sizeof(int), S->stream));
+    CKC(cudaMemsetAsync(d_next, 0, 2 * sizeof(int), S->stream));
     CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     double* yout_p = own_yout ? d_yout : y_out;
     CKC(cudaMemsetAsync(yout_p, 0, out_bytes, S->stream));
@@ -1753,6 +1760,11 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.nsteps = nsteps > 0 ? nsteps : 1000;
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.next_sys = d_next;
+    // quads first; a lattice whose quads leave too many Krylov iterations is repeated with 16-ion groups
+    const bool may_restart = L.quad && L.pcg == 4 && S->can16 && S->pcg_auto;
+    A.restart = may_restart ? d_next + 1 : nullptr;
+    A.restart_steps = CL_RESTART_STEPS;
+    A.restart_its = CL_RESTART_ITS;
     A.prof = d_prof;
     S->last_G = plan.G; S->last_groups = plan.n_clusters;
     if (getenv("STB_VERBOSE"))
@@ -1808,6 +1820,16 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     // handle (other host threads) then wait for this solve to finish.
     CKC(cudaStreamSynchronize(S->stream));
     tm.mark("sync_kernels");
+    if (may_restart) {
+        int req = 0;
+        CKC(copy_on(S->stream, &req, d_next + 1, sizeof(int), cudaMemcpyDeviceToHost));
+        if (req) {
+            S->hL.pcg = 16;
+            CKC(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
+            CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
+            return STB_RESTART_GROUPS;
+        }
+    }
     if (avg_out) {
         if (!dev)
             CKC(cudaMemcpyAsync(avg_out, d_avg, sizeof(double) * (size_t)n * n_t * (L.s[0] + L.s[1]),
@@ -1898,9 +1920,19 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
             else if (atoi(env) != 0 && plan.G > 0) use_cl = true;
         }
         tm.mark("cl_choose");
-        if (use_cl)
-            return integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
-                                     avg_out, stats, dev);
+        if (use_cl) {
+            rc = integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
+                                   avg_out, stats, dev);
+            if (rc != STB_RESTART_GROUPS) return rc;
+            // the handle now uses the 16-ion groups (and keeps them): plan and run again
+            const float ms_quads = S->last_ms;          // the abandoned launch counts in the reported time
+            if (!cl_choose(S, n, plan))
+                return fail(STB_ESTATE, "no cluster plan for the 16-ion groups");
+            rc = integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
+                                   avg_out, stats, dev);
+            S->last_ms += ms_quads;
+            return rc;
+        }
     }
     if (S->hL.n_coop && L.lpr < 32)
         return fail(STB_EINVAL, "cooperative energy transfer in the grid integrator needs rows handled by whole "
@@ -1995,12 +2027,12 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     }
     if (own_yout) WSI(WS_YOUT, d_yout, out_bytes);
     WSI(WS_PART, d_part, sizeof(double) * (size_t)n_groups * 2 * G * STB_KRED);
-    WSI(WS_BAR, d_bar, sizeof(unsigned long long) * n_groups);
+    WSI(WS_BAR, d_bar, sizeof(unsigned long long) * ((size_t)n_groups + (size_t)n_groups * G));    // + neighbour flags
     WSI(WS_STATS, d_stats, sizeof(stb_stats) * n);
     WSI(WS_PROF, d_prof, sizeof(long long) * 8 * n);
     CKI(ws_events(S));
     CKI(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 8 * n, S->stream));
-    CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * n_groups, S->stream));
+    CKI(cudaMemsetAsync(d_bar, 0, sizeof(unsigned long long) * ((size_t)n_groups + (size_t)n_groups * G), S->stream));
     CKI(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     CKI(cudaMemsetAsync(d_work, 0, sizeof(double) * (size_t)n_groups * work_stride, S->stream));
     double* yout_p = own_yout ? d_yout : y_out;

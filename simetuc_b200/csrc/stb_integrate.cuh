@@ -30,6 +30,10 @@
 // rejected step or a failed Newton iteration the next CL_LIN_TIGHT_STEPS accepted steps use STB_LIN_RMS
 // (240S/108A: 489 -> 511 ms; C2 sweep 675 -> 731 solves/s; profiles/r02_lin_tol.txt).
 #define CL_LIN_TIGHT_STEPS 40
+// quads -> 16-ion groups (see stb_system_create): iterations per linear solve over windows of this many steps
+#define CL_RESTART_STEPS 48
+#define CL_RESTART_ITS 5.0
+#define STB_RESTART_GROUPS 1000     // internal return code of integrate_cluster
 // The Newton convergence rate is carried across steps (LSODA / CVODE `crate`): a step whose first
 // update already satisfies 1.5 * min(1, crate) * ||dy|| < newton_tol is accepted without a second
 // residual evaluation; every STB_VERIFY_EVERY such steps a second iteration is forced, which
@@ -87,6 +91,7 @@ struct Ctl {
     double pc_c;              // c of the step the lagged block inverses were factored at
     int pc_age, pc_refresh;   // steps since then; factor them in this Newton iteration
     int lin_tight;            // accepted steps still to be solved with the tight GMRES tolerance
+    long long chk_jv, chk_lin;   // counters at the last check of the restart rule (CL_RESTART_STEPS)
     double RU[(STB_MAXORD + 1) * (STB_MAXORD + 1)];
     double p[STB_MAXORD + 1];
     int order, n_equal, status, kk, flag, flag2, newton_it, n_iter, since_verify;
@@ -252,6 +257,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     __shared__ double red[STB_NW * 4];
     __shared__ double rv[STB_KRED];
     __shared__ double Gs[STB_GDIM * (STB_GDIM + 1)];    // group block being assembled / inverted
+    __shared__ int ss_n, ss_st[STB_MAX_PROC][4];        // active S-S processes of the system (ii, fi, if, ff) ...
+    __shared__ double ss_C[STB_MAX_PROC];               // ... and their strengths: the couplings inside a group
     STB_DYN_SMEM(zs);                // staged gather vector (N doubles) when A.staged, or the TMA ring
 
     const int gid = blockIdx.x / A.G;
@@ -278,19 +285,48 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         r_lo[T] = min(sl_lo[T] * L.R, L.n[T]);
         r_hi[T] = min(sl_hi[T] * L.R, L.n[T]);
     }
-    // group preconditioner: a CTA owns whole groups of sensitizers (type-local rows grp*m .. grp*m + grp-1,
-    // see group_sensitizers: what counts is that no strongly coupled pair is cut by a group boundary)
+    // group preconditioner: a CTA owns - as vectors: Krylov basis, dot products, preconditioner - whole
+    // groups of sensitizers (type-local rows grp*m .. grp*m + grp-1, see group_sensitizers: what counts is
+    // that no strongly coupled pair is cut by a group boundary).  The PAIR PASS keeps the split balanced to
+    // a row (pr_lo .. pr_hi: whole groups per CTA cost 14-20 % of a pass on the C1 lattices): rows near a
+    // boundary are streamed by one CTA and post-processed by its neighbour, which waits for it
+    // (neighbour_sync) - both ranges differ by less than a group, so only adjacent CTAs are involved.
     const int grp = A.grp;
     int n_ch = 0, ch_slot = 0;
+    int pr_lo[2] = {r_lo[0], r_lo[1]}, pr_hi[2] = {r_hi[0], r_hi[1]};
+    bool split = false;
     if (grp) {
         const int ng = (L.n[0] + grp - 1) / grp;
         ch_slot = (int)(((int64_t)ng * g.cta) / g.G);
         n_ch = (int)(((int64_t)ng * (g.cta + 1)) / g.G) - ch_slot;
         r_lo[0] = min(ch_slot * grp, L.n[0]);
         r_hi[0] = min((ch_slot + n_ch) * grp, L.n[0]);
-        sl_lo[0] = r_lo[0] / L.R;
-        sl_hi[0] = (r_hi[0] + L.R - 1) / L.R;
+        // (not with the release-only barriers of the staged mode: the rows a neighbour post-processes are
+        //  read by plain loads)
+        split = g.G > 1 && !A.staged && L.n[0] / g.G >= 2 * grp;
+        if (!split) {
+            pr_lo[0] = r_lo[0];
+            pr_hi[0] = r_hi[0];
+            sl_lo[0] = r_lo[0] / L.R;
+            sl_hi[0] = (r_hi[0] + L.R - 1) / L.R;
+        }
     }
+    // the CTA's pass rows are written: wait until the two neighbours have written theirs (same flavour as
+    // group_sync: the fences make the neighbours' rows visible to plain loads)
+    unsigned long long* nb_flags = A.bar + A.n_groups + (int64_t)gid * A.G;
+    unsigned long long nb_epoch = 0;
+    auto neighbour_sync = [&]() {
+        __syncthreads();
+        nb_epoch += 1;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(nb_flags + g.cta), "l"(nb_epoch) : "memory");
+            if (g.cta > 0) while (ld_acquire_u64(nb_flags + g.cta - 1) < nb_epoch) { }
+            if (g.cta + 1 < g.G) while (ld_acquire_u64(nb_flags + g.cta + 1) < nb_epoch) { }
+            __threadfence();
+        }
+        __syncthreads();
+    };
     // first row (type-local) and ion count of the CTA's group j
     auto chunk_rows = [&](int j, int& row0, int& m) {
         row0 = r_lo[0] + j * grp;
@@ -401,7 +437,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     TmaRing R;
     if (A.tma) tma_ring_init(R, zs, A.tma_kc, A.tma_stages, 0);
     auto tma_rows = [&](const double* zg, double fscale, auto&& epi) {
-        tma_rows_pass(R, L, r_lo, r_hi, 1, zg, fscale, warp, lane, epi);   // activator rows first
+        tma_rows_pass(R, L, pr_lo, pr_hi, 1, zg, fscale, warp, lane, epi);   // activator rows first
     };
     auto rhs_phase = [&](const double* z, double* fout, int mode, double c, double (&part)[2]) {
         part[0] = 0.0;
@@ -463,7 +499,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         //      q, partner k: rate = C g_qk y_q[ii] y_k[fi] moves q: ii -> if, k: fi -> ff), inverted in
         //      shared memory by the whole CTA (Gauss-Jordan without pivoting: column-diagonally-
         //      dominant M-matrix), stored and applied to the residual of the group
-        auto group_blocks = [&]() {
+        //      Without the TMA ring: the whole CTA per group, one tile.
+        auto group_blocks_cta = [&]() {
             const int s0 = L.s[0], n0 = L.n[0], GD = STB_GDIM, LD = STB_GDIM + 1;
             const double* g00 = L.blk[0][0].g[0];
             const double* yS = z + L.off[0];
@@ -483,19 +520,18 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                     } else {
                         v = 0.0;
                         const double gw = g00[(int64_t)iq * L.ld[0] + ik];
-                        for (int p = 0; p < L.n_proc; ++p) {
-                            const stb_process pr = A.procs[p];
-                            if (pr.donor_type != 0 || pr.partner_type != 0 || P.C[p] == 0.0) continue;
-                            const double cg = c * P.C[p] * gw;
-                            if (ak == pr.fi) {            // q donor, k partner: d rate / d y_k[fi]
-                                const double w = cg * yS[pr.ii * n0 + iq];
-                                if (aq == pr.ii) v += w;
-                                if (aq == pr.if_) v -= w;
+                        for (int p = 0; p < ss_n; ++p) {
+                            const int p_ii = ss_st[p][0], p_fi = ss_st[p][1], p_if = ss_st[p][2], p_ff = ss_st[p][3];
+                            const double cg = c * ss_C[p] * gw;
+                            if (ak == p_fi) {            // q donor, k partner: d rate / d y_k[fi]
+                                const double w = cg * yS[p_ii * n0 + iq];
+                                if (aq == p_ii) v += w;
+                                if (aq == p_if) v -= w;
                             }
-                            if (ak == pr.ii) {            // k donor, q partner: d rate / d y_k[ii]
-                                const double w = cg * yS[pr.fi * n0 + iq];
-                                if (aq == pr.fi) v += w;
-                                if (aq == pr.ff) v -= w;
+                            if (ak == p_ii) {            // k donor, q partner: d rate / d y_k[ii]
+                                const double w = cg * yS[p_fi * n0 + iq];
+                                if (aq == p_fi) v += w;
+                                if (aq == p_ff) v -= w;
                             }
                         }
                     }
@@ -547,8 +583,118 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             }
             __syncthreads();
         };
+        //      TMA passes: one warp per group, lane = row, tile in shared memory - the ring is idle between
+        //      two passes and holds a tile per warp
+        auto group_blocks_warp = [&]() {
+            const int s0 = L.s[0], n0 = L.n[0], GD = STB_GDIM, LD = STB_GDIM + 1;
+            const double* g00 = L.blk[0][0].g[0];
+            const double* yS = z + L.off[0];
+            const int nt = min(STB_NW, (int)(tma_ring_bytes(A.tma_kc, A.tma_stages) / (GD * LD * sizeof(double))));
+            __syncthreads();
+            if (warp < nt) {
+                double* Tq = R.ring + warp * GD * LD;
+                const int mq = lane / s0, aq = lane - mq * s0;
+                for (int gq = warp; gq < n_ch; gq += nt) {
+                    int row0, mg;
+                    chunk_rows(gq, row0, mg);
+                    const bool ok = mq < mg;
+                    const int iq = ok ? row0 + mq : row0;
+                    // row `lane` of the block: identity / ion block first, then the couplings to the other
+                    // ions of the group (their pair rates are loaded eight at a time: independent loads)
+                    for (int gam = 0; gam < GD; ++gam) Tq[lane * LD + gam] = lane == gam ? 1.0 : 0.0;
+                    double yq[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) yq[a] = (ok && a < s0) ? yS[a * n0 + iq] : 0.0;
+                    if (ok) {
+                        for (int ak = 0; ak < s0; ++ak)
+                            Tq[lane * LD + mq * s0 + ak] = Minv[(int64_t)(aq * s0 + ak) * n0 + iq];
+                        for (int mk0 = 0; mk0 < mg; mk0 += 8) {
+                            double gw[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int mk = mk0 + u;
+                                gw[u] = (mk < mg && mk != mq) ? g00[(int64_t)iq * L.ld[0] + row0 + mk] : 0.0;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                const int mk = mk0 + u;
+                                if (mk >= mg || mk == mq) continue;
+                                for (int ak = 0; ak < s0; ++ak) {
+                                    double v = 0.0;
+                                    for (int p = 0; p < ss_n; ++p) {
+                                        const int p_ii = ss_st[p][0], p_fi = ss_st[p][1], p_if = ss_st[p][2], p_ff = ss_st[p][3];
+                                        const double cg = c * ss_C[p] * gw[u];
+                                        if (ak == p_fi) {            // q donor, k partner: d rate / d y_k[fi]
+                                            const double w = cg * yq[p_ii];
+                                            if (aq == p_ii) v += w;
+                                            if (aq == p_if) v -= w;
+                                        }
+                                        if (ak == p_ii) {            // k donor, q partner: d rate / d y_k[ii]
+                                            const double w = cg * yq[p_fi];
+                                            if (aq == p_fi) v += w;
+                                            if (aq == p_ff) v -= w;
+                                        }
+                                    }
+                                    Tq[lane * LD + mk * s0 + ak] = v;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    // in-place Gauss-Jordan: the pivot row is scaled by the lanes (one column each), then
+                    // every other lane eliminates the pivot column from its own row
+                    for (int p = 0; p < GD; ++p) {
+                        const double piv = Tq[p * LD + p];
+                        const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+                        const double fr = Tq[lane * LD + p];
+                        __syncwarp();
+                        Tq[p * LD + lane] = lane == p ? inv : Tq[p * LD + lane] * inv;
+                        __syncwarp();
+                        if (lane != p) {
+                            // eight columns at a time: the loads of a chunk are independent of its stores
+                            for (int j0 = 0; j0 < GD; j0 += 8) {
+                                double pj[8], ow[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    pj[u] = Tq[p * LD + j0 + u];
+                                    ow[u] = Tq[lane * LD + j0 + u];
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    Tq[lane * LD + j0 + u] = j0 + u == p ? -fr * pj[u] : fma(-fr, pj[u], ow[u]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    double* Gp = Ginv + (int64_t)(ch_slot + gq) * GD * GD;
+                    const int e = L.off[0] + aq * n0 + (ok ? iq : n0 - 1);
+                    const double r = ok ? gv[e] : 0.0;
+                    double acc = 0.0;
+                    for (int col = 0; col < GD; ++col) {
+                        const double bv = Tq[lane * LD + col];
+                        Gp[col * GD + lane] = bv;
+                        acc = fma(bv, __shfl_sync(FULL, r, col), acc);      // x = B^-1 r, lane = row
+                    }
+                    if (ok) {
+                        const double x = acc / scale[e];
+                        wv[e] = x;
+                        gv[e] = acc;
+                        part[0] = fma(x, x, part[0]);
+                    }
+                    __syncwarp();
+                }
+            }
+            // the next pass writes the ring through the async proxy
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+        };
+        auto group_blocks = [&]() {
+            if (A.tma) group_blocks_warp();
+            else group_blocks_cta();
+        };
         if (A.tma) {
             tma_rows(zg, 1.0, rhs_row);
+            if (split) neighbour_sync();
             if (mode == 1 && grp) group_blocks();
             return;
         }
@@ -599,6 +745,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 }
             }
         }
+        if (split) neighbour_sync();
         if (mode == 1 && grp) group_blocks();
     };
 
@@ -653,7 +800,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 double acc = 0.0;
 #pragma unroll 8
                 for (int col = 0; col < GD; ++col)
-                    acc = fma(__ldcg(Gp + col * GD), __shfl_sync(FULL, r, col), acc);
+                    acc = fma(Gp[col * GD], __shfl_sync(FULL, r, col), acc);     // (written by this CTA only)
                 if (ok) wbuf[e] = acc / scale[e];
             }
         };
@@ -661,6 +808,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             long long t0_ = clock64();
             tma_rows(zg, inrm, arn_row);
             if (threadIdx.x == 0) C.prof[6] += clock64() - t0_;
+            if (split) neighbour_sync();
             if (grp) group_apply();
             return;
         }
@@ -701,6 +849,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 }
             }
         }
+        if (split) neighbour_sync();
         if (grp) group_apply();
     };
 
@@ -745,6 +894,20 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         const double* y0 = A.y0 + (int64_t)sysl * N;
         double* y_out = A.y_out + (int64_t)sysl * A.n_t * N;
         const double rtol = A.rtol, atol = A.atol;
+        if (grp) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int m = 0;
+                for (int p = 0; p < L.n_proc; ++p) {
+                    const stb_process pr = A.procs[p];
+                    if (pr.donor_type != 0 || pr.partner_type != 0 || P.C[p] == 0.0) continue;
+                    ss_st[m][0] = pr.ii; ss_st[m][1] = pr.fi; ss_st[m][2] = pr.if_; ss_st[m][3] = pr.ff;
+                    ss_C[m] = P.C[p];
+                    ++m;
+                }
+                ss_n = m;
+            }
+        }
         if (threadIdx.x == 0) {
             C.t = A.t[0];
             C.t_end = A.t[A.n_t - 1];

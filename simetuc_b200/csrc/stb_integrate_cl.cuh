@@ -157,6 +157,12 @@ struct ClArgs {
     int piece_fix;                 // ... and the fixed cost of a piece, in steps (CL_PIECE_FIX)
     double lin_rms;                // GMRES tolerance in units of the error test (CL_LIN_RMS) ...
     int lin_tight_steps;           // ... tightened to STB_LIN_RMS for this many steps after a rejection
+    // quads that do not hold the Krylov iterations down: a system that has needed more than restart_its
+    // iterations per linear solve over a window of restart_steps steps stops with status 4 and raises *restart; the
+    // host repeats the launch with the 16-ion groups (null: never)
+    int* restart;
+    int restart_steps;
+    double restart_its;
     int pc_maxage;                 // lagged block inverses: refresh after this many steps ...
     double pc_drift;               // ... or when |c / c_factored - 1| exceeds this (CL_PC_MAXAGE, CL_PC_DRIFT)
     int compact;                   // layout without the per-element work vectors (k_integrate_cl2_t)
@@ -1032,6 +1038,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
             C.tol_lin = tol_loose;
             C.lin_tight = 0;
+            C.chk_jv = 0;
+            C.chk_lin = 0;
             C.crate = 1.0;
             C.since_verify = 0;
             C.gfac = 0.0;
@@ -1516,6 +1524,15 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 }
                 if (lane == 0) {
                     C.st.n_steps += 1;
+                    if (A.restart && C.st.n_steps % A.restart_steps == 0) {
+                        // iterations per linear solve over the last restart_steps steps
+                        if ((double)(C.st.n_jv - C.chk_jv) > A.restart_its * (double)(C.st.n_lin - C.chk_lin)) {
+                            C.status = 4;
+                            *A.restart = 1;
+                        }
+                        C.chk_jv = C.st.n_jv;
+                        C.chk_lin = C.st.n_lin;
+                    }
                     C.steps_since_out = wrote ? 1 : C.steps_since_out + 1;
                     C.k_out = k_out_l;
                     C.st.n_out = k_out_l;

@@ -163,7 +163,7 @@ class RateSystem:
         return out
 
     def get_option(self, name: str) -> float:
-        """`stb_get_option`: 'sm_budget', 'quad', 'cell_lists'."""
+        """`stb_get_option`: 'sm_budget', 'quad', 'pc_group', 'cell_lists'."""
         out = C.c_double()
         _lib.check(self.lib.stb_get_option(self.handle, name.encode(), C.byref(out)))
         return float(out.value)

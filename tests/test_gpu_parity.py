@@ -565,3 +565,67 @@ def test_tma_kernels_single_species(monkeypatch):
             assert np.all(np.abs(res[mode][1][b] - jv_ref) <= 1e-12 * np.abs(jv_ref).max())
     assert np.array_equal(res['0'][0], res['1'][0]) and np.array_equal(res['0'][1], res['1'][1])
     system.close()
+
+
+def test_group_preconditioners_agree(monkeypatch):
+    """Block preconditioners over groups of 16 sensitizers (32 x 32 blocks): they change the Krylov
+    iteration counts, never the solution.  Grid integrator with and without them, cluster integrator with
+    quads and with groups - all four on the reference's 240S/108A lattice, against the committed oracle
+    trajectory (`|delta| <= 1e-4 |ref| + 1e-12`), and the iteration counts must drop."""
+    g = load_golden('240S_108A')
+    with np.load(os.path.join(GOLDEN, 'traj_fix240.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    t_sol = gold['t_sol']
+    t_pulse = np.linspace(0.0, t_sol[0], 2)
+    jv = {}
+    for key, env in (('grid', {'STB_CLUSTER': '0', 'STB_GRID_GROUPS': '0'}),
+                     ('grid+groups', {'STB_CLUSTER': '0', 'STB_GRID_GROUPS': '1'}),
+                     ('cluster quads', {'STB_CLUSTER': '1', 'STB_PCG': '4'}),
+                     ('cluster groups', {'STB_CLUSTER': '1', 'STB_PCG': '16'})):
+        for k in ('STB_CLUSTER', 'STB_GRID_GROUPS', 'STB_PCG'):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        system = make_system(g, configs.sim_cte())
+        assert system.get_option('pc_group') == (16 if key == 'cluster groups' else 4)
+        _, _, pop = system.ground_states()
+        _, y, avg, st_p, st = system.integrate_dynamics(t_pulse, t_sol, pop.astype(float), rtol=1e-8, atol=1e-15,
+                                                        nsteps=100000, want_y=True)
+        assert st[0]['status'] == 0 and st_p[0]['status'] == 0, key
+        ref = gold['y_rows']
+        assert np.all(np.abs(y[0][gold['rows']] - ref) <= 1e-4 * np.abs(ref) + 1e-12), key
+        jv[key] = st[0]['n_jv']
+        system.close()
+    assert jv['grid+groups'] * 10 < jv['grid'] and jv['cluster groups'] * 10 < jv['cluster quads'], jv
+
+
+def test_cluster_switches_to_groups_when_quads_struggle(monkeypatch):
+    """A handle starts with quads; a launch whose quads leave more than CL_RESTART_ITS Krylov iterations per
+    linear solve is repeated with the 16-ion groups, and the handle keeps them (stb_abi.cu,
+    integrate_cluster).  The 240S/108A lattice with the test parameters is such a case; a Yb-Tm lattice
+    at 5 % Yb is not."""
+    monkeypatch.delenv('STB_PCG', raising=False)
+    monkeypatch.setenv('STB_CLUSTER', '1')
+    g = load_golden('240S_108A')
+    with np.load(os.path.join(GOLDEN, 'traj_fix240.npz')) as z:
+        gold = {k: z[k] for k in z.files}
+    system = make_system(g, configs.sim_cte())
+    assert system.get_option('pc_group') == 4
+    _, _, pop = system.ground_states()
+    t_sol = gold['t_sol']
+    _, y, _, _, st = system.integrate_dynamics(np.linspace(0.0, t_sol[0], 2), t_sol, pop.astype(float), rtol=1e-8,
+                                               atol=1e-15, nsteps=100000, want_y=True)
+    assert st[0]['status'] == 0
+    assert system.get_option('pc_group') == 16
+    assert st[0]['n_jv'] < 5 * st[0]['n_lin']
+    ref = gold['y_rows']
+    assert np.all(np.abs(y[0][gold['rows']] - ref) <= 1e-4 * np.abs(ref) + 1e-12)
+    system.close()
+    cte = configs.yb_tm_cte(N_uc=8, S_conc=5.0, A_conc=0.5, power_dens=1e7, t_pulse=1e-8)
+    system = precalculate.build_system(cte, lattice.generate(cte, seed=5), n_sys=1)
+    _, _, pop = system.ground_states()
+    t_sol = np.logspace(-8, -2, 200)
+    _, _, _, _, st = system.integrate_dynamics(np.linspace(0.0, 1e-8, 2), t_sol, pop.astype(float), rtol=1e-8,
+                                               atol=1e-15, want_y=False)
+    assert st[0]['status'] == 0 and system.get_option('pc_group') == 4
+    system.close()

@@ -69,4 +69,6 @@ for n_uc in big:
         print('C1 N_uc %d (%d ions) groups %s: %.1f ms (build %.2f s) steps %d rhs %d jv %d rej %d nf %d status %d | curves vs groups 0: %.2e' % (
             n_uc, system.n_ions, grp, ms, t_build, st[0]['n_steps'], st_p[0]['n_rhs'] + st[0]['n_rhs'],
             st_p[0]['n_jv'] + st[0]['n_jv'], st[0]['n_rejected'], st[0]['n_newton_fail'], st[0]['status'], c), flush=True)
+        prof = system.last_profile()
+        print('   cycles (M):', {k: round(v / 1e6, 1) for k, v in prof.items() if k not in ('G', 'groups')}, flush=True)
         system.close()
