@@ -318,13 +318,14 @@ struct stb_system {
     int sm_count = 148;
     int sm_budget = 148;     // SMs one solve of this handle may occupy (stb_set_option "sm_budget")
     bool built_with_cells = false;   // the cutoff lists came from the cell-list build
+    std::vector<int> restart_list;         // systems of the last launch that asked for the 16-ion groups
     bool can16 = false, pcg_auto = true;   // 16-ion preconditioner groups possible / chosen by the restart rule
     bool avg_raw = false;            // the relaxation of a cumulative run: unclipped means (see k_cumtrapz)
     bool avg_cumulative = false;     // stb_integrate_dynamics returns the running time integral of the curves
     // integrator workspace: grow-only device buffers kept for the life of the handle, so a solve
     // issues no cudaMalloc / cudaFree (both synchronise the device and jitter by tens of ms)
     enum { WS_WORK, WS_Y0, WS_TMP, WS_T, WS_YOUT, WS_AVG, WS_NEXT, WS_STATS, WS_PROF, WS_PART, WS_BAR,
-           WS_DYN_T, WS_DYN_TMP, WS_DYN_Y0, WS_DYN_YP, WS_DYN_YS, WS_DYN_AVG, WS_COUNT };
+           WS_DYN_T, WS_DYN_TMP, WS_DYN_Y0, WS_DYN_YP, WS_DYN_YS, WS_DYN_AVG, WS_LIST, WS_COUNT };
     void* ws_ptr[WS_COUNT] = {};
     size_t ws_cap[WS_COUNT] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -876,9 +877,10 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     // lattices (1.4-3.6 iterations with quads) groups save 15-22 % of the iterations and cost as much in
     // 32-pivot Gauss-Jordan sweeps, and whole groups per CTA unbalance small clusters (C2: 334 sensitizers
     // on 4 CTAs, 96 instead of 84 rows, pair rows no longer all resident: 722 -> 499 solves/s).  So a handle
-    // starts with quads and a launch that needs more than CL_RESTART_ITS iterations per solve after
-    // CL_RESTART_STEPS steps is repeated - and the handle continues - with groups (integrate_cluster).
-    // STB_PCG=4 / 16 fixes the choice.
+    // starts with quads.  A single system that needs more than CL_RESTART_ITS iterations per solve over a
+    // window of CL_RESTART_STEPS steps (within its first CL_RESTART_LAST steps) is stopped and solved again -
+    // and the handle continues - with groups; a batch is never stopped, but switches for its next launches
+    // when its systems averaged more than CL_BATCH_ITS (integrate_cluster).  STB_PCG=4 / 16 fixes the choice.
     L.grp16 = quad && S->n[0] > 4;
     if (const char* env = getenv("STB_GROUP16")) if (atoi(env) == 0) L.grp16 = 0;
     S->can16 = L.grp16 && 16 * S->s[0] <= 32;
@@ -1680,7 +1682,10 @@ static bool cl_choose(stb_system* S, int n, ClPlan& plan) {
 
 static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, int32_t n, int32_t pulse,
                              int64_t n_t, const double* t, const double* y0, double rtol, double atol,
-                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats, bool dev) {
+                             int64_t nsteps, double* y_out, double* avg_out, stb_stats* stats, bool dev,
+                             const std::vector<int>* list = nullptr) {
+    // list: solve only these systems of the batch (local indices); the others keep the results of the
+    // previous launch in the workspace (second pass of the quads -> groups rule)
     const int N = S->N;
     const DevLattice& L = S->hL;
     HostTimer tm;
@@ -1718,9 +1723,19 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     CKC(ws_events(S));
     CKC(cudaMemsetAsync(d_prof, 0, sizeof(long long) * 64, S->stream));
     CKC(cudaMemsetAsync(d_next, 0, 2 * sizeof(int), S->stream));
-    CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
     double* yout_p = own_yout ? d_yout : y_out;
-    CKC(cudaMemsetAsync(yout_p, 0, out_bytes, S->stream));
+    int* d_list = nullptr;
+    if (!list) {
+        CKC(cudaMemsetAsync(d_stats, 0, sizeof(stb_stats) * n, S->stream));
+        CKC(cudaMemsetAsync(yout_p, 0, out_bytes, S->stream));
+    } else {
+        for (int k : *list) {
+            CKC(cudaMemsetAsync(d_stats + k, 0, sizeof(stb_stats), S->stream));
+            CKC(cudaMemsetAsync(yout_p + (size_t)k * n_t * N, 0, sizeof(double) * (size_t)n_t * N, S->stream));
+        }
+        WSC(WS_LIST, d_list, sizeof(int) * list->size());
+        CKC(copy_on(S->stream, d_list, list->data(), sizeof(int) * list->size(), cudaMemcpyHostToDevice));
+    }
     const double *t_p = t, *y0_p = y0;
     if (!dev) {
         CKC(cudaMemcpyAsync(d_t, t, sizeof(double) * n_t, cudaMemcpyHostToDevice, S->stream));
@@ -1761,7 +1776,14 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.y_out = yout_p; A.stats = d_stats; A.work = d_work; A.work_stride = work_stride;
     A.next_sys = d_next;
     // quads first; a lattice whose quads leave too many Krylov iterations is repeated with 16-ion groups
-    const bool may_restart = L.quad && L.pcg == 4 && S->can16 && S->pcg_auto;
+    A.sys_list = d_list;
+    A.n_list = list ? (int)list->size() : 0;
+    // (a single system: stopped and solved again as soon as it shows; a batch: never stopped - one stiff
+    //  candidate of a parameter scan must not cost the others their launch - but if its systems needed
+    //  more than CL_BATCH_ITS iterations per solve on average, the handle uses the groups from the next
+    //  launch on)
+    const bool may_switch = !list && L.quad && L.pcg == 4 && S->can16 && S->pcg_auto;
+    const bool may_restart = may_switch && n == 1;
     A.restart = may_restart ? d_next + 1 : nullptr;
     A.restart_steps = CL_RESTART_STEPS;
     A.restart_its = CL_RESTART_ITS;
@@ -1824,10 +1846,21 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         int req = 0;
         CKC(copy_on(S->stream, &req, d_next + 1, sizeof(int), cudaMemcpyDeviceToHost));
         if (req) {
+            std::vector<stb_stats> hs(n);
+            CKC(copy_on(S->stream, hs.data(), d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost));
+            S->restart_list.clear();
+            for (int k = 0; k < n; ++k) if (hs[k].status == 4) S->restart_list.push_back(k);
+            CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
+            if (!S->restart_list.empty()) return STB_RESTART_GROUPS;
+        }
+    } else if (may_switch && !pulse) {
+        std::vector<stb_stats> hs(n);
+        CKC(copy_on(S->stream, hs.data(), d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost));
+        double jv = 0.0, lin = 0.0;
+        for (const stb_stats& h : hs) { jv += (double)h.n_jv; lin += (double)h.n_lin; }
+        if (jv > CL_BATCH_ITS * lin) {
             S->hL.pcg = 16;
             CKC(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
-            CKC(cudaEventElapsedTime(&S->last_ms, e0, e1));
-            return STB_RESTART_GROUPS;
         }
     }
     if (avg_out) {
@@ -1925,11 +1958,21 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
                                    avg_out, stats, dev);
             if (rc != STB_RESTART_GROUPS) return rc;
             // the handle now uses the 16-ion groups (and keeps them): plan and run again
-            const float ms_quads = S->last_ms;          // the abandoned launch counts in the reported time
-            if (!cl_choose(S, n, plan))
+            // the systems that asked for it are solved again with the 16-ion groups.  All of them: the
+            // handle keeps the groups; some of a batch: the next launch starts with quads again
+            const float ms_quads = S->last_ms;          // the abandoned work counts in the reported time
+            const std::vector<int> again = S->restart_list;
+            const bool all = (int)again.size() == n;
+            S->hL.pcg = 16;
+            CK(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
+            if (!cl_choose(S, (int)again.size(), plan))
                 return fail(STB_ESTATE, "no cluster plan for the 16-ion groups");
             rc = integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
-                                   avg_out, stats, dev);
+                                   avg_out, stats, dev, all ? nullptr : &again);
+            if (!all) {
+                S->hL.pcg = 4;
+                CK(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
+            }
             S->last_ms += ms_quads;
             return rc;
         }
@@ -2059,8 +2102,10 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     A.guess = 1;
     A.grp = grp; A.NGinv = NGinv; A.procs = S->d_procs;
-    A.lin_rms = STB_LIN_RMS;
+    A.lin_rms = GRID_LIN_RMS;
+    A.lin_tight_steps = CL_LIN_TIGHT_STEPS;
     if (const char* env = getenv("STB_LIN_RMS_GRID")) A.lin_rms = std::max(1e-6, atof(env));
+    if (const char* env = getenv("STB_LIN_TIGHT_STEPS")) A.lin_tight_steps = std::max(0, atoi(env));
     if (const char* env = getenv("STB_CL_OPTS")) A.guess = atoi(env) & CL_OPT_GUESS;
     S->last_G = G; S->last_groups = n_groups;
     cudaEvent_t e0 = S->ev0, e1 = S->ev1;

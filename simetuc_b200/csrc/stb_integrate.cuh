@@ -30,9 +30,13 @@
 // rejected step or a failed Newton iteration the next CL_LIN_TIGHT_STEPS accepted steps use STB_LIN_RMS
 // (240S/108A: 489 -> 511 ms; C2 sweep 675 -> 731 solves/s; profiles/r02_lin_tol.txt).
 #define CL_LIN_TIGHT_STEPS 40
+#define GRID_LIN_RMS 2e-2      // grid integrator (with the same tightening rule): -6..7 % on the C1 lattices, flat
+                               // between 1e-2 and 5e-2, parity metric unchanged (profiles/r02_lin_tol.txt)
 // quads -> 16-ion groups (see stb_system_create): iterations per linear solve over windows of this many steps
 #define CL_RESTART_STEPS 48
-#define CL_RESTART_ITS 5.0
+#define CL_RESTART_ITS 10.0
+#define CL_BATCH_ITS 8.0
+#define CL_RESTART_LAST 480
 #define STB_RESTART_GROUPS 1000     // internal return code of integrate_cluster
 // The Newton convergence rate is carried across steps (LSODA / CVODE `crate`): a step whose first
 // update already satisfies 1.5 * min(1, crate) * ||dy|| < newton_tol is accepted without a second
@@ -64,7 +68,8 @@ struct IntArgs {
     int tma;                  // dense rows fed by bulk copies through a shared-memory ring (stb_tma.cuh)
     int tma_kc, tma_stages;
     int guess;                // Newton starts from the previous step's correction (see CL_OPT_GUESS)
-    double lin_rms;           // GMRES tolerance in units of the error test (STB_LIN_RMS)
+    double lin_rms;           // GMRES tolerance in units of the error test (GRID_LIN_RMS), tightened to
+    int lin_tight_steps;      // STB_LIN_RMS for this many steps after a rejection (as the cluster integrator)
     // group block preconditioner: the sensitizers are stored in compact groups of `grp` ions
     // (grp * s_S = STB_GDIM unknowns) and the block of I - cJ over a whole group is inverted instead
     // of the single-ion blocks (0: off).  NGinv doubles per system hold the inverses.
@@ -918,6 +923,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.steps_since_out = 0;
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
             C.tol_lin = A.lin_rms * sqrtN;
+            C.lin_tight = 0;
             C.crate = 1.0;
             C.since_verify = 0;
             C.gfac = 0.0;
@@ -1182,6 +1188,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 // Newton / Krylov failure: halve the step (scipy: factor 0.5 with current Jacobian)
                 if (threadIdx.x == 0) {
                     C.st.n_newton_fail += 1;
+                    C.lin_tight = A.lin_tight_steps;
+                    C.tol_lin = fmin(A.lin_rms, STB_LIN_RMS) * sqrtN;
                     compute_RU(C.order, 0.5, C.RU);
                     C.h *= 0.5;
                     C.n_equal = 0;
@@ -1216,6 +1224,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                         C.h *= factor;
                         C.n_equal = 0;
                         C.st.n_rejected += 1;
+                        C.lin_tight = A.lin_tight_steps;
+                        C.tol_lin = fmin(A.lin_rms, STB_LIN_RMS) * sqrtN;
                         C.steps_since_out += 1;
                         C.flag = 1;
                         C.gfac *= stb_ipow(factor, order + 1);
@@ -1289,6 +1299,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     C.st.n_steps += 1;
+                    if (C.lin_tight > 0 && --C.lin_tight == 0) C.tol_lin = A.lin_rms * sqrtN;
                     C.steps_since_out += 1;
                     C.n_equal += 1;
                     C.t = t_new;

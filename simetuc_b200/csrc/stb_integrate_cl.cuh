@@ -158,7 +158,8 @@ struct ClArgs {
     double lin_rms;                // GMRES tolerance in units of the error test (CL_LIN_RMS) ...
     int lin_tight_steps;           // ... tightened to STB_LIN_RMS for this many steps after a rejection
     // quads that do not hold the Krylov iterations down: a system that has needed more than restart_its
-    // iterations per linear solve over a window of restart_steps steps stops with status 4 and raises *restart; the
+    // iterations per linear solve over a window of restart_steps steps within the first CL_RESTART_LAST steps
+    // (what a new start may throw away is bounded) stops with status 4 and raises *restart; the
     // host repeats the launch with the 16-ion groups (null: never)
     int* restart;
     int restart_steps;
@@ -176,6 +177,8 @@ struct ClArgs {
     double* work;              // [n_clusters][G][work_stride]: spilled V / D
     int64_t work_stride;
     int* next_sys;             // work counter (dynamic assignment of systems to clusters)
+    const int* sys_list;       // null, or the n_list systems (local indices) this launch solves
+    int n_list;
     long long* prof;           // [64] clock64 cycles per phase (cluster 0, rank 0, thread 0) + counters, per-warp pair-pass cycles and work-list positions; may be null
 };
 
@@ -1021,8 +1024,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             }
         }
         sync_all();
-        const int sysl = S.cur_sys;
-        if (sysl >= A.n_sys) break;
+        if (S.cur_sys >= (A.sys_list ? A.n_list : A.n_sys)) break;
+        const int sysl = A.sys_list ? A.sys_list[S.cur_sys] : S.cur_sys;
         const int sys = A.first + sysl;
         load_sys_params(L, A.blocks, A.strengths, sys, A.pulse, P);
         const double* y0 = A.y0 + (int64_t)sysl * N;
@@ -1524,7 +1527,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
                 }
                 if (lane == 0) {
                     C.st.n_steps += 1;
-                    if (A.restart && C.st.n_steps % A.restart_steps == 0) {
+                    if (A.restart && C.st.n_steps % A.restart_steps == 0 && C.st.n_steps <= CL_RESTART_LAST) {
                         // iterations per linear solve over the last restart_steps steps
                         if ((double)(C.st.n_jv - C.chk_jv) > A.restart_its * (double)(C.st.n_lin - C.chk_lin)) {
                             C.status = 4;

