@@ -990,7 +990,46 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             if (L.s[T] <= 2 || cnt[T] <= 0 || (quadpc && T == 0)) continue;
             gauss_jordan(Minv + Y.moff[T], L.s[T], Y.cntm[T], cnt[T]);
         }
-        if (quadpc && cnt[0] > 0) gauss_jordan(Qinv, Y.sq, Y.nqm, (cnt[0] + L.pcg - 1) / L.pcg);
+        // 32 x 32 group blocks: one warp per block, lane = one column of the stored matrix (consecutive
+        // lanes read consecutive words), eight entries at a time so that the loads of a chunk do not wait
+        // for its stores; no CTA barrier inside (the CTA-wide version above pays 64 of them per block)
+        auto gauss_jordan_warp32 = [&](double* base, int cm, int count) {
+            // view T[r][c] = stored[c][r]: row operations on T invert the stored matrix as well
+            for (int blk = warp; blk < count; blk += STB_NW) {
+                double* Mq = base + blk;
+                for (int p = 0; p < 32; ++p) {
+                    const double piv = Mq[(p * 32 + p) * cm];
+                    const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+                    const double fr = Mq[(p * 32 + lane) * cm];            // T[lane][p]
+                    __syncwarp();
+                    {
+                        double* tp = Mq + (lane * 32 + p) * cm;             // T[p][lane]
+                        *tp = lane == p ? inv : *tp * inv;
+                    }
+                    __syncwarp();
+                    if (lane != p) {
+                        for (int j0 = 0; j0 < 32; j0 += 8) {
+                            double pj[8], ow[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                pj[u] = Mq[((j0 + u) * 32 + p) * cm];       // T[p][j]
+                                ow[u] = Mq[((j0 + u) * 32 + lane) * cm];    // T[lane][j]
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u)
+                                Mq[((j0 + u) * 32 + lane) * cm] = j0 + u == p ? -fr * pj[u] : fma(-fr, pj[u], ow[u]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        };
+        if (quadpc && cnt[0] > 0) {
+            const int nblk = (cnt[0] + L.pcg - 1) / L.pcg;
+            if (Y.sq == 32) gauss_jordan_warp32(Qinv, Y.nqm, nblk);
+            else gauss_jordan(Qinv, Y.sq, Y.nqm, nblk);
+        }
     };
 
     auto apply_change_D = [&](int order) {
