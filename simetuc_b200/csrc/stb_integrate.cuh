@@ -308,7 +308,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         r_hi[0] = min((ch_slot + n_ch) * grp, L.n[0]);
         // (not with the release-only barriers of the staged mode: the rows a neighbour post-processes are
         //  read by plain loads)
-        split = g.G > 1 && !A.staged && L.n[0] / g.G >= 2 * grp;
+        // (with at least grp + 1 rows per CTA the group range of a CTA lies inside the pass ranges of the CTA
+        //  and its two neighbours: group boundaries sit within (-grp, padding + 1] of the pass boundaries)
+        split = g.G > 1 && !A.staged && L.n[0] / g.G >= grp + 1;
         if (!split) {
             pr_lo[0] = r_lo[0];
             pr_hi[0] = r_hi[0];

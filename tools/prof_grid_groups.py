@@ -50,7 +50,7 @@ for name in os.environ.get('CASES', 'c1p,c3b,fix240').split(','):
         system.close()
 
 for n_uc in big:
-    cte = configs.yb_tm_cte(N_uc=n_uc, S_conc=25.0, A_conc=0.3, power_dens=1e7, t_pulse=1e-8, rtol=1e-8, atol=1e-15,
+    cte = configs.yb_tm_cte(N_uc=n_uc, S_conc=float(os.environ.get('SCONC', '25')), A_conc=float(os.environ.get('ACONC', '0.3')), power_dens=float(os.environ.get('POWER', '1e7')), t_pulse=1e-8, rtol=1e-8, atol=1e-15,
                             N_steps=1000)
     ref_avg = None
     for grp in ('0', '1'):
