@@ -1860,6 +1860,11 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
         for (const stb_stats& h : hs) { jv += (double)h.n_jv; lin += (double)h.n_lin; }
         if (jv > CL_BATCH_ITS * lin) {
             S->hL.pcg = 16;
+            ClPlan probe;
+            if (!cl_choose(S, n, probe)) {       // the group blocks do not fit: quads it is, for good
+                S->hL.pcg = 4;
+                S->pcg_auto = false;
+            }
             CKC(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
         }
     }
@@ -1965,8 +1970,17 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
             const bool all = (int)again.size() == n;
             S->hL.pcg = 16;
             CK(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
-            if (!cl_choose(S, (int)again.size(), plan))
-                return fail(STB_ESTATE, "no cluster plan for the 16-ion groups");
+            if (!cl_choose(S, (int)again.size(), plan)) {
+                // the group blocks do not fit next to this lattice's rows: quads it is, for good
+                S->hL.pcg = 4;
+                S->pcg_auto = false;
+                CK(copy_on(S->stream, S->dL, &S->hL, sizeof(DevLattice), cudaMemcpyHostToDevice));
+                if (!cl_choose(S, n, plan)) return fail(STB_ESTATE, "no cluster plan");
+                rc = integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
+                                       avg_out, stats, dev);
+                S->last_ms += ms_quads;
+                return rc;
+            }
             rc = integrate_cluster(S, plan, first, n, pulse, n_t, t, y0, rtol, atol, nsteps, y_out,
                                    avg_out, stats, dev, all ? nullptr : &again);
             if (!all) {

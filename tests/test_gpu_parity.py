@@ -630,6 +630,25 @@ def test_cluster_switches_to_groups_when_quads_struggle(monkeypatch):
     ref = gold['y_rows']
     assert np.all(np.abs(y[0][gold['rows']] - ref) <= 1e-4 * np.abs(ref) + 1e-12)
     system.close()
+    # a batch is never stopped: it finishes with quads and the handle uses the groups from the next launch on
+    cte = configs.sim_cte()
+    system = make_system(g, cte)
+    system.set_batch(2)
+    system.set_decay_blocks(*precalculate.decay_blocks(cte))
+    system.set_abs_blocks(*precalculate.absorption_blocks(cte))
+    y0 = np.tile(pop.astype(float), (2, 1))
+    t_short = t_sol
+    for launch in range(2):
+        assert system.get_option('pc_group') == (4 if launch == 0 else 16)
+        _, y, _, _, st = system.integrate_dynamics(np.linspace(0.0, t_sol[0], 2), t_short, y0, rtol=1e-8,
+                                                   atol=1e-15, nsteps=100000, want_y=True)
+        assert all(x['status'] == 0 for x in st)
+        rows = gold['rows'][gold['rows'] < len(t_short)]
+        ref = gold['y_rows'][:len(rows)]
+        for k in range(2):
+            assert np.all(np.abs(y[k][rows] - ref) <= 1e-4 * np.abs(ref) + 1e-12)
+    assert system.get_option('pc_group') == 16
+    system.close()
     cte = configs.yb_tm_cte(N_uc=8, S_conc=5.0, A_conc=0.5, power_dens=1e7, t_pulse=1e-8)
     system = precalculate.build_system(cte, lattice.generate(cte, seed=5), n_sys=1)
     _, _, pop = system.ground_states()
