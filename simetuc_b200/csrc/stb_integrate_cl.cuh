@@ -410,6 +410,44 @@ struct ClShared {
 
 // COOP: the instance for systems with a cooperative (three-ion) process; the plain instance
 // carries none of that code (it costs registers: +5 % on the C2 sweep when compiled in).
+// In-place inversion of 32 x 32 blocks stored [entry][block] (block stride 1, entry stride cm): one warp per
+// block, lane = one column of the stored matrix (consecutive lanes read consecutive words), eight entries at
+// a time so that the loads of a chunk do not wait for its stores; no CTA barrier inside (a CTA-wide
+// Gauss-Jordan pays 64 of them per block).  Out of line: the cluster kernel is instruction-cache bound and
+// this runs once per preconditioner refresh.  View T[r][c] = stored[c][r]: row operations on T invert the
+// stored matrix as well.  All threads of the CTA call it; ends with a CTA barrier.
+__device__ __noinline__ void cl_gauss_jordan_warp32(double* base, int cm, int count, int warp, int lane) {
+    for (int blk = warp; blk < count; blk += STB_NW) {
+        double* Mq = base + blk;
+        for (int p = 0; p < 32; ++p) {
+            const double piv = Mq[(p * 32 + p) * cm];
+            const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
+            const double fr = Mq[(p * 32 + lane) * cm];            // T[lane][p]
+            __syncwarp();
+            {
+                double* tp = Mq + (lane * 32 + p) * cm;             // T[p][lane]
+                *tp = lane == p ? inv : *tp * inv;
+            }
+            __syncwarp();
+            if (lane != p) {
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                    double pj[8], ow[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        pj[u] = Mq[((j0 + u) * 32 + p) * cm];       // T[p][j]
+                        ow[u] = Mq[((j0 + u) * 32 + lane) * cm];    // T[lane][j]
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        Mq[((j0 + u) * 32 + lane) * cm] = j0 + u == p ? -fr * pj[u] : fma(-fr, pj[u], ow[u]);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+}
+
 template <bool COOP>
 __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     STB_DYN_SMEM(dyn);
@@ -514,6 +552,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
     // (needs the operator in the form Minv (M v - c k(v)), i.e. the lagged mode)
     const bool quadpc = L.quad && lagpc && (A.opts & CL_OPT_QUAD) != 0 && A.procs != nullptr;
     double* Qinv = dyn + Y.qinv;
+    const int pg_sh = L.pcg == 16 ? 4 : 2;      // log2 of the ions per preconditioner group
     double* F = dyn + Y.F;
     double* Pp = dyn + Y.Pp;
     double* part = dyn + Y.part;
@@ -821,8 +860,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
         if (quadpc && T == 0) {
             // row (i % pcg) * s + a of the inverse of the group's block; the blocks are stored TRANSPOSED
             // ([column][row][group]): the threads of a warp own different rows and read consecutive words
-            const int pg = L.pcg, Q = i / pg, sq = Y.sq;
-            const double* Bp = Qinv + ((i - Q * pg) * s + a) * Y.nqm + Q;
+            const int pg = L.pcg, Q = i >> pg_sh, sq = Y.sq;
+            const double* Bp = Qinv + ((i & (pg - 1)) * s + a) * Y.nqm + Q;
             const double* rq = r + ob[0] + pg * Q;
             double acc = 0.0;
             for (int m = 0; m < pg; ++m) {
@@ -990,44 +1029,9 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate_cl_t(ClArgs A) {
             if (L.s[T] <= 2 || cnt[T] <= 0 || (quadpc && T == 0)) continue;
             gauss_jordan(Minv + Y.moff[T], L.s[T], Y.cntm[T], cnt[T]);
         }
-        // 32 x 32 group blocks: one warp per block, lane = one column of the stored matrix (consecutive
-        // lanes read consecutive words), eight entries at a time so that the loads of a chunk do not wait
-        // for its stores; no CTA barrier inside (the CTA-wide version above pays 64 of them per block)
-        auto gauss_jordan_warp32 = [&](double* base, int cm, int count) {
-            // view T[r][c] = stored[c][r]: row operations on T invert the stored matrix as well
-            for (int blk = warp; blk < count; blk += STB_NW) {
-                double* Mq = base + blk;
-                for (int p = 0; p < 32; ++p) {
-                    const double piv = Mq[(p * 32 + p) * cm];
-                    const double inv = piv != 0.0 ? 1.0 / piv : 0.0;
-                    const double fr = Mq[(p * 32 + lane) * cm];            // T[lane][p]
-                    __syncwarp();
-                    {
-                        double* tp = Mq + (lane * 32 + p) * cm;             // T[p][lane]
-                        *tp = lane == p ? inv : *tp * inv;
-                    }
-                    __syncwarp();
-                    if (lane != p) {
-                        for (int j0 = 0; j0 < 32; j0 += 8) {
-                            double pj[8], ow[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                pj[u] = Mq[((j0 + u) * 32 + p) * cm];       // T[p][j]
-                                ow[u] = Mq[((j0 + u) * 32 + lane) * cm];    // T[lane][j]
-                            }
-#pragma unroll
-                            for (int u = 0; u < 8; ++u)
-                                Mq[((j0 + u) * 32 + lane) * cm] = j0 + u == p ? -fr * pj[u] : fma(-fr, pj[u], ow[u]);
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        };
         if (quadpc && cnt[0] > 0) {
             const int nblk = (cnt[0] + L.pcg - 1) / L.pcg;
-            if (Y.sq == 32) gauss_jordan_warp32(Qinv, Y.nqm, nblk);
+            if (Y.sq == 32) cl_gauss_jordan_warp32(Qinv, Y.nqm, nblk, warp, lane);
             else gauss_jordan(Qinv, Y.sq, Y.nqm, nblk);
         }
     };
