@@ -152,8 +152,13 @@ int stb_from_planes(const stb_system* sys, int32_t n, const double* y_planes_dev
 
 /* ---- stiff integrator ------------------------------------------------------------------------
  * Replaces odesolver._solve_ode / solve_pulse / solve_relax (odesolver.py:85-209) and scipy's
- * VODE/LSODA: variable-order (1-5) BDF, Jacobian-free Newton-Krylov (GMRES) with a per-ion
- * block-Jacobi preconditioner, entirely on the device.
+ * VODE/LSODA: variable-order (1-5) BDF, Jacobian-free Newton-Krylov (GMRES) with block-Jacobi
+ * preconditioners (per ion; over quads or groups of 16 strongly coupled sensitizers), entirely on the
+ * device.  Which integrator (one thread-block cluster per system / the persistent grid) and which blocks
+ * are used is the library's choice per call (INTEGRATION.md lists the switches); the cluster integrator may
+ * abandon a launch whose quads leave too many Krylov iterations and solve it again with the groups - the
+ * caller sees one result, the statistics of the launch that produced it, and a device time that includes
+ * the abandoned work.
  *   t        double[n_t]           output times, t[0] = start (shared by the batch)
  *   y0       double[n, N]          initial populations (reference layout)
  *   y_out    double[n, n_t, N]     row 0 = y0 verbatim (odesolver.py:107); may be NULL
