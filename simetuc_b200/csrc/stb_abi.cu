@@ -2116,6 +2116,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.tma = tma; A.tma_kc = tma ? tma_args.tma_kc : 0; A.tma_stages = tma ? tma_args.tma_stages : 0;
     A.guess = 1;
     A.grp = grp; A.NGinv = NGinv; A.procs = S->d_procs;
+    A.lag = 1;
+    if (const char* env = getenv("STB_GRID_LAG")) A.lag = atoi(env) != 0;
     A.lin_rms = GRID_LIN_RMS;
     A.lin_tight_steps = CL_LIN_TIGHT_STEPS;
     if (const char* env = getenv("STB_LIN_RMS_GRID")) A.lin_rms = std::max(1e-6, atof(env));

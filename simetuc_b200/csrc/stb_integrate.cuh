@@ -75,7 +75,10 @@ struct IntArgs {
     // of the single-ion blocks (0: off).  NGinv doubles per system hold the inverses.
     int grp, NGinv;
     const stb_process* procs;
+    int lag;                  // keep the inverses of the group blocks across steps (STB_PC_MAXAGE, STB_PC_DRIFT)
 };
+#define STB_PC_MAXAGE 20
+#define STB_PC_DRIFT 0.3
 #define STB_GDIM 32           // unknowns of a group block: one warp applies it, lane = row
 
 __device__ __forceinline__ double stb_ipow(double x, int n) {
@@ -695,8 +698,35 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
         };
+        // lagged blocks (CVODE's rule, as the cluster integrator): between refreshes the stored inverses
+        // of an earlier step precondition the residual - B~^-1 (M v - c k(v)) stays exact in M and k
+        auto group_blocks_stored = [&]() {
+            __syncthreads();
+            const int s0 = L.s[0], n0 = L.n[0], GD = STB_GDIM;
+            for (int gq = warp; gq < n_ch; gq += STB_NW) {
+                int row0, mg;
+                chunk_rows(gq, row0, mg);
+                const int m = lane / s0, a = lane - m * s0, iq = row0 + m;
+                const bool ok = m < mg;
+                const int e = L.off[0] + a * n0 + (ok ? iq : n0 - 1);
+                const double r = ok ? gv[e] : 0.0;
+                const double* Gp = Ginv + (int64_t)(ch_slot + gq) * GD * GD + lane;
+                double acc = 0.0;
+#pragma unroll 8
+                for (int col = 0; col < GD; ++col)
+                    acc = fma(Gp[col * GD], __shfl_sync(FULL, r, col), acc);
+                if (ok) {
+                    const double x = acc / scale[e];
+                    wv[e] = x;
+                    gv[e] = acc;
+                    part[0] = fma(x, x, part[0]);
+                }
+            }
+            __syncthreads();
+        };
         auto group_blocks = [&]() {
-            if (A.tma) group_blocks_warp();
+            if (!C.pc_refresh) group_blocks_stored();
+            else if (A.tma) group_blocks_warp();
             else group_blocks_cta();
         };
         if (A.tma) {
@@ -926,6 +956,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             C.newton_tol = fmax(10.0 * 2.220446049250313e-16 / rtol, fmin(0.03, sqrt(rtol)));
             C.tol_lin = A.lin_rms * sqrtN;
             C.lin_tight = 0;
+            C.pc_age = -1;
+            C.pc_refresh = 1;
             C.crate = 1.0;
             C.since_verify = 0;
             C.gfac = 0.0;
@@ -1044,6 +1076,13 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
             __syncthreads();
             while (true) {       // flag: 0 iterate, 1 converged, 2 failed
                 PROF(7)
+                if (threadIdx.x == 0) {
+                    // refresh the group blocks when c = h / alpha has drifted by 30 %, after STB_PC_MAXAGE
+                    // steps, or after a failed Newton iteration (identical decision in every CTA)
+                    C.pc_refresh = !A.lag || C.pc_age < 0 || C.pc_age >= STB_PC_MAXAGE ||
+                                   fabs(c / C.pc_c - 1.0) > STB_PC_DRIFT;
+                    if (C.pc_refresh) { C.pc_c = c; C.pc_age = 0; }
+                }
                 group_sync(g);   // yk complete in the whole group
                 PROF(3)
                 rhs_phase(yk, f, 1, c, part);
@@ -1190,6 +1229,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 // Newton / Krylov failure: halve the step (scipy: factor 0.5 with current Jacobian)
                 if (threadIdx.x == 0) {
                     C.st.n_newton_fail += 1;
+                    C.pc_age = -1;
                     C.lin_tight = A.lin_tight_steps;
                     C.tol_lin = fmin(A.lin_rms, STB_LIN_RMS) * sqrtN;
                     compute_RU(C.order, 0.5, C.RU);
@@ -1301,6 +1341,7 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     C.st.n_steps += 1;
+                    if (C.pc_age >= 0) C.pc_age += 1;
                     if (C.lin_tight > 0 && --C.lin_tight == 0) C.tol_lin = A.lin_rms * sqrtN;
                     C.steps_since_out += 1;
                     C.n_equal += 1;
