@@ -2117,6 +2117,8 @@ static int integrate_core(stb_system* S, int32_t first, int32_t n, int32_t pulse
     A.guess = 1;
     A.grp = grp; A.NGinv = NGinv; A.procs = S->d_procs;
     A.lag = 1;
+    A.a_ctas = 1;
+    if (const char* env = getenv("STB_A_CTAS")) A.a_ctas = atoi(env) != 0;
     if (const char* env = getenv("STB_GRID_LAG")) A.lag = atoi(env) != 0;
     A.lin_rms = GRID_LIN_RMS;
     A.lin_tight_steps = CL_LIN_TIGHT_STEPS;

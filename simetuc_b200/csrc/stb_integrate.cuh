@@ -76,6 +76,7 @@ struct IntArgs {
     int grp, NGinv;
     const stb_process* procs;
     int lag;                  // keep the inverses of the group blocks across steps (STB_PC_MAXAGE, STB_PC_DRIFT)
+    int a_ctas;               // TMA passes: activator rows on CTAs of their own
 };
 #define STB_PC_MAXAGE 20
 #define STB_PC_DRIFT 0.3
@@ -293,6 +294,35 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         r_lo[T] = min(sl_lo[T] * L.R, L.n[T]);
         r_hi[T] = min(sl_hi[T] * L.R, L.n[T]);
     }
+    // TMA passes: the few activator rows go to CTAs of their own.  Dealt over all CTAs (35 activators on 148
+    // CTAs at N_uc 20) they give a quarter of the CTAs one more row tile - a tile of one row costs a whole sweep
+    // over the partner columns - and every pass waits for those: the arrival skew at the group barriers was one
+    // tile time.  So, while a CTA has at most four tiles of sensitizer rows, nA CTAs take one tile of activator
+    // rows each and no sensitizer row (N_uc 20: 207 -> 197 ms).  Beyond that the extra one-row tile is a small
+    // part of a pass and an activator row costs several sensitizer rows (more field slots): dedicated CTAs
+    // become the slowest ones (N_uc 30 with one CTA for all 73 activators: 624 -> 938 ms), so the rows stay dealt.
+    int cS = g.cta, GS = g.G;            // this CTA's index among the CTAs that own sensitizer rows, their number
+    const int nA_want = (L.n[1] + STB_TMA_ROWS - 1) / STB_TMA_ROWS;
+    if (A.tma && A.a_ctas && L.n[0] > 0 && L.n[1] > 0 && 2 * nA_want <= g.G &&
+        (L.n[0] + g.G * STB_TMA_ROWS - 1) / (g.G * STB_TMA_ROWS) <= 4) {
+        const int nA = nA_want;
+        GS = g.G - nA;
+        if (g.cta < nA) {
+            cS = -1;
+            r_lo[1] = (int)(((int64_t)L.n[1] * g.cta) / nA);
+            r_hi[1] = (int)(((int64_t)L.n[1] * (g.cta + 1)) / nA);
+            r_lo[0] = r_hi[0] = 0;
+        } else {
+            cS = g.cta - nA;
+            r_lo[0] = (int)(((int64_t)L.n[0] * cS) / GS);
+            r_hi[0] = (int)(((int64_t)L.n[0] * (cS + 1)) / GS);
+            r_lo[1] = r_hi[1] = L.n[1];
+        }
+        for (int T = 0; T < 2; ++T) {       // (TMA passes: one row per slice)
+            sl_lo[T] = r_lo[T] / L.R;
+            sl_hi[T] = (r_hi[T] + L.R - 1) / L.R;
+        }
+    }
     // group preconditioner: a CTA owns - as vectors: Krylov basis, dot products, preconditioner - whole
     // groups of sensitizers (type-local rows grp*m .. grp*m + grp-1, see group_sensitizers: what counts is
     // that no strongly coupled pair is cut by a group boundary).  The PAIR PASS keeps the split balanced to
@@ -303,23 +333,26 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
     int n_ch = 0, ch_slot = 0;
     int pr_lo[2] = {r_lo[0], r_lo[1]}, pr_hi[2] = {r_hi[0], r_hi[1]};
     bool split = false;
-    if (grp) {
+    if (grp && cS >= 0) {
         const int ng = (L.n[0] + grp - 1) / grp;
-        ch_slot = (int)(((int64_t)ng * g.cta) / g.G);
-        n_ch = (int)(((int64_t)ng * (g.cta + 1)) / g.G) - ch_slot;
+        ch_slot = (int)(((int64_t)ng * cS) / GS);
+        n_ch = (int)(((int64_t)ng * (cS + 1)) / GS) - ch_slot;
         r_lo[0] = min(ch_slot * grp, L.n[0]);
         r_hi[0] = min((ch_slot + n_ch) * grp, L.n[0]);
         // (not with the release-only barriers of the staged mode: the rows a neighbour post-processes are
         //  read by plain loads)
         // (with at least grp + 1 rows per CTA the group range of a CTA lies inside the pass ranges of the CTA
         //  and its two neighbours: group boundaries sit within (-grp, padding + 1] of the pass boundaries)
-        split = g.G > 1 && !A.staged && L.n[0] / g.G >= grp + 1;
+        split = GS > 1 && !A.staged && L.n[0] / GS >= grp + 1;
         if (!split) {
             pr_lo[0] = r_lo[0];
             pr_hi[0] = r_hi[0];
             sl_lo[0] = r_lo[0] / L.R;
             sl_hi[0] = (r_hi[0] + L.R - 1) / L.R;
         }
+    } else if (grp) {
+        // (a CTA of activator rows: it takes part in the hand-over rounds of the others, without waiting)
+        split = GS > 1 && !A.staged && L.n[0] / GS >= grp + 1;
     }
     // the CTA's pass rows are written: wait until the two neighbours have written theirs (same flavour as
     // group_sync: the fences make the neighbours' rows visible to plain loads)
@@ -331,8 +364,8 @@ __global__ void __launch_bounds__(STB_NT, 1) k_integrate(IntArgs A) {
         if (threadIdx.x == 0) {
             __threadfence();
             asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(nb_flags + g.cta), "l"(nb_epoch) : "memory");
-            if (g.cta > 0) while (ld_acquire_u64(nb_flags + g.cta - 1) < nb_epoch) { }
-            if (g.cta + 1 < g.G) while (ld_acquire_u64(nb_flags + g.cta + 1) < nb_epoch) { }
+            if (cS > 0) while (ld_acquire_u64(nb_flags + g.cta - 1) < nb_epoch) { }
+            if (cS >= 0 && cS + 1 < GS) while (ld_acquire_u64(nb_flags + g.cta + 1) < nb_epoch) { }
             __threadfence();
         }
         __syncthreads();
