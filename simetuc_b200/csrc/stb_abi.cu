@@ -880,7 +880,7 @@ extern "C" stb_system* stb_system_create(int32_t device, int64_t n_ions, const u
     // starts with quads.  A single system that needs more than CL_RESTART_ITS iterations per solve over a
     // window of CL_RESTART_STEPS steps (within its first CL_RESTART_LAST steps) is stopped and solved again -
     // and the handle continues - with groups; a batch is never stopped, but switches for its next launches
-    // when its systems averaged more than CL_BATCH_ITS (integrate_cluster).  STB_PCG=4 / 16 fixes the choice.
+    // when most of its systems needed more than CL_BATCH_ITS (integrate_cluster).  STB_PCG=4 / 16 fixes the choice.
     L.grp16 = quad && S->n[0] > 4;
     if (const char* env = getenv("STB_GROUP16")) if (atoi(env) == 0) L.grp16 = 0;
     S->can16 = L.grp16 && 16 * S->s[0] <= 32;
@@ -1779,8 +1779,8 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     A.sys_list = d_list;
     A.n_list = list ? (int)list->size() : 0;
     // (a single system: stopped and solved again as soon as it shows; a batch: never stopped - one stiff
-    //  candidate of a parameter scan must not cost the others their launch - but if its systems needed
-    //  more than CL_BATCH_ITS iterations per solve on average, the handle uses the groups from the next
+    //  candidate of a parameter scan must not cost the others their launch - but if most of its systems
+    //  needed more than CL_BATCH_ITS iterations per solve, the handle uses the groups from the next
     //  launch on)
     const bool may_switch = !list && L.quad && L.pcg == 4 && S->can16 && S->pcg_auto;
     const bool may_restart = may_switch && n == 1;
@@ -1856,9 +1856,11 @@ static int integrate_cluster(stb_system* S, const ClPlan& plan, int32_t first, i
     } else if (may_switch && !pulse) {
         std::vector<stb_stats> hs(n);
         CKC(copy_on(S->stream, hs.data(), d_stats, sizeof(stb_stats) * n, cudaMemcpyDeviceToHost));
-        double jv = 0.0, lin = 0.0;
-        for (const stb_stats& h : hs) { jv += (double)h.n_jv; lin += (double)h.n_lin; }
-        if (jv > CL_BATCH_ITS * lin) {
+        // (the majority of the systems, not their mean: a few stiff candidates of a parameter scan do not make
+        //  the groups pay for the others - C5: 184 -> 106 solves/s when its 8-candidate warm-up switched)
+        int stiff = 0;
+        for (const stb_stats& h : hs) stiff += (double)h.n_jv > CL_BATCH_ITS * (double)h.n_lin;
+        if (2 * stiff > n) {
             S->hL.pcg = 16;
             ClPlan probe;
             if (!cl_choose(S, n, probe)) {       // the group blocks do not fit: quads it is, for good
