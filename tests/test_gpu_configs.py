@@ -39,6 +39,11 @@ def _integrators(monkeypatch, which):
     """Select the integrator through the library's environment switches."""
     if which == 'grid':
         monkeypatch.setenv('STB_CLUSTER', '0')
+    elif which == 'grid-tma':
+        # the grid integrator as the large lattices run it: TMA-fed passes, group blocks with the balanced
+        # pair pass and the neighbour hand-over, activator rows on their own CTAs, lagged inverses
+        monkeypatch.setenv('STB_CLUSTER', '0')
+        monkeypatch.setenv('STB_TMA', '1')
     else:
         monkeypatch.delenv('STB_CLUSTER', raising=False)
 
@@ -82,7 +87,7 @@ def _ybtm_system(gold):
     return precalculate.build_system(cte, lat, n_sys=1)
 
 
-@pytest.mark.parametrize('which', ['cluster', 'grid'])
+@pytest.mark.parametrize('which', ['cluster', 'grid', 'grid-tma'])
 def test_c1_parity_scale(monkeypatch, which):
     """C1 (config_file.cfg shape: 25 % Yb, 0.3 % Tm, 980 nm pulse) at the survey's parity scale
     N_uc = 12 (~1370 states): pulse + 1000-point relaxation."""
@@ -93,7 +98,7 @@ def test_c1_parity_scale(monkeypatch, which):
     system.close()
 
 
-@pytest.mark.parametrize('which', ['cluster', 'grid'])
+@pytest.mark.parametrize('which', ['cluster', 'grid', 'grid-tma'])
 @pytest.mark.parametrize('case', ['c3a', 'c3b'])
 def test_c3_grid_corners(monkeypatch, which, case):
     """Two corners of the C3 concentration grid (10 % / 0.1 % and 50 % / 2 %), dynamics."""
